@@ -1,0 +1,128 @@
+"""Frozen per-environment constants, transcribed from the reference.
+
+Sources (all under /root/reference/pybulletgym/envs/):
+  ids, max_episode_steps, reward_threshold     __init__.py:4-103
+  robot ctor arguments, power, foot lists      roboschool/robot_locomotors.py:82-302, robot_pendula.py:5-51
+  per-joint power_coef                         roboschool/robot_bases.py:89, robot_locomotors.py:103-127,152-164
+  scene parameters                             roboschool/gym_locomotion_envs.py:18-20, gym_pendulum_envs.py:13-14,
+                                               scene_bases.py:60-73, scene_stadium.py:13-14,33
+  reward coefficients                          roboschool/gym_locomotion_envs.py:48-52,150-151
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+KIND_PENDULUM, KIND_PENDULUM_SWINGUP, KIND_HOPPER, KIND_WALKER2D, KIND_HALFCHEETAH, KIND_ANT, KIND_HUMANOID, \
+    KIND_FLAGRUN, KIND_FLAGRUN_HARDER = range(9)
+
+
+@dataclass(frozen=True)
+class SceneSpec:
+    """World.clean_everything parameters (scene_bases.py:60-73) and the stadium ground (scene_stadium.py:33).
+
+    The [EXT] block holds the pybullet/Bullet solver defaults the reference never overrides
+    (SURVEY.md Appendix C4); they are restated from upstream Bullet and are part of the pin list.
+    """
+    gravity: float = 9.8
+    timestep: float = 0.0165 / 4
+    frame_skip: int = 4
+    num_solver_iterations: int = 5
+    contact_erp: float = 0.9            # setDefaultContactERP(0.9) -> solverInfo.m_erp2
+    ground_friction: float = 0.8
+    ground_restitution: float = 0.5     # combined with link restitution 0 -> 0
+    stadium_halflen: float = 105 * 0.25
+    stadium_halfwidth: float = 50 * 0.25
+    # [EXT]
+    erp: float = 0.2                    # solverInfo.m_erp, used by joint-limit rows
+    linear_slop: float = 1e-5
+    warmstarting_factor: float = 0.1
+    max_coordinate_velocity: float = 100.0
+    limit_max_impulse: float = 100.0
+    limit_split_impulse: bool = False   # see DESIGN.md "limit rows"
+    split_impulse_threshold: float = -0.04
+
+    @property
+    def dt(self) -> float:
+        return self.timestep * self.frame_skip
+
+
+@dataclass(frozen=True)
+class EnvSpec:
+    id: str
+    kind: int
+    xml: str
+    robot_name: str
+    action_dim: int
+    obs_dim: int
+    power: float
+    power_coef: Dict[str, float] = field(default_factory=dict)   # overrides of the default 100.0
+    foot_list: Tuple[str, ...] = ()
+    initial_z: Optional[float] = None        # None: latch torso z at the first calc_state after reset
+    electricity_cost: float = -2.0
+    stall_torque_cost: float = -0.1
+    joints_at_limit_cost: float = -0.1
+    scene: SceneSpec = SceneSpec()
+    max_episode_steps: int = 1000
+    reward_threshold: Optional[float] = None
+    walk_target: Tuple[float, float] = (1e3, 0.0)
+    entry_point: str = ""
+
+    def torque_scale(self, ordered_joint_names: List[str]) -> List[float]:
+        """tau_max per ordered joint = power * power_coef (robot_locomotors.py:29,189)."""
+        if self.kind in (KIND_PENDULUM, KIND_PENDULUM_SWINGUP):
+            # robot_pendula.py:25: only the slider is driven, 100 * clip(a)
+            return [100.0 if n == "slider" else 0.0 for n in ordered_joint_names]
+        return [self.power * self.power_coef.get(n, 100.0) for n in ordered_joint_names]
+
+
+_PENDULUM_SCENE = SceneSpec(timestep=0.0165, frame_skip=1)
+_HUMANOID_POWER = {
+    "abdomen_z": 100, "abdomen_y": 100, "abdomen_x": 100,
+    "right_hip_x": 100, "right_hip_z": 100, "right_hip_y": 300, "right_knee": 200,
+    "left_hip_x": 100, "left_hip_z": 100, "left_hip_y": 300, "left_knee": 200,
+    "right_shoulder1": 75, "right_shoulder2": 75, "right_elbow": 75,
+    "left_shoulder1": 75, "left_shoulder2": 75, "left_elbow": 75,
+}
+_RS = "pybulletgym.envs.roboschool."
+
+SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
+    EnvSpec("InvertedPendulumPyBulletEnv-v0", KIND_PENDULUM, "inverted_pendulum.xml", "cart", 1, 5, 1.0,
+            scene=_PENDULUM_SCENE, reward_threshold=950.0,
+            entry_point=_RS + "gym_pendulum_envs:InvertedPendulumBulletEnv"),
+    EnvSpec("InvertedPendulumSwingupPyBulletEnv-v0", KIND_PENDULUM_SWINGUP, "inverted_pendulum.xml", "cart", 1, 5,
+            1.0, scene=_PENDULUM_SCENE, reward_threshold=800.0,
+            entry_point=_RS + "gym_pendulum_envs:InvertedPendulumSwingupBulletEnv"),
+    EnvSpec("HopperPyBulletEnv-v0", KIND_HOPPER, "hopper.xml", "torso", 3, 15, 0.75, foot_list=("foot",),
+            reward_threshold=2500.0, entry_point=_RS + "gym_locomotion_envs:HopperBulletEnv"),
+    EnvSpec("Walker2DPyBulletEnv-v0", KIND_WALKER2D, "walker2d.xml", "torso", 6, 22, 0.40,
+            power_coef={"foot_joint": 30.0, "foot_left_joint": 30.0}, foot_list=("foot", "foot_left"),
+            reward_threshold=2500.0, entry_point=_RS + "gym_locomotion_envs:Walker2DBulletEnv"),
+    EnvSpec("HalfCheetahPyBulletEnv-v0", KIND_HALFCHEETAH, "half_cheetah.xml", "torso", 6, 26, 0.90,
+            power_coef={"bthigh": 120.0, "bshin": 90.0, "bfoot": 60.0, "fthigh": 140.0, "fshin": 60.0, "ffoot": 30.0},
+            foot_list=("ffoot", "fshin", "fthigh", "bfoot", "bshin", "bthigh"), reward_threshold=3000.0,
+            entry_point=_RS + "gym_locomotion_envs:HalfCheetahBulletEnv"),
+    EnvSpec("AntPyBulletEnv-v0", KIND_ANT, "ant.xml", "torso", 8, 28, 2.5,
+            foot_list=("front_left_foot", "front_right_foot", "left_back_foot", "right_back_foot"),
+            reward_threshold=2500.0, entry_point=_RS + "gym_locomotion_envs:AntBulletEnv"),
+    EnvSpec("HumanoidPyBulletEnv-v0", KIND_HUMANOID, "humanoid_symmetric.xml", "torso", 17, 44, 0.41,
+            power_coef=_HUMANOID_POWER, foot_list=("right_foot", "left_foot"), initial_z=0.8,
+            electricity_cost=4.25 * -2.0, stall_torque_cost=4.25 * -0.1,
+            entry_point=_RS + "gym_locomotion_envs:HumanoidBulletEnv"),
+    EnvSpec("HumanoidFlagrunPyBulletEnv-v0", KIND_FLAGRUN, "humanoid_symmetric.xml", "torso", 17, 44, 0.41,
+            power_coef=_HUMANOID_POWER, foot_list=("right_foot", "left_foot"), initial_z=0.8,
+            electricity_cost=4.25 * -2.0, stall_torque_cost=4.25 * -0.1, reward_threshold=2000.0,
+            entry_point=_RS + "gym_locomotion_envs:HumanoidFlagrunBulletEnv"),
+    EnvSpec("HumanoidFlagrunHarderPyBulletEnv-v0", KIND_FLAGRUN_HARDER, "humanoid_symmetric.xml", "torso", 17, 44,
+            0.41, power_coef=_HUMANOID_POWER, foot_list=("right_foot", "left_foot"), initial_z=0.8,
+            electricity_cost=4.25 * -2.0, stall_torque_cost=4.25 * -0.1,   # quirk Q6: the `/= 4` is dead
+            entry_point=_RS + "gym_locomotion_envs:HumanoidFlagrunHarderBulletEnv"),
+]}
+
+# ids the reference registers (envs/__init__.py) that this backend does not implement
+UNBACKED_IDS = (
+    "InvertedDoublePendulumPyBulletEnv-v0", "ReacherPyBulletEnv-v0", "PusherPyBulletEnv-v0",
+    "ThrowerPyBulletEnv-v0", "StrikerPyBulletEnv-v0", "AtlasPyBulletEnv-v0",
+    "InvertedPendulumMuJoCoEnv-v0", "InvertedDoublePendulumMuJoCoEnv-v0", "Walker2DMuJoCoEnv-v0",
+    "HalfCheetahMuJoCoEnv-v0", "AntMuJoCoEnv-v0", "HopperMuJoCoEnv-v0", "HumanoidMuJoCoEnv-v0",
+)
