@@ -1,0 +1,179 @@
+/*
+ * pbg.h -- C ABI of libpbg_b200.so, the B200-native batched physics backend.
+ *
+ * This is the drop-in boundary of the hot path.  In the reference the path sits behind ~30
+ * pybullet client calls made from Python once per joint / link / foot and env step
+ * (/root/reference/pybulletgym/envs/roboschool/, "rs/" below).  Here one call
+ * steps a whole batch of environments on one GPU.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - return 0 on success, a negative pbg_status otherwise; pbg_last_error() gives the message;
+ *     nothing throws across the ABI.
+ *   - all *_dev pointers are device pointers on the handle's device, row-major [num_envs, dim],
+ *     fp32 (done: uint8).  The caller owns every I/O buffer; the library owns its internal state.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are asynchronous and
+ *     ordered by the stream, except the *_host entry points, which synchronise before returning.
+ *   - a handle is bound to one device and is not thread-safe.  Multi-GPU = one handle per device.
+ */
+#ifndef PBG_H
+#define PBG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBG_VERSION 100
+
+typedef enum {
+    PBG_OK = 0,
+    PBG_ERR_INVALID = -1,      /* bad argument / model does not fit the compiled kernel configuration */
+    PBG_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+    PBG_ERR_UNSUPPORTED = -3   /* env kind without a kernel */
+} pbg_status;
+
+/* env kinds: one per reference robot/env class pair (rs/gym_locomotion_envs.py:122-173,
+ * rs/gym_pendulum_envs.py:7-49) */
+enum {
+    PBG_KIND_PENDULUM = 0, PBG_KIND_PENDULUM_SWINGUP = 1, PBG_KIND_HOPPER = 2, PBG_KIND_WALKER2D = 3,
+    PBG_KIND_HALFCHEETAH = 4, PBG_KIND_ANT = 5, PBG_KIND_HUMANOID = 6, PBG_KIND_FLAGRUN = 7,
+    PBG_KIND_FLAGRUN_HARDER = 8
+};
+
+enum { PBG_JT_FIXED = 0, PBG_JT_REVOLUTE = 1, PBG_JT_PRISMATIC = 2, PBG_JT_FREE = 3 };
+enum { PBG_G_SPHERE = 0, PBG_G_CAPSULE = 1, PBG_G_BOX = 2 };
+
+/*
+ * Flat articulation tables produced by the host-side MJCF compiler
+ * (pybullet_gym_b200/mjcf/compiler.py: ReducedModel).  Replaces what the reference obtains from
+ * loadMJCF + getNumJoints/getJointInfo/getBodyInfo (rs/robot_bases.py:54-89,116) and the scene
+ * parameters it sets through setGravity / setDefaultContactERP / setPhysicsEngineParameter /
+ * changeDynamics (rs/scene_bases.py:70-73, rs/scene_stadium.py:33).
+ * All arrays are copied by pbg_create; the caller may free them afterwards.
+ */
+typedef struct pbg_model {
+    /* reduced dynamics tree, bodies in depth-first order */
+    int32_t nb, nj, floating;
+    const int32_t *parent;        /* [nb] */
+    const int32_t *jtype;         /* [nb] PBG_JT_* of the joint connecting the body to its parent */
+    const double *q0;             /* [nb*4] parent frame -> body frame at q = 0, (x,y,z,w) */
+    const double *anchor_p;       /* [nb*3] joint anchor in the parent frame, from the parent COM (root: world pose) */
+    const double *com_off;        /* [nb*3] body COM relative to the anchor, body frame */
+    const double *axis;           /* [nb*3] joint axis, body frame */
+    const double *mass;           /* [nb] */
+    const double *inertia;        /* [nb*6] xx yy zz xy xz yz about the COM, body frame */
+    /* joints (one per non-root body, same order) */
+    const double *jnt_lower, *jnt_upper;     /* [nj]; lower > upper: no limit */
+    const double *jnt_damping;               /* [nj] */
+    const int32_t *jnt_act;                  /* [nj] action index driving the joint, -1: none */
+    const double *jnt_torque;                /* [nj] power * power_coef (rs/robot_locomotors.py:29) */
+    /* Bullet links folded into the bodies: robot.parts membership and per-link damping */
+    int32_t ns;
+    const int32_t *sub_body;      /* [ns] */
+    const double *sub_off;        /* [ns*3] link COM relative to the body COM, body frame */
+    const double *sub_mass;       /* [ns] */
+    const double *sub_inertia;    /* [ns*3] */
+    const int32_t *sub_in_parts;  /* [ns] */
+    int32_t torso_sub;            /* robot_body: index into sub_* */
+    /* collision geometry */
+    int32_t ng;
+    const int32_t *geom_body, *geom_type, *geom_ground, *geom_foot;   /* [ng]; geom_foot: index into foot_list or -1 */
+    const double *geom_radius, *geom_p0, *geom_p1, *geom_friction, *geom_threshold;
+    int32_t npair;
+    const int32_t *pair_a, *pair_b;
+    /* scene */
+    double gravity, timestep;
+    int32_t frame_skip, num_solver_iterations;
+    double contact_erp, erp, linear_slop, warmstarting_factor, link_damping, max_coordinate_velocity;
+    double ground_friction, limit_max_impulse, split_impulse_threshold;
+    int32_t limit_split_impulse, max_contacts;
+    /* task (rs/robot_locomotors.py, rs/gym_locomotion_envs.py:48-52) */
+    int32_t kind, action_dim, obs_dim, nfeet, max_episode_steps;
+    double initial_z;             /* < 0: latch torso z at the first calc_state after reset */
+    double electricity_cost, stall_torque_cost, joints_at_limit_cost;
+    double walk_target_x, walk_target_y;
+    double stadium_halflen, stadium_halfwidth;
+} pbg_model;
+
+typedef struct pbg_handle pbg_handle;
+
+/* device-side episode statistics, accumulated since creation / the last pbg_stats(reset=1) */
+typedef struct pbg_episode_stats {
+    double return_sum;            /* sum of finished-episode returns */
+    double length_sum;            /* sum of finished-episode lengths */
+    int64_t episodes;             /* finished episodes (terminated or truncated) */
+    int64_t truncated;            /* of which ended by max_episode_steps */
+    int64_t nonfinite;            /* episodes ended by a non-finite observation (rs/gym_locomotion_envs.py:63-65) */
+    int64_t steps;                /* env steps taken */
+} pbg_episode_stats;
+
+int pbg_version(void);
+
+/* Creates `num_envs` independent worlds of one env kind on `device`.  Replaces BulletClient() +
+ * scene/robot construction in BaseBulletEnv._reset (rs/env_bases.py:46-71).  env i of this handle
+ * uses RNG stream (seed, env_offset + i), so shards of one job stay decorrelated across GPUs. */
+int pbg_create(const pbg_model *model, int32_t num_envs, int32_t device, uint64_t seed, uint64_t env_offset,
+               pbg_handle **out);
+int pbg_destroy(pbg_handle *h);
+const char *pbg_last_error(const pbg_handle *h);   /* h may be NULL: error of the last failed pbg_create */
+
+/* sizes */
+int pbg_num_envs(const pbg_handle *h);
+int pbg_obs_dim(const pbg_handle *h);
+int pbg_action_dim(const pbg_handle *h);
+int pbg_state_dim(const pbg_handle *h);     /* canonical state: [pos3 quat4(xyzw) omega3 vel3] (floating) + q[nj] + qd[nj] */
+
+/* Episode reset (rs/gym_locomotion_envs.py:22-39, rs/robot_locomotors.py:16-24): restores the
+ * MJCF pose, draws U(-0.1,0.1) joint noise from the counter RNG, returns the first observation.
+ * mask_dev: uint8[num_envs] or NULL (= all).  floor_in_parts: reference quirk Q1 -- 0 reproduces the
+ * very first reset of an env's life (floor not yet in robot.parts), 1 every later reset. */
+int pbg_reset(pbg_handle *h, const uint8_t *mask_dev, int32_t floor_in_parts, float *obs_dev, void *stream);
+/* Same, with the joint noise given by the caller (float[num_envs, action_dim]), for parity tests. */
+int pbg_reset_with(pbg_handle *h, const float *joint_noise_dev, int32_t floor_in_parts, float *obs_dev, void *stream);
+
+/* One env step for every env: apply_action + stepSimulation + calc_state + reward/termination
+ * (rs/gym_locomotion_envs.py:54-114, rs/gym_pendulum_envs.py:26-39) fused in one kernel launch.
+ * Envs that finish (done or max_episode_steps) are reset inside the kernel when auto-reset is on;
+ * obs then holds the first observation of the new episode and final_obs_dev (optional) the last
+ * observation of the finished one.  reward_terms_dev: optional float[num_envs,5] =
+ * [alive, progress, electricity, joints_at_limit, feet_collision] (the reference's self.rewards).
+ * truncated_dev: optional uint8[num_envs], 1 where the episode hit max_episode_steps. */
+int pbg_step(pbg_handle *h, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+             float *reward_terms_dev, float *final_obs_dev, uint8_t *truncated_dev, void *stream);
+
+/* Host-buffer variant (the reference-facing call: numpy in, numpy out).  Copies actions H2D,
+ * steps, copies obs/reward/done D2H and synchronises.  Buffers should be pinned for full speed. */
+int pbg_step_host(pbg_handle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *done_host);
+
+int pbg_set_auto_reset(pbg_handle *h, int32_t enabled);
+
+/* Canonical state access for parity tests (replaces getJointState / getBasePositionAndOrientation /
+ * getBaseVelocity / resetJointState / resetBasePositionAndOrientation / resetBaseVelocity,
+ * rs/robot_bases.py:233-275,323-356).  float[num_envs, pbg_state_dim]. */
+int pbg_get_state(pbg_handle *h, float *state_dev, void *stream);
+int pbg_set_state(pbg_handle *h, const float *state_dev, void *stream);
+/* Physics only (apply_action + stepSimulation), no task bookkeeping; for single-step parity tests. */
+int pbg_physics_step(pbg_handle *h, const float *actions_dev, void *stream);
+/* calc_state + reward of the current state without physics (uses the given actions for the
+ * electricity terms); outputs as pbg_step.  For the 1e-5 observation/reward parity tier. */
+int pbg_observe(pbg_handle *h, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+                float *reward_terms_dev, void *stream);
+/* feet_contact flags as the reference's robot.feet_contact, float[num_envs, nfeet] */
+int pbg_get_feet_contact(pbg_handle *h, float *out_dev, void *stream);
+/* pbg_physics_step that also reports the contact points active in the last substep, int32[num_envs]
+ * (what getContactPoints would list after stepSimulation, rs/robot_bases.py:281) */
+int pbg_physics_step_counts(pbg_handle *h, const float *actions_dev, int32_t *ncontact_dev, void *stream);
+/* contact points the kernel of `kind` keeps per env (deepest first); the model passed to pbg_create
+ * must carry the same max_contacts */
+int pbg_max_contacts(int kind);
+
+int pbg_stats(pbg_handle *h, pbg_episode_stats *out_host, int32_t reset);
+
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t pbg_launch_count(const pbg_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

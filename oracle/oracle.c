@@ -877,6 +877,9 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
     if (m->initial_z >= 0) { e->initial_z = m->initial_z; e->have_initial_z = 1; } else e->have_initial_z = 0;
     if (is_walker(m->kind)) { walker_calc_state(e, obs); e->potential = calc_potential(e); }
     else pendulum_calc_state(e, obs);
+    /* quirk Q1: the env adds the floor to robot.parts right after this first calc_state
+     * (rs/gym_locomotion_envs.py:30-31), so every later calc_state of the episode averages it in */
+    e->floor_in_parts = 1;
 }
 
 void orc_reset_with(orc_env *e, const double *noise, int floor_in_parts, double *obs) {
@@ -891,6 +894,33 @@ void orc_reset(orc_env *e, int floor_in_parts, double *obs) {
     for (int k = 0; k < n; k++) noise[k] = rng_uniform(e->seed, e->env_index, e->episode, (uint32_t)k, -0.1f, 0.1f);
     reset_common(e, noise, floor_in_parts, obs);
 }
+
+/* physics step driven by raw joint torques (dof order), as setJointMotorControl2(TORQUE_CONTROL)
+ * would: used by the fake-pybullet backend that generates the task-layer golden vectors */
+void orc_physics_step_torque(orc_env *e, const double *tau) {
+    const orc_model *m = &e->m;
+    for (int d = 0; d < e->nd; d++) e->tau[d] = tau[d] - m->damping[e->link_of_dof[d]] * e->qd[d];
+    for (int s = 0; s < m->nsub; s++) substep(e);
+    for (int d = 0; d < e->nd; d++) e->tau[d] = 0;
+}
+/* per link: COM position(3), orientation quaternion xyzw(4), COM linear velocity(3) */
+void orc_link_state(orc_env *e, double *out) {
+    fk(e); velocities(e);
+    for (int i = 0; i < e->m.nl; i++) {
+        double q[4]; mat_to_quat((double(*)[3])e->R[i], q);
+        v3 v; link_com_vel(e, i, v);
+        for (int k = 0; k < 3; k++) out[10 * i + k] = e->c[i][k];
+        for (int k = 0; k < 4; k++) out[10 * i + 3 + k] = q[k];
+        for (int k = 0; k < 3; k++) out[10 * i + 7 + k] = v[k];
+    }
+}
+/* contact points of the last substep: link A, link B (-1 = floor), distance */
+int orc_get_contacts(const orc_env *e, int32_t *la, int32_t *lb, double *dist) {
+    for (int c = 0; c < e->nct; c++) { la[c] = e->ct[c].la; lb[c] = e->ct[c].lb; dist[c] = e->ct[c].dist; }
+    return e->nct;
+}
+void orc_set_joint(orc_env *e, int dof, double q, double qd) { e->q[dof] = q; e->qd[dof] = qd; }
+void orc_get_joint(const orc_env *e, int dof, double *q, double *qd) { *q = e->q[dof]; *qd = e->qd[dof]; }
 
 int orc_num_contacts(const orc_env *e) { return e->nct; }
 void orc_feet_contact(const orc_env *e, double *out) { for (int f = 0; f < e->m.nfeet; f++) out[f] = e->feet_contact[f]; }

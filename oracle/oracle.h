@@ -84,6 +84,12 @@ void orc_get_state(const orc_env *e, double *state);
 void orc_set_state(orc_env *e, const double *state);
 /* observation / task bookkeeping of the *current* state (no physics); same outputs as orc_step */
 int orc_observe(orc_env *e, const double *action, double *obs, double *reward, double *terms);
+/* hooks for the fake-pybullet backend (tools/fake_pybullet.py) */
+void orc_physics_step_torque(orc_env *e, const double *tau /* [nd] */);
+void orc_link_state(orc_env *e, double *out /* [nl*10]: com3 quat4 vel3 */);
+int orc_get_contacts(const orc_env *e, int32_t *la, int32_t *lb, double *dist);
+void orc_set_joint(orc_env *e, int dof, double q, double qd);
+void orc_get_joint(const orc_env *e, int dof, double *q, double *qd);
 /* diagnostics */
 int orc_num_contacts(const orc_env *e);
 void orc_feet_contact(const orc_env *e, double *out);

@@ -87,6 +87,12 @@ def lib():
         L.orc_energy.argtypes = [C.c_void_p]
         L.orc_energy.restype = C.c_double
         L.orc_mass_matrix_inv.argtypes = [C.c_void_p, _pd]
+        L.orc_physics_step_torque.argtypes = [C.c_void_p, _pd]
+        L.orc_link_state.argtypes = [C.c_void_p, _pd]
+        L.orc_get_contacts.argtypes = [C.c_void_p, _pi, _pi, _pd]
+        L.orc_get_contacts.restype = C.c_int
+        L.orc_set_joint.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        L.orc_get_joint.argtypes = [C.c_void_p, C.c_int, _pd, _pd]
         L.orc_rollout.argtypes = [C.c_void_p, C.c_long, C.c_uint64, _pd, C.POINTER(C.c_long)]
         L.orc_rollout.restype = C.c_long
         _lib = L
@@ -228,6 +234,29 @@ class OracleEnv:
         s = _d(s)
         assert s.size == self.model.state_size
         lib().orc_set_state(self._h, s.ctypes.data_as(_pd))
+
+    def physics_step_torque(self, tau):
+        t = _d(tau)
+        assert t.size == self.model.nd
+        lib().orc_physics_step_torque(self._h, t.ctypes.data_as(_pd))
+
+    def link_state(self):
+        out = np.zeros(10 * self.model.c.nl)
+        lib().orc_link_state(self._h, out.ctypes.data_as(_pd))
+        return out.reshape(-1, 10)
+
+    def contacts(self):
+        la, lb, d = np.zeros(256, np.int32), np.zeros(256, np.int32), np.zeros(256)
+        n = lib().orc_get_contacts(self._h, la.ctypes.data_as(_pi), lb.ctypes.data_as(_pi), d.ctypes.data_as(_pd))
+        return la[:n].copy(), lb[:n].copy(), d[:n].copy()
+
+    def set_joint(self, dof, q, qd):
+        lib().orc_set_joint(self._h, int(dof), float(q), float(qd))
+
+    def get_joint(self, dof):
+        q, qd = C.c_double(0), C.c_double(0)
+        lib().orc_get_joint(self._h, int(dof), C.byref(q), C.byref(qd))
+        return q.value, qd.value
 
     def num_contacts(self):
         return lib().orc_num_contacts(self._h)

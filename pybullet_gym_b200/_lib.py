@@ -1,0 +1,197 @@
+"""ctypes binding of libpbg_b200.so (include/pbg.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``build_extension()`` with
+``nvcc -gencode arch=compute_100a,code=sm_100a``.  There is no CPU fallback: if the library is
+missing or cannot be loaded, importing anything that steps physics raises ``BackendUnavailable``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+from .mjcf import compiler as mj
+from .spec import EnvSpec
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpbg_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+INCLUDE = os.path.join(_PKG, "..", "include")
+
+
+class BackendUnavailable(RuntimeError):
+    pass
+
+
+class PbgError(RuntimeError):
+    pass
+
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int32)
+_pf = C.POINTER(C.c_float)
+_pu8 = C.POINTER(C.c_uint8)
+
+
+class PbgModel(C.Structure):
+    _fields_ = [
+        ("nb", C.c_int32), ("nj", C.c_int32), ("floating", C.c_int32),
+        ("parent", _pi), ("jtype", _pi),
+        ("q0", _pd), ("anchor_p", _pd), ("com_off", _pd), ("axis", _pd), ("mass", _pd), ("inertia", _pd),
+        ("jnt_lower", _pd), ("jnt_upper", _pd), ("jnt_damping", _pd), ("jnt_act", _pi), ("jnt_torque", _pd),
+        ("ns", C.c_int32),
+        ("sub_body", _pi), ("sub_off", _pd), ("sub_mass", _pd), ("sub_inertia", _pd), ("sub_in_parts", _pi),
+        ("torso_sub", C.c_int32),
+        ("ng", C.c_int32),
+        ("geom_body", _pi), ("geom_type", _pi), ("geom_ground", _pi), ("geom_foot", _pi),
+        ("geom_radius", _pd), ("geom_p0", _pd), ("geom_p1", _pd), ("geom_friction", _pd), ("geom_threshold", _pd),
+        ("npair", C.c_int32),
+        ("pair_a", _pi), ("pair_b", _pi),
+        ("gravity", C.c_double), ("timestep", C.c_double),
+        ("frame_skip", C.c_int32), ("num_solver_iterations", C.c_int32),
+        ("contact_erp", C.c_double), ("erp", C.c_double), ("linear_slop", C.c_double),
+        ("warmstarting_factor", C.c_double), ("link_damping", C.c_double), ("max_coordinate_velocity", C.c_double),
+        ("ground_friction", C.c_double), ("limit_max_impulse", C.c_double), ("split_impulse_threshold", C.c_double),
+        ("limit_split_impulse", C.c_int32), ("max_contacts", C.c_int32),
+        ("kind", C.c_int32), ("action_dim", C.c_int32), ("obs_dim", C.c_int32), ("nfeet", C.c_int32),
+        ("max_episode_steps", C.c_int32),
+        ("initial_z", C.c_double),
+        ("electricity_cost", C.c_double), ("stall_torque_cost", C.c_double), ("joints_at_limit_cost", C.c_double),
+        ("walk_target_x", C.c_double), ("walk_target_y", C.c_double),
+        ("stadium_halflen", C.c_double), ("stadium_halfwidth", C.c_double),
+    ]
+
+
+class PbgEpisodeStats(C.Structure):
+    _fields_ = [("return_sum", C.c_double), ("length_sum", C.c_double), ("episodes", C.c_int64),
+                ("truncated", C.c_int64), ("nonfinite", C.c_int64), ("steps", C.c_int64)]
+
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build_extension(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into libpbg_b200.so for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(INCLUDE, "pbg.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB_PATH, os.path.join(CSRC, "pbg_abi.cu")]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BackendUnavailable(
+            "libpbg_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+            "this backend has no CPU fallback")
+    try:
+        L = C.CDLL(LIB_PATH)
+    except OSError as e:
+        raise BackendUnavailable("cannot load %s: %s (no CPU fallback)" % (LIB_PATH, e)) from e
+    vp = C.c_void_p
+    L.pbg_version.restype = C.c_int
+    L.pbg_max_contacts.argtypes = [C.c_int]
+    L.pbg_create.argtypes = [C.POINTER(PbgModel), C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(vp)]
+    L.pbg_destroy.argtypes = [vp]
+    L.pbg_last_error.argtypes = [vp]
+    L.pbg_last_error.restype = C.c_char_p
+    for f in ("pbg_num_envs", "pbg_obs_dim", "pbg_action_dim", "pbg_state_dim"):
+        getattr(L, f).argtypes = [vp]
+    L.pbg_reset.argtypes = [vp, vp, C.c_int32, vp, vp]
+    L.pbg_reset_with.argtypes = [vp, vp, C.c_int32, vp, vp]
+    L.pbg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.pbg_step_host.argtypes = [vp, vp, vp, vp, vp]
+    L.pbg_set_auto_reset.argtypes = [vp, C.c_int32]
+    L.pbg_get_state.argtypes = [vp, vp, vp]
+    L.pbg_set_state.argtypes = [vp, vp, vp]
+    L.pbg_physics_step.argtypes = [vp, vp, vp]
+    L.pbg_physics_step_counts.argtypes = [vp, vp, vp, vp]
+    L.pbg_observe.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.pbg_get_feet_contact.argtypes = [vp, vp, vp]
+    L.pbg_stats.argtypes = [vp, C.POINTER(PbgEpisodeStats), C.c_int32]
+    L.pbg_launch_count.argtypes = [vp]
+    L.pbg_launch_count.restype = C.c_int64
+    _lib = L
+    return L
+
+
+EXPORTS = ["pbg_version", "pbg_create", "pbg_destroy", "pbg_last_error", "pbg_num_envs", "pbg_obs_dim",
+           "pbg_action_dim", "pbg_state_dim", "pbg_reset", "pbg_reset_with", "pbg_step", "pbg_step_host",
+           "pbg_set_auto_reset", "pbg_get_state", "pbg_set_state", "pbg_physics_step", "pbg_physics_step_counts",
+           "pbg_max_contacts", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count"]
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class ModelTables:
+    """pbg_model built from an EnvSpec: MJCF -> BulletModel -> ReducedModel -> flat C arrays."""
+
+    def __init__(self, spec: EnvSpec, rules: Optional[mj.ImporterRules] = None, max_contacts: Optional[int] = None):
+        self.spec = spec
+        self.bullet = bm = mj.parse_mjcf(spec.xml, rules)
+        ordered = [bm.links[i].joint_name for i in bm.ordered_joints()]
+        self.ordered_joint_names = ordered
+        act_names = ordered[:spec.action_dim]
+        self.reduced = rm = mj.reduce_model(bm, act_names)
+        scale = dict(zip(ordered, spec.torque_scale(ordered)))
+        k = self._keep = {}
+        k["parent"], k["jtype"] = _i(rm.parent), _i(rm.jtype)
+        k["q0"], k["anchor_p"], k["com_off"], k["axis"] = _d(rm.q0), _d(rm.anchor_p), _d(rm.com_off), _d(rm.axis)
+        k["mass"], k["inertia"] = _d(rm.mass), _d(rm.inertia)
+        k["jnt_lower"], k["jnt_upper"], k["jnt_damping"] = _d(rm.jnt_lower), _d(rm.jnt_upper), _d(rm.jnt_damping)
+        k["jnt_act"] = _i(rm.jnt_act)
+        k["jnt_torque"] = _d([scale.get(n, 0.0) if a >= 0 else 0.0 for n, a in zip(rm.jnt_names, rm.jnt_act)])
+        k["sub_body"], k["sub_off"], k["sub_mass"] = _i(rm.sub_body), _d(rm.sub_off), _d(rm.sub_mass)
+        k["sub_inertia"], k["sub_in_parts"] = _d(rm.sub_inertia), _i(rm.sub_in_parts)
+        foot_of_link = {name: n for n, name in enumerate(spec.foot_list)}
+        k["geom_foot"] = _i([foot_of_link.get(rm.sub_names[s], -1) for s in rm.geom_link])
+        k["geom_body"], k["geom_type"], k["geom_ground"] = _i(rm.geom_body), _i(rm.geom_type), _i(rm.geom_ground)
+        k["geom_radius"], k["geom_p0"], k["geom_p1"] = _d(rm.geom_radius), _d(rm.geom_p0), _d(rm.geom_p1)
+        k["geom_friction"], k["geom_threshold"] = _d(rm.geom_friction), _d(rm.geom_threshold)
+        k["pair_a"], k["pair_b"] = _i(rm.pair_a), _i(rm.pair_b)
+        m = PbgModel()
+        m.nb, m.nj, m.floating = rm.nb, rm.nj, int(rm.floating)
+        m.ns, m.ng, m.npair = len(rm.sub_body), len(rm.geom_body), len(rm.pair_a)
+        m.torso_sub = rm.sub_names.index(spec.robot_name)
+        for name, arr in k.items():
+            setattr(m, name, arr.ctypes.data_as(_pd if arr.dtype == np.float64 else _pi))
+        sc = spec.scene
+        m.gravity, m.timestep, m.frame_skip, m.num_solver_iterations = sc.gravity, sc.timestep, sc.frame_skip, sc.num_solver_iterations
+        m.contact_erp, m.erp, m.linear_slop, m.warmstarting_factor = sc.contact_erp, sc.erp, sc.linear_slop, sc.warmstarting_factor
+        m.link_damping, m.max_coordinate_velocity = rm.link_damping, sc.max_coordinate_velocity
+        m.ground_friction, m.limit_max_impulse = sc.ground_friction, sc.limit_max_impulse
+        m.split_impulse_threshold, m.limit_split_impulse = sc.split_impulse_threshold, int(sc.limit_split_impulse)
+        m.max_contacts = lib().pbg_max_contacts(spec.kind) if max_contacts is None else max_contacts
+        m.kind, m.action_dim, m.obs_dim, m.nfeet = spec.kind, spec.action_dim, spec.obs_dim, len(spec.foot_list)
+        m.max_episode_steps = spec.max_episode_steps
+        m.initial_z = -1.0 if spec.initial_z is None else spec.initial_z
+        m.electricity_cost, m.stall_torque_cost = spec.electricity_cost, spec.stall_torque_cost
+        m.joints_at_limit_cost = spec.joints_at_limit_cost
+        m.walk_target_x, m.walk_target_y = spec.walk_target
+        m.stadium_halflen, m.stadium_halfwidth = sc.stadium_halflen, sc.stadium_halfwidth
+        self.c = m
+
+
+def check(rc: int, handle=None):
+    if rc != 0:
+        msg = lib().pbg_last_error(handle)
+        raise PbgError("libpbg_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))

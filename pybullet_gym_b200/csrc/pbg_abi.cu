@@ -1,0 +1,443 @@
+// C ABI of libpbg_b200.so (see include/pbg.h): host-side model flattening, state allocation and
+// kernel dispatch.  One handle = one env kind x num_envs worlds on one device.
+#include "../../include/pbg.h"
+#include "pbg_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pbg;
+
+// kernel configurations: NB, NJ, FLOATING, NLIM, MAXC, LPE, NCAND, NPAIR, NFEET, NACT, OBS
+using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5>;
+using CfgHopper = KCfg<6, 6, 0, 3, 8, 16, 8, 0, 1, 3, 15>;
+using CfgWalker = KCfg<9, 9, 0, 6, 8, 16, 14, 0, 2, 6, 22>;
+using CfgCheetah = KCfg<9, 9, 0, 6, 8, 16, 16, 0, 6, 6, 26>;
+using CfgAnt = KCfg<9, 8, 1, 8, 8, 16, 25, 0, 4, 8, 28>;
+using CfgHumanoid = KCfg<18, 17, 1, 17, 15, 32, 30, 66, 2, 17, 44>;
+
+struct KernelInfo {
+    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads;
+    size_t smem;
+    void (*launch)(const DevModel *, const StepBuffers &, const LaunchArgs &, cudaStream_t);
+    cudaError_t (*prepare)();
+};
+
+template <class C>
+static void launch_cfg(const DevModel *m, const StepBuffers &b, const LaunchArgs &la, cudaStream_t s) {
+    const int blocks = (la.E + C::EPB - 1) / C::EPB;
+    env_kernel<C><<<blocks, C::THREADS, C::SMEM_BYTES, s>>>(m, b, la);
+}
+template <class C>
+static cudaError_t prepare_cfg() {
+    return cudaFuncSetAttribute(env_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+}
+template <class C>
+static KernelInfo info_of() {
+    return KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
+}
+
+static bool kernel_for_kind(int kind, KernelInfo *out) {
+    switch (kind) {
+    case PBG_KIND_PENDULUM: case PBG_KIND_PENDULUM_SWINGUP: *out = info_of<CfgPendulum>(); return true;
+    case PBG_KIND_HOPPER: *out = info_of<CfgHopper>(); return true;
+    case PBG_KIND_WALKER2D: *out = info_of<CfgWalker>(); return true;
+    case PBG_KIND_HALFCHEETAH: *out = info_of<CfgCheetah>(); return true;
+    case PBG_KIND_ANT: *out = info_of<CfgAnt>(); return true;
+    case PBG_KIND_HUMANOID: *out = info_of<CfgHumanoid>(); return true;
+    default: return false;
+    }
+}
+
+struct pbg_handle {
+    int device = 0;
+    int E = 0;
+    KernelInfo k{};
+    DevModel *dmodel = nullptr;
+    float *state = nullptr;
+    unsigned long long *stats = nullptr;
+    // staging for pbg_step_host
+    float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;
+    uint8_t *d_done = nullptr;
+    cudaStream_t hstream = nullptr;
+    unsigned long long seed = 0, env_offset = 0;
+    int auto_reset = 1;
+    int64_t launches = 0;
+    int64_t steps = 0;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(pbg_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+#define CUDA_TRY(h, expr)                                                                             \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(h, PBG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+
+static void quat_to_mat(const double *q, float *R) {
+    double x = q[0], y = q[1], z = q[2], w = q[3];
+    double n = std::sqrt(x * x + y * y + z * z + w * w);
+    x /= n; y /= n; z /= n; w /= n;
+    R[0] = float(1 - 2 * (y * y + z * z)); R[1] = float(2 * (x * y - w * z)); R[2] = float(2 * (x * z + w * y));
+    R[3] = float(2 * (x * y + w * z)); R[4] = float(1 - 2 * (x * x + z * z)); R[5] = float(2 * (y * z - w * x));
+    R[6] = float(2 * (x * z - w * y)); R[7] = float(2 * (y * z + w * x)); R[8] = float(1 - 2 * (x * x + y * y));
+}
+
+// flatten the caller's tables into the device model; returns "" or an error message
+static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, DevModel *d) {
+    char buf[256];
+    memset(d, 0, sizeof(DevModel));
+    if (pm->nb != k.nb || pm->nj != k.nj || pm->floating != k.floating) {
+        snprintf(buf, sizeof buf, "model has nb=%d nj=%d floating=%d, kernel for kind %d expects %d/%d/%d", pm->nb, pm->nj,
+                 pm->floating, pm->kind, k.nb, k.nj, k.floating);
+        return buf;
+    }
+    if (pm->action_dim != k.nact || pm->obs_dim != k.obs || pm->nfeet != k.nfeet) return "action/obs/feet dims do not match the kernel";
+    if (pm->ns > MSUB) return "too many Bullet links";
+    if (pm->max_contacts != k.maxc) {
+        snprintf(buf, sizeof buf, "max_contacts=%d but the kernel keeps %d", pm->max_contacts, k.maxc);
+        return buf;
+    }
+    const int F = pm->floating ? 6 : 0;
+    d->nb = pm->nb; d->nj = pm->nj; d->nd = pm->nj + F; d->floating = pm->floating;
+    d->nact = pm->action_dim; d->nfeet = pm->nfeet; d->obs_dim = pm->obs_dim; d->kind = pm->kind;
+    int jidx = 0, nlim = 0;
+    for (int b = 0; b < pm->nb; ++b) {
+        d->parent[b] = pm->parent[b]; d->jtype[b] = pm->jtype[b];
+        if (pm->parent[b] >= b) return "bodies are not in depth-first order";
+        d->depth[b] = pm->parent[b] < 0 ? 0 : d->depth[pm->parent[b]] + 1;
+        if (d->depth[b] > d->maxdepth) d->maxdepth = d->depth[b];
+        quat_to_mat(pm->q0 + 4 * b, d->q0m[b]);
+        for (int i = 0; i < 3; ++i) {
+            d->anchor_p[b][i] = (float)pm->anchor_p[3 * b + i];
+            d->com_off[b][i] = (float)pm->com_off[3 * b + i];
+            d->axis[b][i] = (float)pm->axis[3 * b + i];
+        }
+        d->mass[b] = (float)pm->mass[b];
+        for (int i = 0; i < 6; ++i) d->inertia[b][i] = (float)pm->inertia[6 * b + i];
+        if (pm->jtype[b] == PBG_JT_FREE) {
+            if (b != 0) return "floating joint on a non-root body";
+            d->dof[b] = 0;
+            for (int i = 0; i < 3; ++i) d->base_pos0[i] = (float)pm->anchor_p[i];
+            for (int i = 0; i < 4; ++i) d->base_quat0[i] = (float)pm->q0[i];
+        } else if (pm->jtype[b] == PBG_JT_REVOLUTE || pm->jtype[b] == PBG_JT_PRISMATIC) {
+            d->dof[b] = F + jidx;
+            d->jbody[jidx] = b;
+            d->jrev[jidx] = pm->jtype[b] == PBG_JT_REVOLUTE;
+            d->jlo[jidx] = (float)pm->jnt_lower[jidx]; d->jhi[jidx] = (float)pm->jnt_upper[jidx];
+            d->jlimited[jidx] = pm->jnt_lower[jidx] < pm->jnt_upper[jidx];
+            nlim += d->jlimited[jidx];
+            d->jdamp[jidx] = (float)pm->jnt_damping[jidx];
+            d->jact[jidx] = pm->jnt_act[jidx];
+            d->jtorque[jidx] = (float)pm->jnt_torque[jidx];
+            if (pm->jnt_act[jidx] >= 0) {
+                if (pm->jnt_act[jidx] >= pm->action_dim) return "action index out of range";
+                d->act_joint[pm->jnt_act[jidx]] = jidx;
+            }
+            ++jidx;
+        } else return "unsupported joint type in the reduced tree";
+    }
+    if (jidx != pm->nj) return "joint count mismatch";
+    if (nlim > k.nlim) return "more limited joints than the kernel has limit rows";
+    d->nlim = nlim;
+    // dof relations
+    for (int b = 0; b < pm->nb; ++b) {
+        unsigned mask = 0;
+        for (int a = b; a >= 0; a = pm->parent[a]) {
+            if (pm->jtype[a] == PBG_JT_FREE) mask |= 0x3fu;
+            else mask |= 1u << d->dof[a];
+        }
+        d->anc[b] = mask;
+    }
+    for (int kk = 0; kk < d->nd; ++kk) {
+        const int body = (pm->floating && kk < 6) ? 0 : d->jbody[kk - F];
+        d->up[kk] = d->anc[body];
+    }
+    for (int kk = 0; kk < d->nd; ++kk) {
+        unsigned dn = 0;
+        for (int l = 0; l < d->nd; ++l) if ((d->up[l] >> kk) & 1u) dn |= 1u << l;
+        d->down[kk] = dn;
+    }
+    // Bullet links: parts membership and damping entries grouped by body
+    std::vector<std::vector<int>> by_body(pm->nb);
+    for (int s = 0; s < pm->ns; ++s) {
+        const int b = pm->sub_body[s];
+        if (b < 0 || b >= pm->nb) return "sub_body out of range";
+        if (pm->sub_in_parts[s]) {
+            d->part_cnt[b] += 1.f;
+            for (int i = 0; i < 3; ++i) d->part_sum[b][i] += (float)pm->sub_off[3 * s + i];
+        }
+        if (pm->sub_mass[s] > 0) by_body[b].push_back(s);
+    }
+    int nds = 0;
+    for (int b = 0; b < pm->nb; ++b) {
+        d->ds_begin[b] = nds;
+        for (int s : by_body[b]) {
+            for (int i = 0; i < 3; ++i) { d->ds_off[nds][i] = (float)pm->sub_off[3 * s + i]; d->ds_inertia[nds][i] = (float)pm->sub_inertia[3 * s + i]; }
+            d->ds_mass[nds] = (float)pm->sub_mass[s];
+            ++nds;
+        }
+    }
+    for (int b = pm->nb; b <= MB; ++b) d->ds_begin[b] = nds;
+    if (pm->torso_sub < 0 || pm->torso_sub >= pm->ns) return "torso_sub out of range";
+    d->torso_body = pm->sub_body[pm->torso_sub];
+    for (int i = 0; i < 3; ++i) d->torso_off[i] = (float)pm->sub_off[3 * pm->torso_sub + i];
+    if (pm->floating) {
+        // the canonical base state is the Bullet base-link COM; the kernel integrates the merged root body
+        double o = 0;
+        for (int i = 0; i < 3; ++i) o += std::fabs(pm->sub_off[i]);
+        if (o > 1e-9) return "root body COM differs from the Bullet base-link COM (not supported)";
+    }
+    // contact candidates: sphere -> centre, capsule -> both end spheres
+    int nc = 0;
+    std::vector<int> first_cand(pm->ng, -1);
+    for (int g = 0; g < pm->ng; ++g) {
+        if (pm->geom_type[g] == PBG_G_BOX) return "box geoms are not supported by this kernel";
+        const int npt = pm->geom_type[g] == PBG_G_CAPSULE ? 2 : 1;
+        if (!pm->geom_ground[g]) continue;
+        first_cand[g] = nc;
+        for (int e = 0; e < npt; ++e) {
+            if (nc >= MCAND || nc >= k.ncand) return "too many ground contact candidates for the kernel";
+            d->c_body[nc] = pm->geom_body[g];
+            d->c_foot[nc] = pm->geom_foot[g];
+            const double *p = e ? pm->geom_p1 + 3 * g : pm->geom_p0 + 3 * g;
+            for (int i = 0; i < 3; ++i) d->c_p[nc][i] = (float)p[i];
+            d->c_rad[nc] = (float)pm->geom_radius[g];
+            d->c_thr[nc] = (float)pm->geom_threshold[g];
+            d->c_mu[nc] = (float)(pm->geom_friction[g] * pm->ground_friction);
+            ++nc;
+        }
+    }
+    d->ncand = nc;
+    if (pm->npair > k.npair || pm->npair > MPAIR) return "too many self-collision pairs for the kernel";
+    d->npair = pm->npair;
+    for (int p = 0; p < pm->npair; ++p) {
+        const int a = pm->pair_a[p], b = pm->pair_b[p];
+        d->p_ba[p] = pm->geom_body[a]; d->p_bb[p] = pm->geom_body[b];
+        for (int i = 0; i < 3; ++i) {
+            d->p_a0[p][i] = (float)pm->geom_p0[3 * a + i]; d->p_a1[p][i] = (float)pm->geom_p1[3 * a + i];
+            d->p_b0[p][i] = (float)pm->geom_p0[3 * b + i]; d->p_b1[p][i] = (float)pm->geom_p1[3 * b + i];
+        }
+        d->p_ra[p] = (float)pm->geom_radius[a]; d->p_rb[p] = (float)pm->geom_radius[b];
+        d->p_thr[p] = (float)std::fmin(pm->geom_threshold[a], pm->geom_threshold[b]);
+        d->p_mu[p] = (float)(pm->geom_friction[a] * pm->geom_friction[b]);
+    }
+    d->gravity = (float)pm->gravity; d->h = (float)pm->timestep; d->erp_contact = (float)pm->contact_erp;
+    d->erp_limit = (float)pm->erp; d->slop = (float)pm->linear_slop; d->warm = (float)pm->warmstarting_factor;
+    d->kdamp = (float)pm->link_damping; d->maxvel = (float)pm->max_coordinate_velocity;
+    d->limit_max_imp = (float)pm->limit_max_impulse; d->split_thr = (float)pm->split_impulse_threshold;
+    d->nsub = pm->frame_skip; d->niter = pm->num_solver_iterations; d->limit_split = pm->limit_split_impulse;
+    d->max_contacts = pm->max_contacts;
+    d->initial_z = (float)pm->initial_z; d->elec_cost = (float)pm->electricity_cost; d->stall_cost = (float)pm->stall_torque_cost;
+    d->limit_cost = (float)pm->joints_at_limit_cost; d->walk_tx = (float)pm->walk_target_x; d->walk_ty = (float)pm->walk_target_y;
+    d->halflen = (float)pm->stadium_halflen; d->halfwidth = (float)pm->stadium_halfwidth;
+    d->dt_scene = pm->timestep * pm->frame_skip;
+    d->max_steps = pm->max_episode_steps;
+    return "";
+}
+
+extern "C" {
+
+int pbg_version(void) { return PBG_VERSION; }
+
+int pbg_max_contacts(int kind) {
+    KernelInfo k;
+    if (!kernel_for_kind(kind, &k)) return PBG_ERR_UNSUPPORTED;
+    return k.maxc;
+}
+
+const char *pbg_last_error(const pbg_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int pbg_create(const pbg_model *model, int32_t num_envs, int32_t device, uint64_t seed, uint64_t env_offset, pbg_handle **out) {
+    if (!model || !out || num_envs <= 0) return fail(nullptr, PBG_ERR_INVALID, "pbg_create: bad arguments");
+    KernelInfo k;
+    if (!kernel_for_kind(model->kind, &k)) return fail(nullptr, PBG_ERR_UNSUPPORTED, "pbg_create: no kernel for this env kind");
+    DevModel hm;
+    std::string e = build_dev_model(model, k, &hm);
+    if (!e.empty()) return fail(nullptr, PBG_ERR_INVALID, "pbg_create: " + e);
+    pbg_handle *h = new pbg_handle();
+    h->device = device; h->E = num_envs; h->k = k; h->seed = seed; h->env_offset = env_offset;
+#define CREATE_TRY(expr)                                                                  \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            g_create_err = std::string(#expr) + ": " + cudaGetErrorString(_e);            \
+            pbg_destroy(h);                                                               \
+            return PBG_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    CREATE_TRY(k.prepare());
+    CREATE_TRY(cudaMalloc(&h->dmodel, sizeof(DevModel)));
+    CREATE_TRY(cudaMemcpy(h->dmodel, &hm, sizeof(DevModel), cudaMemcpyHostToDevice));
+    const size_t sbytes = size_t(num_envs) * k.sstride * sizeof(float);
+    CREATE_TRY(cudaMalloc(&h->state, sbytes));
+    CREATE_TRY(cudaMemset(h->state, 0, sbytes));
+    CREATE_TRY(cudaMalloc(&h->stats, 8 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(h->stats, 0, 8 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMalloc(&h->d_act, size_t(num_envs) * k.nact * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->d_obs, size_t(num_envs) * k.obs * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->d_rew, size_t(num_envs) * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->d_done, size_t(num_envs)));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+#undef CREATE_TRY
+    *out = h;
+    return PBG_OK;
+}
+
+int pbg_destroy(pbg_handle *h) {
+    if (!h) return PBG_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->dmodel); cudaFree(h->state); cudaFree(h->stats);
+    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
+    if (h->hstream) cudaStreamDestroy(h->hstream);
+    delete h;
+    return PBG_OK;
+}
+
+int pbg_num_envs(const pbg_handle *h) { return h ? h->E : PBG_ERR_INVALID; }
+int pbg_obs_dim(const pbg_handle *h) { return h ? h->k.obs : PBG_ERR_INVALID; }
+int pbg_action_dim(const pbg_handle *h) { return h ? h->k.nact : PBG_ERR_INVALID; }
+int pbg_state_dim(const pbg_handle *h) { return h ? h->k.canon : PBG_ERR_INVALID; }
+int64_t pbg_launch_count(const pbg_handle *h) { return h ? h->launches : 0; }
+
+static int launch(pbg_handle *h, int mode, StepBuffers &b, int floor_in_parts, void *stream) {
+    if (!h) return PBG_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    b.state = h->state;
+    b.stats = h->stats;
+    LaunchArgs la;
+    la.E = h->E; la.mode = mode; la.auto_reset = h->auto_reset; la.floor_in_parts = floor_in_parts;
+    la.seed = h->seed; la.env_offset = h->env_offset;
+    h->k.launch(h->dmodel, b, la, (cudaStream_t)stream);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    return PBG_OK;
+}
+
+int pbg_set_auto_reset(pbg_handle *h, int32_t enabled) {
+    if (!h) return PBG_ERR_INVALID;
+    h->auto_reset = enabled ? 1 : 0;
+    return PBG_OK;
+}
+
+int pbg_reset(pbg_handle *h, const uint8_t *mask_dev, int32_t floor_in_parts, float *obs_dev, void *stream) {
+    StepBuffers b{};
+    b.mask = mask_dev; b.obs = obs_dev;
+    return launch(h, MODE_RESET, b, floor_in_parts, stream);
+}
+
+int pbg_reset_with(pbg_handle *h, const float *joint_noise_dev, int32_t floor_in_parts, float *obs_dev, void *stream) {
+    if (!joint_noise_dev) return fail(h, PBG_ERR_INVALID, "pbg_reset_with: joint_noise_dev is NULL");
+    StepBuffers b{};
+    b.noise = joint_noise_dev; b.obs = obs_dev;
+    return launch(h, MODE_RESET, b, floor_in_parts, stream);
+}
+
+int pbg_step(pbg_handle *h, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+             float *reward_terms_dev, float *final_obs_dev, uint8_t *truncated_dev, void *stream) {
+    if (!h || !actions_dev) return fail(h, PBG_ERR_INVALID, "pbg_step: actions_dev is NULL");
+    StepBuffers b{};
+    b.actions = actions_dev; b.obs = obs_dev; b.reward = reward_dev; b.done = done_dev; b.terms = reward_terms_dev;
+    b.final_obs = final_obs_dev; b.truncated = truncated_dev;
+    h->steps += h->E;
+    return launch(h, MODE_STEP, b, 1, stream);
+}
+
+int pbg_step_host(pbg_handle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *done_host) {
+    if (!h || !actions_host) return fail(h, PBG_ERR_INVALID, "pbg_step_host: actions_host is NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->hstream;
+    const size_t E = h->E;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_act, actions_host, E * h->k.nact * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = pbg_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, nullptr, nullptr, nullptr, s);
+    if (rc != PBG_OK) return rc;
+    if (obs_host) CUDA_TRY(h, cudaMemcpyAsync(obs_host, h->d_obs, E * h->k.obs * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (reward_host) CUDA_TRY(h, cudaMemcpyAsync(reward_host, h->d_rew, E * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (done_host) CUDA_TRY(h, cudaMemcpyAsync(done_host, h->d_done, E, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return PBG_OK;
+}
+
+int pbg_get_state(pbg_handle *h, float *state_dev, void *stream) {
+    if (!h || !state_dev) return fail(h, PBG_ERR_INVALID, "pbg_get_state: NULL buffer");
+    StepBuffers b{};
+    b.canon = state_dev;
+    return launch(h, MODE_GET, b, 1, stream);
+}
+
+int pbg_set_state(pbg_handle *h, const float *state_dev, void *stream) {
+    if (!h || !state_dev) return fail(h, PBG_ERR_INVALID, "pbg_set_state: NULL buffer");
+    StepBuffers b{};
+    b.canon = const_cast<float *>(state_dev);
+    return launch(h, MODE_SET, b, 1, stream);
+}
+
+int pbg_physics_step(pbg_handle *h, const float *actions_dev, void *stream) {
+    if (!h || !actions_dev) return fail(h, PBG_ERR_INVALID, "pbg_physics_step: actions_dev is NULL");
+    StepBuffers b{};
+    b.actions = actions_dev;
+    return launch(h, MODE_PHYSICS, b, 1, stream);
+}
+
+int pbg_observe(pbg_handle *h, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+                float *reward_terms_dev, void *stream) {
+    if (!h || !actions_dev) return fail(h, PBG_ERR_INVALID, "pbg_observe: actions_dev is NULL");
+    StepBuffers b{};
+    b.actions = actions_dev; b.obs = obs_dev; b.reward = reward_dev; b.done = done_dev; b.terms = reward_terms_dev;
+    return launch(h, MODE_OBSERVE, b, 1, stream);
+}
+
+// small helper kernels for diagnostics
+__global__ void gather_kernel(const float *state, int sstride, int off, int n, float *out, int E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < E * n) out[i] = state[size_t(i / n) * sstride + off + i % n];
+}
+
+int pbg_get_feet_contact(pbg_handle *h, float *out_dev, void *stream) {
+    if (!h || !out_dev) return fail(h, PBG_ERR_INVALID, "pbg_get_feet_contact: NULL buffer");
+    if (h->k.nfeet == 0) return PBG_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // feet flags are the last NFEET floats before the padded end of the state row
+    const int F = h->k.floating ? 1 : 0;
+    const int off = 7 * F + h->k.nj + (h->k.nj + 6 * F) + (h->k.ncand + h->k.npair) + TASK_FLOATS;
+    const int n = h->E * h->k.nfeet;
+    gather_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, h->k.sstride, off, h->k.nfeet, out_dev, h->E);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    return PBG_OK;
+}
+
+int pbg_physics_step_counts(pbg_handle *h, const float *actions_dev, int32_t *ncontact_dev, void *stream) {
+    if (!h || !actions_dev) return fail(h, PBG_ERR_INVALID, "pbg_physics_step_counts: actions_dev is NULL");
+    StepBuffers b{};
+    b.actions = actions_dev; b.ncontact_out = ncontact_dev;
+    return launch(h, MODE_PHYSICS, b, 1, stream);
+}
+
+int pbg_stats(pbg_handle *h, pbg_episode_stats *out, int32_t reset) {
+    if (!h || !out) return fail(h, PBG_ERR_INVALID, "pbg_stats: NULL argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    unsigned long long raw[8];
+    CUDA_TRY(h, cudaMemcpy(raw, h->stats, sizeof raw, cudaMemcpyDeviceToHost));
+    out->episodes = (int64_t)raw[0];
+    out->length_sum = (double)raw[1];
+    memcpy(&out->return_sum, &raw[2], sizeof(double));
+    out->truncated = (int64_t)raw[3];
+    out->nonfinite = (int64_t)raw[4];
+    out->steps = h->steps;
+    if (reset) { CUDA_TRY(h, cudaMemset(h->stats, 0, sizeof raw)); h->steps = 0; }
+    return PBG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1072 @@
+// Fused env-step kernel of libpbg_b200 (sm_100a).
+//
+// One environment per LPE-lane group (LPE = 16: two envs per warp, LPE = 32: one env per warp).
+// Replaces, per env step, the reference's apply_action -> stepSimulation -> calc_state -> reward
+// chain (/root/reference/pybulletgym/envs/roboschool/gym_locomotion_envs.py:54-114 and the 23..72
+// pybullet calls behind it) with one launch:
+//
+//   load state (coalesced) -> smem
+//   frame_skip x { FK (lane = body, level by level) -> contact generation (lane = candidate)
+//                  -> composite inertias + bias wrench (lane = body, subtree sums lane = component)
+//                  -> joint-space inertia rows + Cholesky in registers (lane = dof)
+//                  -> constraint rows J, Y = L^-1 J^T (lane = row) -> Delassus matrix A = Y Y^T
+//                  -> projected Gauss-Seidel on lambda (lane = row, one shuffle per row update)
+//                  -> du = L^-T (h y_f + Y^T lambda), semi-implicit integration }
+//   FK -> calc_state / reward / termination (+ in-kernel reset) -> store
+//
+// No tensor cores: per-env matrices are 6..23 wide.
+#pragma once
+#include "pbg_model.cuh"
+#include <math_constants.h>
+
+namespace pbg {
+
+template <int NB_, int NJ_, int FLOATING_, int NLIM_, int MAXC_, int LPE_, int NCAND_, int NPAIR_, int NFEET_,
+          int NACT_, int OBS_>
+struct KCfg {
+    static constexpr int NB = NB_, NJ = NJ_, FLOATING = FLOATING_, ND = NJ_ + 6 * FLOATING_, NLIM = NLIM_;
+    static constexpr int MAXC = MAXC_, LPE = LPE_, NCAND = NCAND_, NPAIR = NPAIR_, NSLOT = NCAND_ + NPAIR_;
+    static constexpr int NFEET = NFEET_, NACT = NACT_, OBS = OBS_;
+    static constexpr int MAXR = NLIM + 3 * MAXC;
+    static constexpr int MAXRP = MAXR > 0 ? MAXR : 1;
+    static constexpr int NDP = (ND + 3) / 4 * 4;
+    static constexpr int LST = NDP + 4;            // row stride of L / Y: float4 rows, conflict-free
+    static constexpr int EPW = 32 / LPE;
+    static constexpr int WARPS = 4, THREADS = 128, EPB = WARPS * EPW;
+    static_assert(MAXR <= 2 * LPE, "at most two row slots per lane");
+    static_assert(ND + 1 <= LPE && NB <= LPE && NCAND <= 2 * LPE, "lane budget");
+    // per-env state (floats)
+    static constexpr int oQ = 7 * FLOATING, oU = oQ + NJ, oW = oU + ND, oT = oW + NSLOT, oF = oT + TASK_FLOATS;
+    static constexpr int SSIZE = oF + NFEET, SSTRIDE = (SSIZE + 3) / 4 * 4;
+    static constexpr int CANON = 13 * FLOATING + 2 * NJ;
+    // shared memory per env (floats)
+    static constexpr int KS = 31;                  // R9 x3 w3 v3 al3 a3 z3 A3 (+1 pad)
+    static constexpr int sST = 0;
+    static constexpr int sKIN = sST + SSTRIDE;
+    static constexpr int sACC = sKIN + NB * KS;
+    static constexpr int sSH = (sACC + NB * 17 + 3) / 4 * 4;
+    static constexpr int sF = sSH + ND * 12;
+    static constexpr int sL = (sF + NDP + 3) / 4 * 4;
+    static constexpr int sINV = sL + (ND + 1) * LST;
+    static constexpr int sCOL = sINV + NDP;
+    static constexpr int sY = (sCOL + 2 * (NDP + 4) + 3) / 4 * 4;
+    static constexpr int sA = sY + MAXRP * LST;
+    static constexpr int sLAM = sA + MAXRP * MAXRP;
+    static constexpr int sCT = sLAM + MAXRP;
+    static constexpr int CTS = 16;                 // contact record: bodyA bodyB slot pad pA3 pB3 n3 dist mu pad
+    static constexpr int sLIM = sCT + (MAXC > 0 ? MAXC : 1) * CTS;
+    static constexpr int sCD = sLIM + 2 * (NLIM > 0 ? NLIM : 1);
+    static constexpr int sMISC = sCD + (NSLOT > 0 ? NSLOT : 1);   // this step's feet flags
+    static constexpr int sOUT = sMISC + 8;                        // staged outputs: obs[64] reward terms[5]
+    static constexpr int ENV_FLOATS = (sOUT + 72 + 3) / 4 * 4;
+    static constexpr size_t SMEM_BYTES = size_t(ENV_FLOATS) * EPB * sizeof(float);
+};
+
+// ---------------------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ V3 ld3(const float *p) { return mk(p[0], p[1], p[2]); }
+__device__ __forceinline__ void st3(float *p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+__device__ __forceinline__ V3 mulR(const float *R, V3 a) {   // row-major 3x3 times vector
+    return mk(R[0] * a.x + R[1] * a.y + R[2] * a.z, R[3] * a.x + R[4] * a.y + R[5] * a.z,
+              R[6] * a.x + R[7] * a.y + R[8] * a.z);
+}
+__device__ __forceinline__ V3 mulRt(const float *R, V3 a) {
+    return mk(R[0] * a.x + R[3] * a.y + R[6] * a.z, R[1] * a.x + R[4] * a.y + R[7] * a.z,
+              R[2] * a.x + R[5] * a.y + R[8] * a.z);
+}
+__device__ __forceinline__ void quat2mat(const float *q, float *R) {
+    float x = q[0], y = q[1], z = q[2], w = q[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+    R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+    R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
+}
+__device__ __forceinline__ void mat2quat(const float *m, float *q) {
+    float t = m[0] + m[4] + m[8];
+    if (t > 0) {
+        float s = sqrtf(t + 1.0f) * 2;
+        q[3] = 0.25f * s; q[0] = (m[7] - m[5]) / s; q[1] = (m[2] - m[6]) / s; q[2] = (m[3] - m[1]) / s;
+    } else if (m[0] >= m[4] && m[0] >= m[8]) {
+        float s = sqrtf(m[0] - m[4] - m[8] + 1.0f) * 2;
+        q[0] = 0.25f * s; q[1] = (m[3] + m[1]) / s; q[2] = (m[6] + m[2]) / s; q[3] = (m[7] - m[5]) / s;
+    } else if (m[4] >= m[8]) {
+        float s = sqrtf(m[4] - m[8] - m[0] + 1.0f) * 2;
+        q[1] = 0.25f * s; q[2] = (m[7] + m[5]) / s; q[0] = (m[1] + m[3]) / s; q[3] = (m[2] - m[6]) / s;
+    } else {
+        float s = sqrtf(m[8] - m[0] - m[4] + 1.0f) * 2;
+        q[2] = 0.25f * s; q[0] = (m[2] + m[6]) / s; q[1] = (m[5] + m[7]) / s; q[3] = (m[3] - m[1]) / s;
+    }
+}
+
+// Philox4x32-10, bit-identical to oracle/oracle.c rng_uniform_s
+__device__ __forceinline__ float rng_uniform(unsigned long long seed, unsigned long long env, unsigned ep,
+                                             unsigned stream, unsigned n, float lo, float hi) {
+    unsigned c0 = (unsigned)env, c1 = (unsigned)(env >> 32), c2 = ep, c3 = (stream << 24) | (n >> 2);
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    unsigned r = (n & 3) == 0 ? c0 : ((n & 3) == 1 ? c1 : ((n & 3) == 2 ? c2 : c3));
+    float u = (float)(r >> 8) * (1.0f / 16777216.0f);
+    return fmaf(hi - lo, u, lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class C>
+struct Env {
+    const DevModel *__restrict__ m;
+    float *sm;          // this env's shared-memory block
+    int gl;             // lane within the group
+    int grp;            // group within the warp
+    // lane-as-body constants
+    int bparent, bjtype, bdepth, bdof;
+    float Q0[9], anchor_p[3], com_off[3], axis[3], bmass, Ib[6];
+    // lane-as-body kinematics of the current pass
+    float R[9];
+    V3 x, w, v, al, a;
+    // lane-as-dof constants
+    unsigned up, down;
+    float tau;          // joint force of this dof for the current env step
+    int nc, nl;         // active contacts / limit rows of this env (group-uniform)
+
+    static constexpr unsigned FULL = 0xffffffffu;
+
+    __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(FULL, v, src, C::LPE); }
+    __device__ __forceinline__ int shfli(int v, int src) const { return __shfl_sync(FULL, v, src, C::LPE); }
+    __device__ __forceinline__ float gsum(float v) const {
+#pragma unroll
+        for (int o = C::LPE / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o, C::LPE);
+        return v;
+    }
+    __device__ __forceinline__ unsigned gballot(bool p) const {
+        unsigned b = __ballot_sync(FULL, p);
+        if (C::LPE == 32) return b;
+        return (b >> (grp * C::LPE)) & ((1u << (C::LPE & 31)) - 1u);
+    }
+    __device__ __forceinline__ int wmax(int v) const { return __reduce_max_sync(FULL, v); }
+
+    __device__ __forceinline__ float *kin(int b) const { return sm + C::sKIN + b * C::KS; }
+    __device__ __forceinline__ float *st() const { return sm + C::sST; }
+    __device__ __forceinline__ float *uvec() const { return sm + C::sST + C::oU; }
+
+    __device__ void load_lane_constants() {
+        const int b = gl < C::NB ? gl : 0;
+        bparent = m->parent[b]; bjtype = m->jtype[b]; bdepth = gl < C::NB ? m->depth[b] : 1000; bdof = m->dof[b];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Q0[i] = m->q0m[b][i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { anchor_p[i] = m->anchor_p[b][i]; com_off[i] = m->com_off[b][i]; axis[i] = m->axis[b][i]; }
+        bmass = m->mass[b];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Ib[i] = m->inertia[b][i];
+        const int k = gl < C::ND ? gl : 0;
+        up = m->up[k]; down = m->down[k];
+        tau = 0.f; nc = 0; nl = 0;
+    }
+
+    // ---------------------------------------------------------------- forward kinematics
+    // lane = body, one tree level per round.  bias=true also propagates the velocity-product
+    // accelerations needed for the bias wrench.
+    __device__ void fk(bool bias) {
+        const float *S = st();
+        const int maxdepth = m->maxdepth;
+        for (int lvl = 0; lvl <= maxdepth; ++lvl) {
+            if (bdepth == lvl) {
+                float Rp[9];
+                V3 xp, wp, vp, alp, ap;
+                if (bparent >= 0) {
+                    const float *kp = kin(bparent);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Rp[i] = kp[i];
+                    xp = ld3(kp + 9); wp = ld3(kp + 12); vp = ld3(kp + 15); alp = ld3(kp + 18); ap = ld3(kp + 21);
+                } else {
+                    Rp[0] = 1; Rp[1] = 0; Rp[2] = 0; Rp[3] = 0; Rp[4] = 1; Rp[5] = 0; Rp[6] = 0; Rp[7] = 0; Rp[8] = 1;
+                    xp = wp = vp = alp = ap = mk(0, 0, 0);
+                }
+                V3 zw = mk(0, 0, 0), A = mk(0, 0, 0);
+                if (bjtype == 3) {   // floating root
+                    quat2mat(S + 3, R);
+                    x = ld3(S); w = ld3(S + C::oU); v = ld3(S + C::oU + 3);
+                    al = a = mk(0, 0, 0);
+                } else {
+                    float Rq[9];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            Rq[3 * i + j] = Rp[3 * i] * Q0[j] + Rp[3 * i + 1] * Q0[3 + j] + Rp[3 * i + 2] * Q0[6 + j];
+                    const float q = S[C::oQ + bdof - 6 * C::FLOATING], qd = S[C::oU + bdof];
+                    A = xp + mulR(Rp, ld3(anchor_p));
+                    const V3 ax = ld3(axis);
+                    zw = mulR(Rq, ax);
+                    const V3 rpA = A - xp;
+                    if (bjtype == 1) {
+                        float s, c;
+                        sincosf(q, &s, &c);
+                        const float t = 1.f - c;
+                        float Rj[9];
+                        Rj[0] = c + t * ax.x * ax.x; Rj[1] = t * ax.x * ax.y - s * ax.z; Rj[2] = t * ax.x * ax.z + s * ax.y;
+                        Rj[3] = t * ax.x * ax.y + s * ax.z; Rj[4] = c + t * ax.y * ax.y; Rj[5] = t * ax.y * ax.z - s * ax.x;
+                        Rj[6] = t * ax.x * ax.z - s * ax.y; Rj[7] = t * ax.y * ax.z + s * ax.x; Rj[8] = c + t * ax.z * ax.z;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j)
+                                R[3 * i + j] = Rq[3 * i] * Rj[j] + Rq[3 * i + 1] * Rj[3 + j] + Rq[3 * i + 2] * Rj[6 + j];
+                        const V3 rAi = mulR(R, ld3(com_off));
+                        x = A + rAi;
+                        w = wp + qd * zw;
+                        v = vp + cross(wp, rpA) + cross(w, rAi);
+                        if (bias) {
+                            al = alp + qd * cross(wp, zw);
+                            const V3 aA = ap + cross(alp, rpA) + cross(wp, cross(wp, rpA));
+                            a = aA + cross(al, rAi) + cross(w, cross(w, rAi));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) R[i] = Rq[i];
+                        x = A + q * zw + mulR(R, ld3(com_off));
+                        w = wp;
+                        const V3 rpi = x - xp;
+                        v = vp + cross(wp, rpi) + qd * zw;
+                        if (bias) {
+                            al = alp;
+                            a = ap + cross(alp, rpi) + cross(wp, cross(wp, rpi)) + (2.f * qd) * cross(wp, zw);
+                        }
+                    }
+                }
+                float *k = kin(gl);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) k[i] = R[i];
+                st3(k + 9, x); st3(k + 12, w); st3(k + 15, v);
+                if (bias) { st3(k + 18, al); st3(k + 21, a); }
+                st3(k + 24, zw); st3(k + 27, A);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---------------------------------------------------------------- contact generation
+    // lane = candidate.  Ground: sphere centre / capsule end spheres against z = 0.  Pairs:
+    // closest points of two segments.  A candidate is a contact when its distance is below the
+    // owning link's manifold breaking threshold; at most MAXC deepest are kept.
+    __device__ void collide(V3 xref, bool want_feet) {
+        if (C::MAXC == 0) { nc = 0; return; }
+        float *cd = sm + C::sCD;
+        float *warm = st() + C::oW;
+        constexpr int PASSES = C::NSLOT > 0 ? (C::NSLOT + C::LPE - 1) / C::LPE : 1;
+        float dist[PASSES];
+        bool act[PASSES];
+        V3 pa[PASSES], pb[PASSES], nn[PASSES];
+        int total = 0;
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const int s = p * C::LPE + gl;
+            act[p] = false; dist[p] = CUDART_INF_F;
+            pa[p] = pb[p] = mk(0, 0, 0); nn[p] = mk(0, 0, 1);
+            if (s < m->ncand) {
+                const float *kb = kin(m->c_body[s]);
+                const V3 c = ld3(kb + 9) + mulR(kb, ld3(m->c_p[s]));
+                const float r = m->c_rad[s];
+                dist[p] = c.z - r;
+                act[p] = dist[p] < m->c_thr[s];
+                pa[p] = mk(c.x, c.y, c.z - r); pb[p] = mk(c.x, c.y, 0.f);
+            } else if (C::NPAIR > 0 && s >= C::NCAND && s - C::NCAND < m->npair) {
+                const int pi = s - C::NCAND;
+                const float *ka = kin(m->p_ba[pi]), *kb = kin(m->p_bb[pi]);
+                const V3 p1 = ld3(ka + 9) + mulR(ka, ld3(m->p_a0[pi])), q1 = ld3(ka + 9) + mulR(ka, ld3(m->p_a1[pi]));
+                const V3 p2 = ld3(kb + 9) + mulR(kb, ld3(m->p_b0[pi])), q2 = ld3(kb + 9) + mulR(kb, ld3(m->p_b1[pi]));
+                const V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+                const float aa = dot(d1, d1), ee = dot(d2, d2), f = dot(d2, r);
+                float sp, tp;
+                const float EPS = 1e-12f;
+                if (aa <= EPS && ee <= EPS) { sp = tp = 0.f; }
+                else if (aa <= EPS) { sp = 0.f; tp = __saturatef(f / ee); }
+                else {
+                    const float cc = dot(d1, r);
+                    if (ee <= EPS) { tp = 0.f; sp = __saturatef(-cc / aa); }
+                    else {
+                        const float bb = dot(d1, d2), den = aa * ee - bb * bb;
+                        sp = den > EPS ? __saturatef((bb * f - cc * ee) / den) : 0.f;
+                        tp = (bb * sp + f) / ee;
+                        if (tp < 0.f) { tp = 0.f; sp = __saturatef(-cc / aa); }
+                        else if (tp > 1.f) { tp = 1.f; sp = __saturatef((bb - cc) / aa); }
+                    }
+                }
+                const V3 ca = p1 + sp * d1, cb = p2 + tp * d2, d = ca - cb;
+                const float len = sqrtf(dot(d, d)), ra = m->p_ra[pi], rb = m->p_rb[pi];
+                dist[p] = len - ra - rb;
+                act[p] = dist[p] < m->p_thr[pi] && len > 1e-9f;
+                const V3 n = (1.f / fmaxf(len, 1e-20f)) * d;
+                nn[p] = n; pa[p] = ca - ra * n; pb[p] = cb + rb * n;
+            }
+            if (s < C::NSLOT) cd[s] = act[p] ? dist[p] : CUDART_INF_F;
+            total += __popc(gballot(act[p]));
+        }
+        __syncwarp();
+        const int cap = C::MAXC;
+        if (wmax(total) > cap) {
+            // keep the MAXC smallest by (distance, slot)
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+                const int s = p * C::LPE + gl;
+                int rank = 0;
+                if (act[p]) {
+                    for (int j = 0; j < C::NSLOT; ++j) {
+                        const float dj = cd[j];
+                        rank += (dj < dist[p] || (dj == dist[p] && j < s)) ? 1 : 0;
+                    }
+                    if (rank >= cap) act[p] = false;
+                }
+            }
+        }
+        int base = 0;
+        unsigned feet = 0;
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const int s = p * C::LPE + gl;
+            const unsigned bal = gballot(act[p]);
+            const int idx = base + __popc(bal & ((1u << gl) - 1u));
+            base += __popc(bal);
+            if (act[p]) {
+                float *ct = sm + C::sCT + idx * C::CTS;
+                int ba, bb; float mu;
+                if (s < C::NCAND) { ba = m->c_body[s]; bb = -1; mu = m->c_mu[s]; }
+                else { ba = m->p_ba[s - C::NCAND]; bb = m->p_bb[s - C::NCAND]; mu = m->p_mu[s - C::NCAND]; }
+                ct[0] = __int_as_float(ba); ct[1] = __int_as_float(bb); ct[2] = __int_as_float(s);
+                st3(ct + 4, pa[p] - xref); st3(ct + 7, pb[p] - xref); st3(ct + 10, nn[p]);
+                ct[13] = dist[p]; ct[14] = mu;
+                if (s < C::NCAND && m->c_foot[s] >= 0) feet |= 1u << m->c_foot[s];
+            } else if (s < C::NSLOT) {
+                warm[s] = 0.f;
+            }
+        }
+        nc = base;
+        if (want_feet) {
+            float *fo = sm + C::sMISC;
+#pragma unroll
+            for (int f = 0; f < C::NFEET; ++f) {
+                const unsigned any = gballot((feet >> f) & 1u);
+                if (gl == 0) fo[f] = any ? 1.f : 0.f;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---------------------------------------------------------------- dynamics of one substep
+    __device__ void substep(bool last) {
+        const float h = m->h;
+        float *S = st();
+        fk(true);
+        const V3 xref = ld3(kin(m->torso_body) + 9);
+        collide(xref, last);
+
+        // --- body wrench + composite inertia entries (lane = body)
+        float *acc = sm + C::sACC;
+        if (gl < C::NB) {
+            // world inertia I = R Ib R^T
+            float T[9];   // R * Ib
+            {
+                const float Ixx = Ib[0], Iyy = Ib[1], Izz = Ib[2], Ixy = Ib[3], Ixz = Ib[4], Iyz = Ib[5];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    T[3 * i + 0] = R[3 * i] * Ixx + R[3 * i + 1] * Ixy + R[3 * i + 2] * Ixz;
+                    T[3 * i + 1] = R[3 * i] * Ixy + R[3 * i + 1] * Iyy + R[3 * i + 2] * Iyz;
+                    T[3 * i + 2] = R[3 * i] * Ixz + R[3 * i + 1] * Iyz + R[3 * i + 2] * Izz;
+                }
+            }
+            float Iw[6];   // xx yy zz xy xz yz
+            Iw[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
+            Iw[1] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5];
+            Iw[2] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8];
+            Iw[3] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
+            Iw[4] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8];
+            Iw[5] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8];
+            auto Imul = [&](V3 q) {
+                return mk(Iw[0] * q.x + Iw[3] * q.y + Iw[4] * q.z, Iw[3] * q.x + Iw[1] * q.y + Iw[5] * q.z,
+                          Iw[4] * q.x + Iw[5] * q.y + Iw[2] * q.z);
+            };
+            V3 F = bmass * mk(a.x, a.y, a.z + m->gravity);
+            V3 N = Imul(al) + cross(w, Imul(w));
+            // Bullet's per-link damping, one entry per massive Bullet link of the body
+            const float kd = m->kdamp;
+            const V3 wl = mulRt(R, w);
+            const float wn = sqrtf(dot(w, w));
+            for (int s = m->ds_begin[gl]; s < m->ds_begin[gl + 1]; ++s) {
+                const V3 ro = mulR(R, ld3(m->ds_off[s]));
+                const V3 vs = v + cross(w, ro);
+                const float vn = sqrtf(dot(vs, vs));
+                const V3 Fd = (-m->ds_mass[s] * (kd + kd * vn)) * vs;
+                const V3 tl = mk(m->ds_inertia[s][0] * wl.x, m->ds_inertia[s][1] * wl.y, m->ds_inertia[s][2] * wl.z);
+                const V3 Nd = (-(kd + kd * wn)) * mulR(R, tl);
+                F = F - Fd;
+                N = N - Nd - cross(ro, Fd);
+            }
+            const V3 r = x - xref;
+            float *ab = acc + gl * 17;
+            const float rr = dot(r, r);
+            ab[0] = bmass;
+            st3(ab + 1, bmass * r);
+            ab[4] = Iw[0] + bmass * (rr - r.x * r.x); ab[5] = Iw[1] + bmass * (rr - r.y * r.y);
+            ab[6] = Iw[2] + bmass * (rr - r.z * r.z);
+            ab[7] = Iw[3] - bmass * r.x * r.y; ab[8] = Iw[4] - bmass * r.x * r.z; ab[9] = Iw[5] - bmass * r.y * r.z;
+            st3(ab + 10, N + cross(r, F));
+            st3(ab + 13, F);
+        }
+        __syncwarp();
+        // --- subtree sums (lane = component): children precede... bodies are in DFS order, so a
+        // reverse sweep folds every body into its parent after its own subtree is complete.
+        if (gl < 16) {
+            for (int b = C::NB - 1; b >= 1; --b) {
+                const int p = m->parent[b];
+                if (p >= 0) acc[p * 17 + gl] += acc[b * 17 + gl];
+            }
+        }
+        __syncwarp();
+
+        // --- motion subspace S_k, H_k = Ic S_k, f_k = tau_k - S_k . W (lane = dof)
+        float *SH = sm + C::sSH;
+        float *fv = sm + C::sF;
+        float Sk[6] = {0, 0, 0, 0, 0, 0}, Hk[6] = {0, 0, 0, 0, 0, 0};
+        if (gl < C::ND) {
+            int body;
+            if (C::FLOATING && gl < 6) {
+                body = 0;
+                const V3 r0 = ld3(kin(0) + 9) - xref;
+                const V3 e = mk(gl % 3 == 0, gl % 3 == 1, gl % 3 == 2);
+                if (gl < 3) { Sk[0] = e.x; Sk[1] = e.y; Sk[2] = e.z; const V3 sv = cross(r0, e); Sk[3] = sv.x; Sk[4] = sv.y; Sk[5] = sv.z; }
+                else { Sk[3] = e.x; Sk[4] = e.y; Sk[5] = e.z; }
+            } else {
+                const int j = gl - 6 * C::FLOATING;
+                body = m->jbody[j];
+                const float *kb = kin(body);
+                const V3 z = ld3(kb + 24);
+                if (m->jrev[j]) {
+                    const V3 ar = ld3(kb + 27) - xref;
+                    const V3 sv = cross(ar, z);
+                    Sk[0] = z.x; Sk[1] = z.y; Sk[2] = z.z; Sk[3] = sv.x; Sk[4] = sv.y; Sk[5] = sv.z;
+                } else { Sk[3] = z.x; Sk[4] = z.y; Sk[5] = z.z; }
+            }
+            const float *ab = acc + body * 17;
+            const float mc = ab[0];
+            const V3 hc = ld3(ab + 1);
+            const V3 so = mk(Sk[0], Sk[1], Sk[2]), sv = mk(Sk[3], Sk[4], Sk[5]);
+            const V3 Iso = mk(ab[4] * so.x + ab[7] * so.y + ab[8] * so.z, ab[7] * so.x + ab[5] * so.y + ab[9] * so.z,
+                              ab[8] * so.x + ab[9] * so.y + ab[6] * so.z);
+            const V3 L = Iso + cross(hc, sv);
+            const V3 P = mc * sv + cross(so, hc);
+            Hk[0] = L.x; Hk[1] = L.y; Hk[2] = L.z; Hk[3] = P.x; Hk[4] = P.y; Hk[5] = P.z;
+            const float Ck = dot(so, ld3(ab + 10)) + dot(sv, ld3(ab + 13));
+            fv[gl] = tau - Ck;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { SH[gl * 12 + i] = Sk[i]; SH[gl * 12 + 6 + i] = Hk[i]; }
+        }
+        __syncwarp();
+
+        // --- joint-space inertia row of this dof (registers), augmented row ND = f
+        float Mr[C::ND];
+#pragma unroll
+        for (int l = 0; l < C::ND; ++l) {
+            const float4 s0 = *reinterpret_cast<const float4 *>(SH + l * 12);
+            const float4 s1 = *reinterpret_cast<const float4 *>(SH + l * 12 + 4);
+            const float4 s2 = *reinterpret_cast<const float4 *>(SH + l * 12 + 8);
+            // S_l = (s0.xyzw, s1.xy)  H_l = (s1.zw, s2.xyzw)
+            const float a_up = s0.x * Hk[0] + s0.y * Hk[1] + s0.z * Hk[2] + s0.w * Hk[3] + s1.x * Hk[4] + s1.y * Hk[5];
+            const float a_dn = Sk[0] * s1.z + Sk[1] * s1.w + Sk[2] * s2.x + Sk[3] * s2.y + Sk[4] * s2.z + Sk[5] * s2.w;
+            float val = ((up >> l) & 1u) ? a_up : (((down >> l) & 1u) ? a_dn : 0.f);
+            if (gl == C::ND) val = fv[l];
+            Mr[l] = val;
+        }
+        // --- Cholesky, rows in registers, column exchange through shared memory
+        float *col = sm + C::sCOL;
+        float *inv = sm + C::sINV;
+#pragma unroll
+        for (int j = 0; j < C::ND; ++j) {
+            const float djj = shfl(Mr[j], j);
+            const float iv = rsqrtf(fmaxf(djj, 1e-20f));
+            const float lij = Mr[j] * iv;
+            Mr[j] = lij;
+            float *cb = col + (j & 1) * (C::NDP + 4);
+            cb[gl < C::NDP + 4 ? gl : 0] = lij;
+            if (gl == j) inv[j] = iv;
+            __syncwarp();
+#pragma unroll
+            for (int c = j + 1; c < C::ND; ++c) Mr[c] -= lij * cb[c];
+        }
+        float *Lm = sm + C::sL;
+        if (gl <= C::ND) {
+#pragma unroll
+            for (int c = 0; c < C::ND; ++c) Lm[gl * C::LST + c] = Mr[c];
+        }
+        __syncwarp();
+        const float *yf = Lm + C::ND * C::LST;     // y_f = L^-1 f
+
+        // --- joint limit rows (lane = joint): a side is a row only while violated (C4.4)
+        float *lim = sm + C::sLIM;
+        {
+            bool lact = false; float pen = 0.f; int side = 0;
+            if (gl < C::NJ && m->jlimited[gl]) {
+                const float q = S[C::oQ + gl];
+                const float pl = q - m->jlo[gl], pu = m->jhi[gl] - q;
+                if (pl <= 0.f) { lact = true; pen = pl; side = 0; }
+                else if (pu <= 0.f) { lact = true; pen = pu; side = 1; }
+            }
+            const unsigned bal = gballot(lact);
+            if (C::NLIM > 0 && lact) {
+                const int idx = __popc(bal & ((1u << gl) - 1u));
+                lim[2 * idx] = __int_as_float((gl + 6 * C::FLOATING) | (side << 8));
+                lim[2 * idx + 1] = pen;
+            }
+            nl = __popc(bal);
+        }
+        __syncwarp();
+
+        // --- constraint rows (lane = row, two slots)
+        const int nr = nl + 3 * nc;
+        const int nrmax = wmax(nr);
+        float *Ym = sm + C::sY;
+        float *Am = sm + C::sA;
+        float *lam = sm + C::sLAM;
+        float *warm = S + C::oW;
+        float *u = uvec();
+        float rhs[2], dinv[2], lo[2], hi[2], lmb[2], mu[2], Yr[2][C::ND];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            rhs[sl] = 0.f; dinv[sl] = 0.f; lo[sl] = 0.f; hi[sl] = 0.f; lmb[sl] = 0.f; mu[sl] = 0.f;
+#pragma unroll
+            for (int k = 0; k < C::ND; ++k) Yr[sl][k] = 0.f;
+            if (sl * C::LPE >= nrmax) continue;
+            const int i = sl * C::LPE + gl;
+            float J[C::ND];
+#pragma unroll
+            for (int k = 0; k < C::ND; ++k) J[k] = 0.f;
+            float pen = 0.f; int kind = -1;     // 0 limit, 1 normal, 2 friction
+            int slot = 0;
+            if (i < nl) {
+                kind = 0;
+                const int code = __float_as_int(lim[2 * i]);
+                const int d = code & 0xff;
+                const float dir = (code >> 8) ? -1.f : 1.f;
+                pen = lim[2 * i + 1];
+#pragma unroll
+                for (int k = 0; k < C::ND; ++k) J[k] = (k == d) ? dir : 0.f;
+            } else if (i < nr) {
+                const int ci = i - nl;
+                int c; V3 d;
+                const float *ct;
+                if (ci < nc) { kind = 1; c = ci; ct = sm + C::sCT + c * C::CTS; d = ld3(ct + 10); }
+                else {
+                    kind = 2; c = (ci - nc) >> 1; ct = sm + C::sCT + c * C::CTS;
+                    const V3 n = ld3(ct + 10);
+                    V3 t1, t2;   // btPlaneSpace1
+                    if (fabsf(n.z) > 0.70710678f) {
+                        const float aa = n.y * n.y + n.z * n.z, k = rsqrtf(aa);
+                        t1 = mk(0.f, -n.z * k, n.y * k); t2 = mk(aa * k, -n.x * t1.z, n.x * t1.y);
+                    } else {
+                        const float aa = n.x * n.x + n.y * n.y, k = rsqrtf(aa);
+                        t1 = mk(-n.y * k, n.x * k, 0.f); t2 = mk(-n.z * t1.y, n.z * t1.x, aa * k);
+                    }
+                    d = ((ci - nc) & 1) ? t2 : t1;
+                }
+                const int ba = __float_as_int(ct[0]), bb = __float_as_int(ct[1]);
+                slot = __float_as_int(ct[2]);
+                pen = ct[13] + m->slop;
+                mu[sl] = ct[14];
+                const V3 pA = ld3(ct + 4), pB = ld3(ct + 7);
+                const unsigned ma = m->anc[ba], mb = bb >= 0 ? m->anc[bb] : 0u;
+#pragma unroll
+                for (int k = 0; k < C::ND; ++k) {
+                    const V3 so = ld3(SH + k * 12), sv = ld3(SH + k * 12 + 3);
+                    float val = 0.f;
+                    if ((ma >> k) & 1u) val += dot(d, sv + cross(so, pA));
+                    if ((mb >> k) & 1u) val -= dot(d, sv + cross(so, pB));
+                    J[k] = val;
+                }
+            }
+            float rel = 0.f;
+#pragma unroll
+            for (int k = 0; k < C::ND; ++k) rel += J[k] * u[k];
+            // forward substitution Y = L^-1 J^T
+#pragma unroll
+            for (int k = 0; k < C::ND; ++k) {
+                float sacc = J[k];
+#pragma unroll
+                for (int mm = 0; mm < k; ++mm) sacc -= Lm[k * C::LST + mm] * J[mm];
+                J[k] = sacc * inv[k];
+            }
+            float dd = 0.f, yy = 0.f;
+#pragma unroll
+            for (int k = 0; k < C::ND; ++k) { dd += J[k] * J[k]; yy += J[k] * yf[k]; Yr[sl][k] = J[k]; }
+            rel += h * yy;                         // J (u + h qdd)
+            const float di = dd > 1e-12f ? 1.f / dd : 0.f;
+            dinv[sl] = di;
+            const float ih = 1.f / h;
+            if (kind == 0) {
+                float poserr = -pen * m->erp_limit * ih;
+                if (m->limit_split && !(pen > m->split_thr)) poserr = 0.f;
+                rhs[sl] = (poserr - rel) * di; lo[sl] = 0.f; hi[sl] = m->limit_max_imp;
+            } else if (kind == 1) {
+                float poserr = 0.f, velerr = -rel;
+                if (pen > 0.f) velerr -= pen * ih; else poserr = -pen * m->erp_contact * ih;
+                rhs[sl] = (poserr + velerr) * di; lo[sl] = 0.f; hi[sl] = 1e10f;
+                lmb[sl] = warm[slot] * m->warm;
+            } else if (kind == 2) {
+                rhs[sl] = -rel * di;
+            } else {
+                dinv[sl] = 0.f;
+            }
+            if (i < C::MAXR) {
+#pragma unroll
+                for (int k = 0; k < C::ND; ++k) Ym[i * C::LST + k] = J[k];
+                lam[i] = lmb[sl];
+            }
+        }
+        __syncwarp();
+
+        // --- Delassus matrix A = Y Y^T and warm-started residual r = A lambda0
+        float r[2] = {0.f, 0.f};
+        if (nrmax > 0) {
+            for (int i = 0; i < nrmax; ++i) {
+                float yi[C::ND];
+#pragma unroll
+                for (int k = 0; k < C::ND; ++k) yi[k] = Ym[i * C::LST + k];
+                const float l0 = lam[i];
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (sl * C::LPE >= nrmax) continue;
+                    float aij = 0.f;
+#pragma unroll
+                    for (int k = 0; k < C::ND; ++k) aij += yi[k] * Yr[sl][k];
+                    const int jrow = sl * C::LPE + gl;
+                    if (jrow < C::MAXR) Am[i * C::MAXRP + jrow] = aij;
+                    r[sl] += aij * l0;
+                }
+            }
+        }
+        __syncwarp();
+
+        // --- projected Gauss-Seidel on lambda, Bullet's row order: limit rows (alternating
+        // direction), contact normals, friction rows (btMultiBodyConstraintSolver::solveSingleIteration)
+        const int niter = m->niter;
+        for (int it = 0; it < niter; ++it) {
+            for (int t = 0; t < nrmax; ++t) {
+                int i = t;
+                if (t < nl) i = (it & 1) ? t : nl - 1 - t;
+                const bool live = t < nr;
+                const int owner = i & (C::LPE - 1);
+                const bool s1 = i >= C::LPE;
+                float flo = s1 ? lo[1] : lo[0], fhi = s1 ? hi[1] : hi[0];
+                const float frhs = s1 ? rhs[1] : rhs[0], fdi = s1 ? dinv[1] : dinv[0];
+                const float fl = s1 ? lmb[1] : lmb[0], fr = s1 ? r[1] : r[0], fmu = s1 ? mu[1] : mu[0];
+                bool skip = !live;
+                {
+                    // friction rows are bounded by mu * (current normal impulse); the shuffle runs for
+                    // every row so that both env groups of the warp stay converged
+                    const bool isfr = i >= nl + nc;
+                    const int nrow = isfr ? nl + ((i - nl - nc) >> 1) : 0;
+                    const float ln = shfl((nrow >= C::LPE) ? lmb[1] : lmb[0], nrow & (C::LPE - 1));
+                    if (isfr) { if (ln > 0.f) { flo = -fmu * ln; fhi = fmu * ln; } else skip = true; }
+                }
+                float dl = frhs - fr * fdi;
+                const float sum = fminf(fmaxf(fl + dl, flo), fhi);
+                dl = skip ? 0.f : sum - fl;
+                if (gl == owner && !skip) { if (s1) lmb[1] = sum; else lmb[0] = sum; }
+                dl = shfl(dl, owner);
+                const float *arow = Am + i * C::MAXRP;
+                r[0] += arow[gl < C::MAXR ? gl : 0] * dl;
+                if (C::MAXR > C::LPE) r[1] += arow[(C::LPE + gl) < C::MAXR ? C::LPE + gl : 0] * dl;
+            }
+        }
+        // --- publish lambda, store warm-start impulses
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            const int i = sl * C::LPE + gl;
+            if (i < nr && i < C::MAXR) {
+                lam[i] = lmb[sl];
+                if (i >= nl && i < nl + nc) warm[__float_as_int(sm[C::sCT + (i - nl) * C::CTS + 2])] = lmb[sl];
+            }
+        }
+        __syncwarp();
+
+        // --- du = L^-T (h y_f + Y^T lambda)   (lane = dof)
+        float g = 0.f;
+        if (gl < C::ND) {
+            g = h * yf[gl];
+            for (int i = 0; i < nr; ++i) g += Ym[i * C::LST + gl] * lam[i];
+        }
+#pragma unroll
+        for (int k = C::ND - 1; k >= 0; --k) {
+            const float xk = shfl(g, k) * inv[k];
+            if (gl == k) g = xk;
+            else if (gl < k) g -= Lm[k * C::LST + gl] * xk;
+        }
+        __syncwarp();
+        if (gl < C::ND) {
+            const float mv = m->maxvel;
+            u[gl] = fminf(fmaxf(u[gl] + g, -mv), mv);
+        }
+        __syncwarp();
+        // --- semi-implicit Euler (btMultiBody::stepPositionsMultiDof)
+        if (gl < C::NJ) S[C::oQ + gl] += h * u[6 * C::FLOATING + gl];
+        if (C::FLOATING && gl == C::LPE - 1) {
+            const V3 om = ld3(u);
+            float wn = sqrtf(dot(om, om));
+            if (wn * h > 0.25f * CUDART_PI_F) wn = 0.5f * (0.5f * CUDART_PI_F) / h;
+            float sc;
+            if (wn < 0.001f) sc = 0.5f * h - h * h * h * 0.020833333333f * wn * wn;
+            else sc = sinf(0.5f * wn * h) / wn;
+            const float ax = om.x * sc, ay = om.y * sc, az = om.z * sc, aw = cosf(0.5f * wn * h);
+            const float bx = S[3], by = S[4], bz = S[5], bw = S[6];
+            float qx = aw * bx + ax * bw + ay * bz - az * by;
+            float qy = aw * by - ax * bz + ay * bw + az * bx;
+            float qz = aw * bz + ax * by - ay * bx + az * bw;
+            float qw = aw * bw - ax * bx - ay * by - az * bz;
+            const float nn = rsqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
+            S[3] = qx * nn; S[4] = qy * nn; S[5] = qz * nn; S[6] = qw * nn;
+        }
+        if (C::FLOATING && gl < 3) S[gl] += h * u[3 + gl];
+        __syncwarp();
+    }
+
+    // ---------------------------------------------------------------- task layer
+    // WalkerBase.calc_state + WalkerBaseBulletEnv._step reward terms
+    // (rs/robot_locomotors.py:31-79, rs/gym_locomotion_envs.py:54-114).  Returns done (group-uniform).
+    // `reset_pass`: first observation of an episode (latches initial_z, sets potential, no reward).
+    __device__ bool walker_task(const float *act, float *obs_out, float *rew_out, float *terms_out, bool reset_pass, bool pred) {
+        float *S = st();
+        float *T = S + C::oT;
+        fk(false);
+        // joint features (lane = action index)
+        float jpos = 0.f, jvel = 0.f, aval = 0.f;
+        bool atlim = false;
+        if (gl < C::NACT) {
+            const int j = m->act_joint[gl];
+            float pos = S[C::oQ + j];
+            const float vel = S[C::oU + 6 * C::FLOATING + j];
+            if (m->jlimited[j]) {
+                const float lo = m->jlo[j], hi = m->jhi[j];
+                pos = 2.f * (pos - 0.5f * (lo + hi)) / (hi - lo);
+            }
+            jpos = pos; jvel = (m->jrev[j] ? 0.1f : 0.5f) * vel;
+            atlim = fabsf(jpos) > 0.99f;
+            aval = act ? act[gl] : 0.f;
+        }
+        const int nlim = __popc(gballot(atlim));
+        const float se = gsum(gl < C::NACT ? fabsf(aval * jvel) : 0.f);
+        const float ss = gsum(gl < C::NACT ? aval * aval : 0.f);
+        // mean x / y of robot.parts (lane = body)
+        float px = 0.f, py = 0.f, pn = 0.f;
+        if (gl < C::NB) {
+            const V3 o = mulR(R, ld3(m->part_sum[gl]));
+            pn = m->part_cnt[gl];
+            px = pn * x.x + o.x; py = pn * x.y + o.y;
+        }
+        px = gsum(px); py = gsum(py); pn = gsum(pn);
+        const float floorp = T[T_FLOOR];
+        const float bx = px / (pn + floorp), by = py / (pn + floorp);
+        // torso pose / speed
+        const float *kt = kin(m->torso_body);
+        const V3 toff = mulR(kt, ld3(m->torso_off));
+        const float z = kt[11] + toff.z;
+        const V3 tsp = ld3(kt + 15) + cross(ld3(kt + 12), toff);
+        float tq[4];
+        mat2quat(kt, tq);
+        const float qx = tq[0], qy = tq[1], qz = tq[2], qw = tq[3];
+        const float sarg = -2.f * (qx * qz - qw * qy);
+        const float roll = atan2f(2.f * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
+        const float pitch = sarg <= -1.f ? -0.5f * CUDART_PI_F : (sarg >= 1.f ? 0.5f * CUDART_PI_F : asinf(sarg));
+        const float yaw = atan2f(2.f * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
+        float initz = T[T_INITZ];
+        if (reset_pass) {
+            initz = m->initial_z >= 0.f ? m->initial_z : z;
+        }
+        const float tx = T[T_TX], ty = T[T_TY];
+        const double ddy = (double)ty - (double)by, ddx = (double)tx - (double)bx;
+        const float theta = atan2f(ty - by, tx - bx);
+        const double dist = sqrt(ddy * ddy + ddx * ddx);
+        const float ang = theta - yaw;
+        float sy, cy;
+        sincosf(-yaw, &sy, &cy);
+        const float vx = cy * tsp.x - sy * tsp.y, vy = sy * tsp.x + cy * tsp.y, vz = tsp.z;
+        float sa, ca;
+        sincosf(ang, &sa, &ca);
+        // observation, clipped to +-5
+        auto clip5 = [](float q) { return fminf(fmaxf(q, -5.f), 5.f); };
+        const float o0 = clip5(z - initz);
+        if (obs_out && pred) {
+            if (gl == 0) {
+                obs_out[0] = o0; obs_out[1] = clip5(sa); obs_out[2] = clip5(ca); obs_out[3] = clip5(0.3f * vx);
+                obs_out[4] = clip5(0.3f * vy); obs_out[5] = clip5(0.3f * vz); obs_out[6] = clip5(roll); obs_out[7] = clip5(pitch);
+            }
+            if (gl < C::NACT) { obs_out[8 + 2 * gl] = clip5(jpos); obs_out[9 + 2 * gl] = clip5(jvel); }
+            if (gl < C::NFEET) obs_out[8 + 2 * C::NACT + gl] = clip5(S[C::oF + gl]);   // previous step's flags (quirk Q2)
+        }
+        const double pot_new = -dist / m->dt_scene;
+        bool done = false;
+        {
+            // alive uses state[0] + initial_z after the float32 round trip (rs/gym_locomotion_envs.py:61)
+            const float zz = (m->initial_z >= 0.f) ? (o0 + initz) : (float)((double)o0 + (double)initz);
+            const float *fc = S + C::oF;
+            float alive;
+            const int kind = m->kind;
+            if (kind == 2 || kind == 3) alive = (zz > 0.8f && fabsf(pitch) < 1.0f) ? 1.f : -1.f;
+            else if (kind == 4) alive = (fabsf(pitch) < 1.0f && fc[1] == 0.f && fc[2] == 0.f && fc[4] == 0.f && fc[5] == 0.f) ? 1.f : -1.f;
+            else if (kind == 5) alive = zz > 0.26f ? 1.f : -1.f;
+            else alive = zz > 0.78f ? 2.f : -1.f;
+            done = alive < 0.f;
+            // non-finite observation ends the episode (rs/gym_locomotion_envs.py:63-65)
+            bool bad = !(isfinite(o0) && isfinite(sa) && isfinite(ca) && isfinite(vx) && isfinite(vy) && isfinite(vz) &&
+                         isfinite(roll) && isfinite(pitch));
+            bad = bad || (gl < C::NACT && !(isfinite(jpos) && isfinite(jvel)));
+            const bool anybad = gballot(bad) != 0u;
+            done = (done || anybad) && !reset_pass;
+            const double pot_old = __hiloint2double(__float_as_int(T[T_POT_HI]), __float_as_int(T[T_POT_LO]));
+            const float progress = (float)(pot_new - pot_old);
+            const float elec = m->elec_cost * (se / (float)C::NACT) + m->stall_cost * (ss / (float)C::NACT);
+            const float limc = m->limit_cost * (float)nlim;
+            if (gl == 0 && pred && !reset_pass) {
+                if (rew_out) *rew_out = alive + progress + elec + limc;
+                if (terms_out) { terms_out[0] = alive; terms_out[1] = progress; terms_out[2] = elec; terms_out[3] = limc; terms_out[4] = 0.f; }
+                if (anybad) T[T_HAVEZ] = 2.f;      // marks a non-finite termination for the statistics
+            }
+        }
+        __syncwarp();
+        if (gl == 0 && pred) {
+            T[T_POT_LO] = __int_as_float(__double2loint(pot_new));
+            T[T_POT_HI] = __int_as_float(__double2hiint(pot_new));
+            if (reset_pass) { T[T_INITZ] = initz; T[T_FLOOR] = 1.f; }   // quirk Q1: the floor joins robot.parts after the reset's calc_state
+        }
+        __syncwarp();
+        return done;
+    }
+
+    // InvertedPendulum (rs/robot_pendula.py:27-51, rs/gym_pendulum_envs.py:26-39)
+    __device__ bool pendulum_task(float *obs_out, float *rew_out, float *terms_out, bool reset_pass, bool pred) {
+        const float *S = st();
+        const float xx = S[C::oQ], th = S[C::oQ + 1], vx = S[C::oU], thd = S[C::oU + 1];
+        float s, c;
+        sincosf(th, &s, &c);
+        if (gl == 0 && pred) {
+            if (obs_out) { obs_out[0] = xx; obs_out[1] = vx; obs_out[2] = c; obs_out[3] = s; obs_out[4] = thd; }
+            if (!reset_pass) {
+                const float rw = (m->kind == 1) ? c : 1.f;
+                if (rew_out) *rew_out = rw;
+                if (terms_out) { terms_out[0] = rw; terms_out[1] = 0.f; terms_out[2] = 0.f; terms_out[3] = 0.f; terms_out[4] = 0.f; }
+            }
+        }
+        return !reset_pass && m->kind == 0 && fabsf(th) > 0.2f;
+    }
+
+    // `pred` guards every persistent write, so that a whole warp can run the task / reset code
+    // while only some of its env groups need it (no divergent __syncwarp / shuffles).
+    __device__ bool task(const float *act, float *obs_out, float *rew_out, float *terms_out, bool reset_pass,
+                         bool pred = true) {
+        if (m->kind <= 1) return pendulum_task(obs_out, rew_out, terms_out, reset_pass, pred);
+        return walker_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
+    }
+
+    // Episode reset: MJCF pose, joint noise (rs/robot_locomotors.py:16-24), zero velocities,
+    // cleared feet flags and warm-start cache.  noise == nullptr draws from the counter RNG.
+    __device__ void reset_state(const LaunchArgs &la, unsigned long long env, const float *noise, int floor_in_parts,
+                                bool pred = true) {
+        float *S = st();
+        float *T = S + C::oT;
+        const unsigned ep = (unsigned)__float_as_int(T[T_EPISODE]) + 1u;
+        __syncwarp();
+        if (pred) {
+            for (int i = gl; i < C::oT; i += C::LPE) S[i] = 0.f;
+            for (int i = gl; i < C::NFEET; i += C::LPE) S[C::oF + i] = 0.f;
+        }
+        __syncwarp();
+        if (pred) {
+            if (C::FLOATING) {
+                if (gl < 3) S[gl] = m->base_pos0[gl];
+                if (gl < 4) S[3 + gl] = m->base_quat0[gl];
+            }
+            if (gl < C::NACT) {
+                const float nz = noise ? noise[gl] : rng_uniform(la.seed, env, ep, 0u, (unsigned)gl, -0.1f, 0.1f);
+                if (m->kind <= 1) { if (gl == 0) S[C::oQ + 1] = nz + (m->kind == 1 ? 3.1415f : 0.f); }
+                else S[C::oQ + m->act_joint[gl]] = nz;
+            }
+            if (gl == 0) {
+                T[T_EPISODE] = __int_as_float((int)ep);
+                T[T_STEPS] = __int_as_float(0);
+                T[T_RETURN] = 0.f;
+                T[T_FLOOR] = floor_in_parts ? 1.f : 0.f;
+                T[T_TX] = m->walk_tx; T[T_TY] = m->walk_ty;
+                T[T_HAVEZ] = 0.f;
+            }
+        }
+        __syncwarp();
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(C::THREADS) env_kernel(const DevModel *__restrict__ model, StepBuffers B, LaunchArgs la) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Env<C> e;
+    e.m = model;
+    e.gl = lane & (C::LPE - 1);
+    e.grp = lane / C::LPE;
+    const int slot = warp * C::EPW + e.grp;
+    e.sm = smem + slot * C::ENV_FLOATS;
+    const long long env_raw = (long long)blockIdx.x * C::EPB + slot;
+    const bool valid = env_raw < la.E;
+    const long long env = valid ? env_raw : (la.E - 1);
+    const unsigned long long genv = la.env_offset + (unsigned long long)env;
+    const int gl = e.gl;
+    e.load_lane_constants();
+
+    float *S = e.st();
+    float *gs = B.state + env * C::SSTRIDE;
+    // coalesced, vectorised state load
+    for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
+        reinterpret_cast<float4 *>(S)[i] = reinterpret_cast<const float4 *>(gs)[i];
+    __syncwarp();
+    float *T = S + C::oT;
+    const int mode = la.mode;
+
+    if (mode == MODE_GET) {
+        float *cs = B.canon + env * C::CANON;
+        if (valid) {
+            if (C::FLOATING) {
+                if (gl < 7) cs[gl] = S[gl];
+                if (gl < 6) cs[7 + gl] = S[C::oU + gl];
+            }
+            for (int j = gl; j < C::NJ; j += C::LPE) {
+                cs[13 * C::FLOATING + j] = S[C::oQ + j];
+                cs[13 * C::FLOATING + C::NJ + j] = S[C::oU + 6 * C::FLOATING + j];
+            }
+        }
+        return;
+    }
+    if (mode == MODE_SET) {
+        const float *cs = B.canon + env * C::CANON;
+        if (C::FLOATING) {
+            if (gl < 7) S[gl] = cs[gl];
+            if (gl < 6) S[C::oU + gl] = cs[7 + gl];
+        }
+        for (int j = gl; j < C::NJ; j += C::LPE) {
+            S[C::oQ + j] = cs[13 * C::FLOATING + j];
+            S[C::oU + 6 * C::FLOATING + j] = cs[13 * C::FLOATING + C::NJ + j];
+        }
+        for (int i = gl; i < C::NSLOT; i += C::LPE) S[C::oW + i] = 0.f;
+        __syncwarp();
+        if (valid) for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
+            reinterpret_cast<float4 *>(gs)[i] = reinterpret_cast<const float4 *>(S)[i];
+        return;
+    }
+
+    const float *act = B.actions ? B.actions + env * C::NACT : nullptr;
+    float *obs = B.obs ? B.obs + env * C::OBS : nullptr;
+    // outputs are staged in shared memory, then written by consecutive lanes
+    float *so = e.sm + C::sOUT;
+    float *so_obs = so, *so_rew = so + 64, *so_terms = so + 65;
+
+    if (mode == MODE_RESET) {
+        const bool doit = !B.mask || B.mask[env];
+        e.reset_state(la, genv, B.noise ? B.noise + env * C::NACT : nullptr, la.floor_in_parts, doit);
+        // envs that are not reset only get their observation refreshed
+        e.task(nullptr, so_obs, nullptr, nullptr, doit, true);
+        __syncwarp();
+        if (valid) {
+            if (obs) for (int i = gl; i < C::OBS; i += C::LPE) obs[i] = so_obs[i];
+            if (doit) for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
+                reinterpret_cast<float4 *>(gs)[i] = reinterpret_cast<const float4 *>(S)[i];
+        }
+        return;
+    }
+
+    if (mode == MODE_STEP || mode == MODE_PHYSICS) {
+        // apply_action: tau = power * power_coef * clip(a, -1, 1) (rs/robot_locomotors.py:26-29),
+        // plus the joint damping torque, both held for all substeps
+        float tq = 0.f;
+        if (gl >= 6 * C::FLOATING && gl < C::ND) {
+            const int j = gl - 6 * C::FLOATING;
+            tq = -model->jdamp[j] * S[C::oU + gl];
+            const int ai = model->jact[j];
+            if (ai >= 0) tq += model->jtorque[j] * fminf(fmaxf(act[ai], -1.f), 1.f);
+        }
+        e.tau = tq;
+        const int nsub = model->nsub;
+        for (int s = 0; s < nsub; ++s) e.substep(s == nsub - 1);
+    }
+    if (mode == MODE_PHYSICS) {
+        if (valid) {
+            for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
+                reinterpret_cast<float4 *>(gs)[i] = reinterpret_cast<const float4 *>(S)[i];
+            if (B.ncontact_out && gl == 0) B.ncontact_out[env] = e.nc;
+        }
+        return;
+    }
+
+    // ---- task layer.  calc_state must still see the previous step's feet flags (quirk Q2: the
+    // reference updates robot.feet_contact after calc_state / alive_bonus); this step's flags were
+    // staged by the last substep's collide() and replace them afterwards.
+    if (mode == MODE_OBSERVE) e.nc = 0;
+    bool done = e.task(act, so_obs, so_rew, so_terms, false);
+    if (mode == MODE_STEP && C::MAXC > 0 && gl < C::NFEET) S[C::oF + gl] = e.sm[C::sMISC + gl];
+    __syncwarp();
+    bool trunc = false;
+    if (mode == MODE_STEP) {
+        if (gl == 0) {
+            const int steps = __float_as_int(T[T_STEPS]) + 1;
+            T[T_STEPS] = __int_as_float(steps);
+            T[T_RETURN] += so_rew[0];
+        }
+        __syncwarp();
+        trunc = !done && __float_as_int(T[T_STEPS]) >= model->max_steps;
+    }
+    const bool finished = done || trunc;
+    if (valid && gl == 0) {
+        if (B.reward) B.reward[env] = so_rew[0];
+        if (B.done) B.done[env] = (done || (trunc && la.auto_reset)) ? 1 : 0;
+        if (B.truncated) B.truncated[env] = trunc ? 1 : 0;
+    }
+    if (valid && B.terms) { if (gl < 5) B.terms[env * 5 + gl] = so_terms[gl]; }
+    if (valid && B.feet_out) { if (gl < C::NFEET) B.feet_out[env * C::NFEET + gl] = S[C::oF + gl]; }
+    if (valid && B.ncontact_out && gl == 0) B.ncontact_out[env] = e.nc;
+    if (mode == MODE_STEP && finished) {
+        if (valid && gl == 0 && B.stats) {
+            atomicAdd(&B.stats[0], 1ull);
+            atomicAdd(&B.stats[1], (unsigned long long)__float_as_int(T[T_STEPS]));
+            atomicAdd(reinterpret_cast<double *>(&B.stats[2]), (double)T[T_RETURN]);
+            if (trunc) atomicAdd(&B.stats[3], 1ull);
+            if (T[T_HAVEZ] == 2.f) atomicAdd(&B.stats[4], 1ull);
+        }
+        if (la.auto_reset && valid && B.final_obs)
+            for (int i = gl; i < C::OBS; i += C::LPE) B.final_obs[env * C::OBS + i] = so_obs[i];
+    }
+    // in-kernel reset: the whole warp runs it when any of its envs finished, predicated per group
+    const bool do_reset = mode == MODE_STEP && finished && la.auto_reset;
+    if (__any_sync(0xffffffffu, do_reset)) {
+        __syncwarp();
+        e.reset_state(la, genv, nullptr, 1, do_reset);
+        e.task(nullptr, so_obs, nullptr, nullptr, true, do_reset);
+    }
+    __syncwarp();
+    if (valid) {
+        if (obs) for (int i = gl; i < C::OBS; i += C::LPE) obs[i] = so_obs[i];
+        if (mode == MODE_STEP)
+            for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
+                reinterpret_cast<float4 *>(gs)[i] = reinterpret_cast<const float4 *>(S)[i];
+    }
+}
+
+}  // namespace pbg

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Generate tests/golden/task_<env>.json by running the reference's UNMODIFIED Python task layer.
+
+The reference modules under /root/reference/pybulletgym/envs/roboschool/ are imported as they are,
+on top of the stub pybullet client of tools/fake_pybullet.py (physics = our CPU oracle).  What gets
+recorded is everything the reference computes *above* the pybullet boundary for a scripted rollout:
+
+  per episode : the reset noise the reference drew (np_random.uniform log), the reset observation
+  per step    : action, physics state after the step (canonical layout), observation, reward,
+                done, the reward-term list `env.rewards`, robot.feet_contact, joints_at_limit
+
+tests/test_golden_task.py replays the same noise/actions through the C oracle (whose physics is
+the same code, so states agree bit for bit) and requires the oracle's task layer to reproduce the
+reference's numbers; this pins SURVEY.md Appendix A incl. quirks Q1-Q3, Q6, Q10 to reference source.
+
+Run in the build container only (needs /root/reference).  Usage: python tools/gen_golden_task.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import fake_pybullet as fp  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(HERE, "..", "tests", "golden")
+
+CASES = {
+    # env id -> (module, class, episodes, max steps per episode, action scale)
+    "InvertedPendulumPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedPendulumBulletEnv", 3, 40, 1.0),
+    "InvertedPendulumSwingupPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedPendulumSwingupBulletEnv", 2, 40, 1.0),
+    "HopperPyBulletEnv-v0": ("gym_locomotion_envs", "HopperBulletEnv", 4, 40, 1.3),
+    "Walker2DPyBulletEnv-v0": ("gym_locomotion_envs", "Walker2DBulletEnv", 4, 40, 1.3),
+    "HalfCheetahPyBulletEnv-v0": ("gym_locomotion_envs", "HalfCheetahBulletEnv", 4, 40, 1.3),
+    "AntPyBulletEnv-v0": ("gym_locomotion_envs", "AntBulletEnv", 3, 60, 1.3),
+    "HumanoidPyBulletEnv-v0": ("gym_locomotion_envs", "HumanoidBulletEnv", 3, 40, 1.3),
+}
+
+
+def main():
+    from pybullet_gym_b200.spec import SPECS
+    fp.install()
+    sys.path.insert(0, REF)
+    import importlib
+    os.makedirs(OUT, exist_ok=True)
+    for env_id, (mod, cls, episodes, max_steps, ascale) in CASES.items():
+        spec = SPECS[env_id]
+        fp.FakeBulletClient.current_spec = spec
+        fp.FakeBulletClient.max_contacts = 0
+        m = importlib.import_module("pybulletgym.envs.roboschool." + mod)
+        import io
+        import contextlib
+        with contextlib.redirect_stdout(io.StringIO()):     # the reference prints "WalkerBase::__init__"
+            env = getattr(m, cls)()
+        # gym.make() patches reset/step/seed to the most-derived _reset/_step/_seed
+        # (gym.envs.registration.patch_deprecated_methods); call those directly
+        env._seed(1234)
+        rng = np.random.RandomState(99)
+        nA = env.action_space.shape[0]
+        eps = []
+        for ep in range(episodes):
+            nlog = len(env.np_random.log)
+            obs0 = env._reset()
+            draws = env.np_random.log[nlog:]
+            noise = [d[3][0] for d in draws if d[0] == "uniform"]
+            rec = {"noise": noise, "obs0": np.asarray(obs0, dtype=np.float64).tolist(), "steps": []}
+            for t in range(max_steps):
+                a = (ascale * rng.uniform(-1, 1, nA)).astype(np.float64)   # |a| > 1 exercises quirk Q3
+                obs, rew, done, info = env._step(a)
+                st = {"a": a.tolist(), "state": env._p.orc.get_state().tolist(),
+                      "obs": np.asarray(obs, dtype=np.float64).tolist(), "reward": float(rew), "done": bool(done),
+                      "rewards": [float(r) for r in env.rewards]}
+                if hasattr(env.robot, "feet_contact"):
+                    st["feet_contact"] = [float(f) for f in env.robot.feet_contact]
+                    st["joints_at_limit"] = int(env.robot.joints_at_limit)
+                    st["body_xyz"] = [float(v) for v in env.robot.body_xyz]
+                rec["steps"].append(st)
+                if done:
+                    break
+            eps.append(rec)
+        calls = dict(env._p.calls)
+        out = {"env_id": env_id, "reference_class": "pybulletgym.envs.roboschool.%s:%s" % (mod, cls),
+               "parts": sorted(env.robot.parts.keys()), "ordered_joints": [j.joint_name for j in env.robot.ordered_joints],
+               "episodes": eps}
+        path = os.path.join(OUT, "task_%s.json" % env_id.split("PyBullet")[0])
+        with open(path, "w") as f:
+            json.dump(out, f)
+        nsteps = sum(len(e["steps"]) for e in eps)
+        print("%-40s episodes=%d steps=%d parts=%d calls/step=%.1f -> %s" % (
+            env_id, episodes, nsteps, len(out["parts"]),
+            sum(v for k, v in calls.items()) / max(1, calls.get("stepSimulation", 1)), os.path.basename(path)))
+
+
+if __name__ == "__main__":
+    main()
