@@ -170,6 +170,10 @@ int pbg_max_contacts(int kind);
 
 int pbg_stats(pbg_handle *h, pbg_episode_stats *out_host, int32_t reset);
 
+/* Measures the FP32 CUDA-core peak of `device` with an FFMA microbenchmark (TFLOP/s); the roofline
+ * denominator MEASURED_PEAKS.json does not carry. */
+int pbg_measure_fp32_peak(int32_t device, double *tflops_out);
+
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t pbg_launch_count(const pbg_handle *h);
 

@@ -122,6 +122,7 @@ def lib():
     L.pbg_observe.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.pbg_get_feet_contact.argtypes = [vp, vp, vp]
     L.pbg_stats.argtypes = [vp, C.POINTER(PbgEpisodeStats), C.c_int32]
+    L.pbg_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     L.pbg_launch_count.argtypes = [vp]
     L.pbg_launch_count.restype = C.c_int64
     _lib = L
@@ -131,7 +132,7 @@ def lib():
 EXPORTS = ["pbg_version", "pbg_create", "pbg_destroy", "pbg_last_error", "pbg_num_envs", "pbg_obs_dim",
            "pbg_action_dim", "pbg_state_dim", "pbg_reset", "pbg_reset_with", "pbg_step", "pbg_step_host",
            "pbg_set_auto_reset", "pbg_get_state", "pbg_set_state", "pbg_physics_step", "pbg_physics_step_counts",
-           "pbg_max_contacts", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count"]
+           "pbg_max_contacts", "pbg_measure_fp32_peak", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count"]
 
 
 def _d(a):

@@ -425,6 +425,50 @@ int pbg_physics_step_counts(pbg_handle *h, const float *actions_dev, int32_t *nc
     return launch(h, MODE_PHYSICS, b, 1, stream);
 }
 
+// FP32 CUDA-core peak of the device the way the roofline needs it: dependent-free FFMA chains,
+// 8 per thread, full occupancy.  2 flops per FFMA.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, float seed) {
+    float a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const float b = 1.0000001f, c = 1e-9f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    const float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 12345.678f) out[0] = r;
+}
+
+int pbg_measure_fp32_peak(int32_t device, double *tflops_out) {
+    if (!tflops_out) return PBG_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return PBG_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PBG_ERR_CUDA;
+    float *buf = nullptr;
+    if (cudaMalloc(&buf, 16) != cudaSuccess) return PBG_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<<<blocks, threads>>>(buf, iters, 0.5f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * iters * double(blocks) * threads;
+        if (rep > 0 && ms > 0) best = std::fmax(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (cudaGetLastError() != cudaSuccess) return PBG_ERR_CUDA;
+    *tflops_out = best;
+    return PBG_OK;
+}
+
 int pbg_stats(pbg_handle *h, pbg_episode_stats *out, int32_t reset) {
     if (!h || !out) return fail(h, PBG_ERR_INVALID, "pbg_stats: NULL argument");
     CUDA_TRY(h, cudaSetDevice(h->device));

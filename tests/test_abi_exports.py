@@ -1,0 +1,64 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/pbg.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "pbg.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(pbg_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pybullet_gym_b200 import _lib
+    _lib.build_extension()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), "libpbg_b200.so does not export %s" % s
+    assert L.pbg_version() == 100
+    assert sorted(_lib.EXPORTS) == syms
+
+
+def test_model_tables_fit_their_kernels():
+    """pbg_create's host-side checks accept the tables of every backed env (create fails later, at the first
+    CUDA call, on a box without a GPU -- with an error code, not a crash)."""
+    from pybullet_gym_b200 import _lib
+    from pybullet_gym_b200.spec import SPECS
+    L = _lib.lib()
+    for env_id, spec in SPECS.items():
+        if spec.kind >= 7:
+            continue
+        t = _lib.ModelTables(spec)
+        h = ctypes.c_void_p()
+        rc = L.pbg_create(ctypes.byref(t.c), 8, 0, 0, 0, ctypes.byref(h))
+        if rc == 0:
+            L.pbg_destroy(h)
+        else:
+            assert rc == -2, (env_id, rc, L.pbg_last_error(None))     # PBG_ERR_CUDA: no device here
+        t.c.max_contacts += 1
+        assert L.pbg_create(ctypes.byref(t.c), 8, 0, 0, 0, ctypes.byref(h)) == -1   # PBG_ERR_INVALID
+        assert b"max_contacts" in L.pbg_last_error(None)
+
+
+def test_no_cpu_fallback():
+    import torch
+    from pybullet_gym_b200 import _lib
+    from pybullet_gym_b200.vector_env import VectorEnv
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.BackendUnavailable):
+        VectorEnv("AntPyBulletEnv-v0", 4)
+
+
+def test_unbacked_ids_raise():
+    from pybullet_gym_b200.envs import make, registry
+    assert "AntPyBulletEnv-v0" in registry and registry["AntPyBulletEnv-v0"]["max_episode_steps"] == 1000
+    with pytest.raises(NotImplementedError):
+        make("ReacherPyBulletEnv-v0")
