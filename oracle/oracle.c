@@ -168,6 +168,8 @@ struct orc_env {
     double walk_target_x, walk_target_y, walk_target_dist;
     double torso_speed[3];
     row rows[MAXROWS];
+    int last_nlim, last_nr;
+    double last_dv[MAXU], last_ufree[MAXU], last_u0[MAXU];
 };
 
 int orc_num_dofs(const orc_model *m) {
@@ -653,6 +655,7 @@ static int build_rows(orc_env *e, double h) {
 
 static void solve_rows(orc_env *e, int packed) {
     int nlim = packed >> 16, nr = packed & 0xffff, nu = e->nu;
+    e->last_nlim = nlim; e->last_nr = nr;
     int nnrm = e->nct, nrm0 = nlim, fr0 = nlim + nnrm;
     double dv[MAXU];
     for (int k = 0; k < nu; k++) dv[k] = 0;
@@ -675,6 +678,7 @@ static void solve_rows(orc_env *e, int packed) {
         }
     }
 #undef RESOLVE
+    for (int k = 0; k < nu; k++) e->last_dv[k] = dv[k];
     add_u(e, dv, 1.0);
     for (int c = 0; c < e->nct; c++) e->warm[e->ct[c].slot] = e->rows[nrm0 + c].lambda;
 }
@@ -702,7 +706,9 @@ static void substep(orc_env *e) {
     velocities(e);
     collide(e);
     articulated_inertias(e);
+    get_u(e, e->last_u0);
     forward_dynamics(e, h);
+    get_u(e, e->last_ufree);
     velocities(e);
     int packed = build_rows(e, h);
     solve_rows(e, packed);
@@ -922,6 +928,14 @@ int orc_get_contacts(const orc_env *e, int32_t *la, int32_t *lb, double *dist) {
 void orc_set_joint(orc_env *e, int dof, double q, double qd) { e->q[dof] = q; e->qd[dof] = qd; }
 void orc_get_joint(const orc_env *e, int dof, double *q, double *qd) { *q = e->q[dof]; *qd = e->qd[dof]; }
 
+/* rows of the last substep: out = [nlim, nct, then per row rhs, dinv, lambda]; returns the row count */
+int orc_get_rows(const orc_env *e, double *out) {
+    int nlim = e->last_nlim, nr = e->last_nr;
+    out[0] = nlim; out[1] = e->nct;
+    for (int i = 0; i < nr; i++) { out[2 + 3 * i] = e->rows[i].rhs; out[3 + 3 * i] = e->rows[i].dinv; out[4 + 3 * i] = e->rows[i].lambda; }
+    return nr;
+}
+void orc_get_debug(const orc_env *e, double *out) { for (int k = 0; k < e->nu; k++) { out[k] = e->last_u0[k]; out[64 + k] = e->last_ufree[k]; out[128 + k] = e->last_dv[k]; } }
 int orc_num_contacts(const orc_env *e) { return e->nct; }
 void orc_feet_contact(const orc_env *e, double *out) { for (int f = 0; f < e->m.nfeet; f++) out[f] = e->feet_contact[f]; }
 void orc_link_com(orc_env *e, double *out) { fk(e); for (int i = 0; i < e->m.nl; i++) for (int k = 0; k < 3; k++) out[3 * i + k] = e->c[i][k]; }

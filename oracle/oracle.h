@@ -91,6 +91,7 @@ int orc_get_contacts(const orc_env *e, int32_t *la, int32_t *lb, double *dist);
 void orc_set_joint(orc_env *e, int dof, double q, double qd);
 void orc_get_joint(const orc_env *e, int dof, double *q, double *qd);
 /* diagnostics */
+int orc_get_rows(const orc_env *e, double *out);
 int orc_num_contacts(const orc_env *e);
 void orc_feet_contact(const orc_env *e, double *out);
 void orc_link_com(orc_env *e, double *xyz_out /* [nl*3] */);

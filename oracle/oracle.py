@@ -93,6 +93,9 @@ def lib():
         L.orc_get_contacts.restype = C.c_int
         L.orc_set_joint.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         L.orc_get_joint.argtypes = [C.c_void_p, C.c_int, _pd, _pd]
+        L.orc_get_rows.argtypes = [C.c_void_p, _pd]
+        L.orc_get_rows.restype = C.c_int
+        L.orc_get_debug.argtypes = [C.c_void_p, _pd]
         L.orc_rollout.argtypes = [C.c_void_p, C.c_long, C.c_uint64, _pd, C.POINTER(C.c_long)]
         L.orc_rollout.restype = C.c_long
         _lib = L
@@ -257,6 +260,17 @@ class OracleEnv:
         q, qd = C.c_double(0), C.c_double(0)
         lib().orc_get_joint(self._h, int(dof), C.byref(q), C.byref(qd))
         return q.value, qd.value
+
+    def rows(self):
+        out = np.zeros(2 + 3 * 256)
+        n = lib().orc_get_rows(self._h, out.ctypes.data_as(_pd))
+        return int(out[0]), int(out[1]), out[2:2 + 3 * n].reshape(n, 3)
+
+    def debug(self):
+        out = np.zeros(192)
+        lib().orc_get_debug(self._h, out.ctypes.data_as(_pd))
+        n = self.model.nu
+        return out[:n], out[64:64 + n], out[128:128 + n]
 
     def num_contacts(self):
         return lib().orc_num_contacts(self._h)

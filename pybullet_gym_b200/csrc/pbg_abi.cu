@@ -66,6 +66,7 @@ struct pbg_handle {
     cudaStream_t hstream = nullptr;
     unsigned long long seed = 0, env_offset = 0;
     int auto_reset = 1;
+    int debug_env = 0;
     int64_t launches = 0;
     int64_t steps = 0;
     std::string err;
@@ -318,7 +319,7 @@ static int launch(pbg_handle *h, int mode, StepBuffers &b, int floor_in_parts, v
     b.stats = h->stats;
     LaunchArgs la;
     la.E = h->E; la.mode = mode; la.auto_reset = h->auto_reset; la.floor_in_parts = floor_in_parts;
-    la.seed = h->seed; la.env_offset = h->env_offset;
+    la.seed = h->seed; la.env_offset = h->env_offset; la.debug_env = h->debug_env;
     h->k.launch(h->dmodel, b, la, (cudaStream_t)stream);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
@@ -416,6 +417,16 @@ int pbg_get_feet_contact(pbg_handle *h, float *out_dev, void *stream) {
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
     return PBG_OK;
+}
+
+// development hook (not part of include/pbg.h): physics step that dumps the constraint rows of env
+// `env` in its last substep: [nl, nc, then per row rhs, 1/A_ii, lambda, residual]
+int pbg_dev_physics_step_rows(pbg_handle *h, const float *actions_dev, int32_t env, float *dbg_dev, void *stream) {
+    if (!h || !actions_dev) return PBG_ERR_INVALID;
+    StepBuffers b{};
+    b.actions = actions_dev; b.debug = dbg_dev;
+    h->debug_env = env;
+    return launch(h, MODE_PHYSICS, b, 1, stream);
 }
 
 int pbg_physics_step_counts(pbg_handle *h, const float *actions_dev, int32_t *ncontact_dev, void *stream) {

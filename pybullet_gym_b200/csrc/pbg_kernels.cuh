@@ -142,6 +142,7 @@ struct Env {
     unsigned up, down;
     float tau;          // joint force of this dof for the current env step
     int nc, nl;         // active contacts / limit rows of this env (group-uniform)
+    float *dbg;         // optional debug dump of the constraint rows (development only)
 
     static constexpr unsigned FULL = 0xffffffffu;
 
@@ -175,7 +176,7 @@ struct Env {
         for (int i = 0; i < 6; ++i) Ib[i] = m->inertia[b][i];
         const int k = gl < C::ND ? gl : 0;
         up = m->up[k]; down = m->down[k];
-        tau = 0.f; nc = 0; nl = 0;
+        tau = 0.f; nc = 0; nl = 0; dbg = nullptr;
     }
 
     // ---------------------------------------------------------------- forward kinematics
@@ -367,6 +368,17 @@ struct Env {
         __syncwarp();
     }
 
+    // x = L^-T g, lane k holds g_k / x_k (one shuffle per column)
+    __device__ __forceinline__ float backsolve(float g, const float *Lm, const float *inv) const {
+#pragma unroll
+        for (int k = C::ND - 1; k >= 0; --k) {
+            const float xk = shfl(g, k) * inv[k];
+            if (gl == k) g = xk;
+            else if (gl < k) g -= Lm[k * C::LST + gl] * xk;
+        }
+        return g;
+    }
+
     // ---------------------------------------------------------------- dynamics of one substep
     __device__ void substep(bool last) {
         const float h = m->h;
@@ -513,7 +525,19 @@ struct Env {
             for (int c = 0; c < C::ND; ++c) Lm[gl * C::LST + c] = Mr[c];
         }
         __syncwarp();
-        const float *yf = Lm + C::ND * C::LST;     // y_f = L^-1 f
+        float *u = uvec();
+        {
+            // free acceleration qdd = L^-T y_f (y_f = L^-1 f is the augmented row), then
+            // u <- clamp(u + h qdd): btMultiBody::applyDeltaVeeMultiDof clamps every generalized
+            // velocity to +-maxCoordinateVelocity right here, before the constraint rows are built
+            float g = (gl < C::ND) ? Lm[C::ND * C::LST + gl] : 0.f;
+            g = backsolve(g, Lm, inv);
+            if (gl < C::ND) {
+                const float mv = m->maxvel;
+                u[gl] = fminf(fmaxf(u[gl] + h * g, -mv), mv);
+            }
+        }
+        __syncwarp();
 
         // --- joint limit rows (lane = joint): a side is a row only while violated (C4.4)
         float *lim = sm + C::sLIM;
@@ -542,7 +566,6 @@ struct Env {
         float *Am = sm + C::sA;
         float *lam = sm + C::sLAM;
         float *warm = S + C::oW;
-        float *u = uvec();
         float rhs[2], dinv[2], lo[2], hi[2], lmb[2], mu[2], Yr[2][C::ND];
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
@@ -608,10 +631,9 @@ struct Env {
                 for (int mm = 0; mm < k; ++mm) sacc -= Lm[k * C::LST + mm] * J[mm];
                 J[k] = sacc * inv[k];
             }
-            float dd = 0.f, yy = 0.f;
+            float dd = 0.f;
 #pragma unroll
-            for (int k = 0; k < C::ND; ++k) { dd += J[k] * J[k]; yy += J[k] * yf[k]; Yr[sl][k] = J[k]; }
-            rel += h * yy;                         // J (u + h qdd)
+            for (int k = 0; k < C::ND; ++k) { dd += J[k] * J[k]; Yr[sl][k] = J[k]; }
             const float di = dd > 1e-12f ? 1.f / dd : 0.f;
             dinv[sl] = di;
             const float ih = 1.f / h;
@@ -697,23 +719,21 @@ struct Env {
             const int i = sl * C::LPE + gl;
             if (i < nr && i < C::MAXR) {
                 lam[i] = lmb[sl];
+                if (dbg) {
+                    dbg[0] = (float)nl; dbg[1] = (float)nc;
+                    dbg[2 + 4 * i] = rhs[sl]; dbg[3 + 4 * i] = dinv[sl]; dbg[4 + 4 * i] = lmb[sl]; dbg[5 + 4 * i] = r[sl];
+                }
                 if (i >= nl && i < nl + nc) warm[__float_as_int(sm[C::sCT + (i - nl) * C::CTS + 2])] = lmb[sl];
             }
         }
         __syncwarp();
 
-        // --- du = L^-T (h y_f + Y^T lambda)   (lane = dof)
+        // --- du = L^-T (Y^T lambda)   (lane = dof), second clamp (btMultiBody::processDeltaVeeMultiDof2)
         float g = 0.f;
         if (gl < C::ND) {
-            g = h * yf[gl];
             for (int i = 0; i < nr; ++i) g += Ym[i * C::LST + gl] * lam[i];
         }
-#pragma unroll
-        for (int k = C::ND - 1; k >= 0; --k) {
-            const float xk = shfl(g, k) * inv[k];
-            if (gl == k) g = xk;
-            else if (gl < k) g -= Lm[k * C::LST + gl] * xk;
-        }
+        if (wmax(nr) > 0) g = backsolve(g, Lm, inv);
         __syncwarp();
         if (gl < C::ND) {
             const float mv = m->maxvel;
@@ -783,13 +803,12 @@ struct Env {
         const V3 toff = mulR(kt, ld3(m->torso_off));
         const float z = kt[11] + toff.z;
         const V3 tsp = ld3(kt + 15) + cross(ld3(kt + 12), toff);
-        float tq[4];
-        mat2quat(kt, tq);
-        const float qx = tq[0], qy = tq[1], qz = tq[2], qw = tq[3];
-        const float sarg = -2.f * (qx * qz - qw * qy);
-        const float roll = atan2f(2.f * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
-        const float pitch = sarg <= -1.f ? -0.5f * CUDART_PI_F : (sarg >= 1.f ? 0.5f * CUDART_PI_F : asinf(sarg));
-        const float yaw = atan2f(2.f * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
+        // getEulerFromQuaternion(torso orientation) (rs/robot_bases.py:216-217) taken straight from the
+        // rotation matrix: roll = atan2(R21, R22), pitch = asin(-R20), yaw = atan2(R10, R00).  The pitch
+        // uses atan2(-R20, sqrt(R00^2 + R10^2)): identical value, but well conditioned in fp32 near +-pi/2.
+        const float roll = atan2f(kt[7], kt[8]);
+        const float pitch = atan2f(-kt[6], sqrtf(kt[0] * kt[0] + kt[3] * kt[3]));
+        const float yaw = atan2f(kt[3], kt[0]);
         float initz = T[T_INITZ];
         if (reset_pass) {
             initz = m->initial_z >= 0.f ? m->initial_z : z;
@@ -932,6 +951,7 @@ __global__ void __launch_bounds__(C::THREADS) env_kernel(const DevModel *__restr
     const unsigned long long genv = la.env_offset + (unsigned long long)env;
     const int gl = e.gl;
     e.load_lane_constants();
+    if (B.debug && env_raw == la.debug_env) e.dbg = B.debug;
 
     float *S = e.st();
     float *gs = B.state + env * C::SSTRIDE;

@@ -67,6 +67,7 @@ struct StepBuffers {
     int *ncontact_out;        // [E] optional
     unsigned long long *stats;  // [8] device episode statistics
     float *canon;             // [E, state_dim] for get/set state
+    float *debug;             // development: constraint-row dump of env `debug_env`
 };
 
 enum { MODE_STEP = 0, MODE_PHYSICS = 1, MODE_OBSERVE = 2, MODE_RESET = 3, MODE_GET = 4, MODE_SET = 5 };
@@ -77,6 +78,7 @@ struct LaunchArgs {
     int auto_reset;
     int floor_in_parts;
     unsigned long long seed, env_offset;
+    int debug_env;
 };
 
 }  // namespace pbg

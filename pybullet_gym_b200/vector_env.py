@@ -32,14 +32,14 @@ class VectorEnv:
     """
 
     def __init__(self, env_id: str, num_envs: int, device: Optional[torch.device | int | str] = None, seed: int = 0,
-                 env_offset: int = 0, auto_reset: bool = True, rules=None):
+                 env_offset: int = 0, auto_reset: bool = True, rules=None, spec: Optional[EnvSpec] = None):
         if env_id in UNBACKED_IDS:
             raise NotImplementedError("%s is registered by the reference but not implemented on this backend" % env_id)
         if env_id not in SPECS:
             raise KeyError("unknown env id %r" % env_id)
         if not torch.cuda.is_available():
             raise _lib.BackendUnavailable("VectorEnv needs a CUDA device (no CPU fallback)")
-        self.spec: EnvSpec = SPECS[env_id]
+        self.spec: EnvSpec = spec if spec is not None else SPECS[env_id]
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != "cuda":
             raise _lib.BackendUnavailable("VectorEnv needs a CUDA device (no CPU fallback)")
