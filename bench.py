@@ -152,7 +152,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     E, K, W = args.envs, args.steps, max(args.warmup, 3)
-    env = VectorEnv(args.env, E, device=dev, seed=0, env_offset=rank * E, auto_reset=True)
+    from pybullet_gym_b200.sharding import shard
+    env_offset, _ = shard(rank, world, E)
+    env = VectorEnv(args.env, E, device=dev, seed=0, env_offset=env_offset, auto_reset=True)
     nA, D = env.action_dim, env.obs_dim
     env.reset()
     gen = torch.Generator(device=dev).manual_seed(rank)
@@ -210,15 +212,13 @@ def run_ours(args):
     t_e2e = time.perf_counter() - t0
     barrier()
 
+    from pybullet_gym_b200 import sharding
+
     def maxr(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(x, device=dev)
 
     t_flushed, t_resident, t_e2e = maxr(t_flushed), maxr(t_resident), maxr(t_e2e)
-    stats = env.stats()
+    stats = sharding.reduce_stats(env.stats(), device=dev)
     if rank == 0:
         peaks = {}
         try:

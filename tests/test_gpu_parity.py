@@ -1,0 +1,253 @@
+"""CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.  Run with -m gpu.
+
+Tiers (BASELINE.json north_star):
+  T1  calc_state / reward given identical state ............ 1e-5 abs (progress: 2e-5 * (1 + |x|), fp32 FK)
+  T2  single sub-step / single env step from identical state  stated below per quantity
+  T3  contact-free pendulum trajectory over a full episode . stated below
+  T4  contact envs: random-policy return / length distributions, two-sample KS, p > 0.01
+The oracle's physics is parity-unpinned against pybullet (oracle/oracle.h); its task layer is pinned
+by tests/test_golden_task.py.
+
+Why T2 uses quantiles for contact states: the dynamics themselves amplify a 1e-7 (fp32 storage)
+perturbation of the state into up to ~4e-3 after one env step when stiff contacts / friction-cone
+switches are active (measured on the double-precision oracle in test_oracle_sensitivity_reference),
+so a max-norm bound at fp32 round-off level is not meaningful there; contact-free steps are held to
+1e-4 in max norm.
+"""
+import dataclasses
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+IDS = ["InvertedPendulumPyBulletEnv-v0", "HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
+       "AntPyBulletEnv-v0", "HumanoidPyBulletEnv-v0"]
+E = 48
+
+
+def _mk(env_id, n=E, spec=None, auto_reset=False, seed=1):
+    from pybullet_gym_b200.vector_env import VectorEnv
+    return VectorEnv(env_id, n, device="cuda:0", seed=seed, auto_reset=auto_reset, spec=spec)
+
+
+def _oracles(oracle_lib, env_id, n, spec=None):
+    from pybullet_gym_b200 import _lib
+    from pybullet_gym_b200.spec import SPECS
+    mc = _lib.lib().pbg_max_contacts(SPECS[env_id].kind)
+    return [oracle_lib.OracleEnv(spec if spec is not None else env_id, max_contacts=mc) for _ in range(n)]
+
+
+def _rel(g, o):
+    return np.abs(g - o) / (1.0 + np.abs(o))
+
+
+@pytest.mark.parametrize("env_id", IDS)
+def test_reset_matches_oracle(env_id, oracle_lib):
+    env = _mk(env_id)
+    rng = np.random.default_rng(0)
+    noise = rng.uniform(-0.1, 0.1, (E, env.action_dim)).astype(np.float32)
+    for floor in (False, True):
+        obs = env.reset(joint_noise=torch.from_numpy(noise), floor_in_parts=floor).cpu().numpy()
+        orcs = _oracles(oracle_lib, env_id, E)
+        oobs = np.stack([o.reset(noise=noise[i].astype(np.float64), floor_in_parts=floor) for i, o in enumerate(orcs)])
+        assert np.abs(obs - oobs).max() < 1e-5
+        st = env.get_state().cpu().numpy()
+        ost = np.stack([o.get_state() for o in orcs])
+        assert np.abs(st - ost).max() < 1e-6
+
+
+@pytest.mark.parametrize("env_id", IDS)
+def test_device_rng_matches_oracle_rng(env_id, oracle_lib):
+    """pbg_reset's Philox draws are bit-identical to the oracle's (same seed / env index / episode)."""
+    env = _mk(env_id, n=8, seed=7)
+    obs = env.reset(floor_in_parts=True).cpu().numpy()
+    for i in range(8):
+        o = oracle_lib.OracleEnv(env_id, seed=7, env_index=i)
+        assert np.abs(o.reset(floor_in_parts=True) - obs[i]).max() < 1e-5
+
+
+@pytest.mark.parametrize("env_id", IDS)
+def test_observation_reward_parity_T1(env_id, oracle_lib):
+    """T1: calc_state + reward terms on identical states, states sampled along oracle rollouts."""
+    env = _mk(env_id)
+    rng = np.random.default_rng(3)
+    nA = env.action_dim
+    noise = rng.uniform(-0.1, 0.1, (E, nA)).astype(np.float32)
+    env.reset(joint_noise=torch.from_numpy(noise), floor_in_parts=True)
+    orcs = _oracles(oracle_lib, env_id, E)
+    for i, o in enumerate(orcs):
+        o.reset(noise=noise[i].astype(np.float64), floor_in_parts=True)
+    worst_obs = worst_terms = worst_prog = 0.0
+    for t in range(30):
+        a = (1.4 * rng.uniform(-1, 1, (E, nA))).astype(np.float32)          # |a| > 1: quirk Q3
+        # advance both on their own physics (keeps feet flags / potentials in step), then pin the state
+        env.physics_step(torch.from_numpy(a))
+        for i, o in enumerate(orcs):
+            o.physics_step(a[i].astype(np.float64))
+        ost = np.stack([o.get_state() for o in orcs]).astype(np.float32)
+        env.set_state(torch.from_numpy(ost))
+        for i, o in enumerate(orcs):
+            o.set_state(ost[i].astype(np.float64))
+        gobs, grew, gdone, gterms = [x.cpu().numpy() for x in env.observe(torch.from_numpy(a))]
+        res = [o.observe(a[i].astype(np.float64)) for i, o in enumerate(orcs)]
+        oobs = np.stack([r[0] for r in res])
+        oterms = np.stack([r[3] for r in res])
+        odone = np.array([r[2] for r in res])
+        nf = len(env.spec.foot_list)
+        body = slice(0, oobs.shape[1] - nf) if nf else slice(None)
+        worst_obs = max(worst_obs, np.abs(gobs[:, body] - oobs[:, body]).max())
+        worst_terms = max(worst_terms, np.abs(gterms[:, [0, 2, 3, 4]] - oterms[:, [0, 2, 3, 4]]).max())
+        if env.spec.kind >= 2:
+            x = np.abs(ost[:, 0] if env.spec.kind >= 5 else ost[:, 0])
+            worst_prog = max(worst_prog, (np.abs(gterms[:, 1] - oterms[:, 1]) / (1.0 + x)).max())
+            # alive / done decisions agree except within float32 round-off of a threshold
+            assert (gdone.astype(bool) != odone).mean() <= 0.05
+    assert worst_obs < 1e-5, worst_obs
+    assert worst_terms < 1e-5, worst_terms
+    assert worst_prog < 2e-5, worst_prog
+
+
+@pytest.mark.parametrize("env_id", IDS)
+def test_single_substep_and_step_parity_T2(env_id, oracle_lib):
+    from pybullet_gym_b200.spec import SPECS
+    spec = SPECS[env_id]
+    spec1 = dataclasses.replace(spec, scene=dataclasses.replace(spec.scene, frame_skip=1))
+    env4, env1 = _mk(env_id), _mk(env_id, spec=spec1)
+    rng = np.random.default_rng(5)
+    nA = env4.action_dim
+    noise = rng.uniform(-0.1, 0.1, (E, nA)).astype(np.float32)
+    env4.reset(joint_noise=torch.from_numpy(noise)); env1.reset(joint_noise=torch.from_numpy(noise))
+    orcs = _oracles(oracle_lib, env_id, E)
+    orcs1 = _oracles(oracle_lib, env_id, E, spec=spec1)
+    for i, o in enumerate(orcs):
+        o.reset(noise=noise[i].astype(np.float64))
+        orcs1[i].reset(noise=noise[i].astype(np.float64))
+    errs1, errs4, free4 = [], [], []
+    for t in range(40):
+        a = rng.uniform(-1, 1, (E, nA)).astype(np.float32)
+        ost = np.stack([o.get_state() for o in orcs]).astype(np.float32)
+        for envx in (env4, env1):
+            envx.set_state(torch.from_numpy(ost))
+        for i in range(E):
+            orcs[i].set_state(ost[i].astype(np.float64)); orcs1[i].set_state(ost[i].astype(np.float64))
+        n4 = env4.physics_step(torch.from_numpy(a), want_contacts=True).cpu().numpy()
+        env1.physics_step(torch.from_numpy(a))
+        g4, g1 = env4.get_state().cpu().numpy(), env1.get_state().cpu().numpy()
+        for i in range(E):
+            orcs[i].physics_step(a[i].astype(np.float64)); orcs1[i].physics_step(a[i].astype(np.float64))
+        o4 = np.stack([o.get_state() for o in orcs]); o1 = np.stack([o.get_state() for o in orcs1])
+        on4 = np.array([o.num_contacts() for o in orcs])
+        errs1.append(_rel(g1, o1).max(axis=1)); errs4.append(_rel(g4, o4).max(axis=1))
+        free4.append((on4 == 0) & (n4 == 0))
+        assert np.isfinite(g4).all()
+    e1, e4, fr = np.concatenate(errs1), np.concatenate(errs4), np.concatenate(free4)
+    # one sub-step (ABA-equivalent dynamics + limit/contact rows + 5 PGS sweeps + integration)
+    assert np.median(e1) < 2e-5 and np.quantile(e1, 0.99) < 5e-3, (np.median(e1), np.quantile(e1, 0.99), e1.max())
+    # one env step = 4 sub-steps
+    assert np.median(e4) < 1e-4 and np.quantile(e4, 0.95) < 2e-2, (np.median(e4), np.quantile(e4, 0.95), e4.max())
+    if env_id in ("InvertedPendulumPyBulletEnv-v0", "AntPyBulletEnv-v0") and fr.any():
+        # contact-free env steps (pendulum always; Ant while airborne) are held to a max-norm bound
+        assert e4[fr].max() < 1e-4, e4[fr].max()
+
+
+def test_oracle_sensitivity_reference(oracle_lib):
+    """Documents the conditioning T2's quantile bounds rest on: the double-precision oracle, perturbed
+    by a float32-storage-sized 1e-7, moves by > 1e-5 after one Ant env step once contacts are active."""
+    rng = np.random.default_rng(0)
+    a_env, b_env = oracle_lib.OracleEnv("AntPyBulletEnv-v0", max_contacts=8), oracle_lib.OracleEnv("AntPyBulletEnv-v0", max_contacts=8)
+    a_env.reset(noise=rng.uniform(-.1, .1, 8)); b_env.reset(noise=np.zeros(8))
+    worst = 0.0
+    for t in range(60):
+        act = rng.uniform(-1, 1, 8)
+        s = a_env.get_state().astype(np.float32).astype(np.float64)
+        a_env.set_state(s); b_env.set_state(s + rng.normal(size=s.size) * 1e-7 * (1 + np.abs(s)))
+        a_env.physics_step(act); b_env.physics_step(act)
+        worst = max(worst, _rel(b_env.get_state(), a_env.get_state()).max())
+    assert worst > 1e-5
+
+
+def test_pendulum_full_episode_trajectory_T3(oracle_lib):
+    """Contact-free cart-pole, 1000 steps, fixed action tape (small actions keep it from diverging fast)."""
+    env_id = "InvertedPendulumSwingupPyBulletEnv-v0"      # never terminates: a full 1000-step episode
+    n = 16
+    env = _mk(env_id, n=n)
+    rng = np.random.default_rng(11)
+    noise = rng.uniform(-0.1, 0.1, (n, 1)).astype(np.float32)
+    env.reset(joint_noise=torch.from_numpy(noise))
+    orcs = [oracle_lib.OracleEnv(env_id) for _ in range(n)]
+    for i, o in enumerate(orcs):
+        o.reset(noise=noise[i].astype(np.float64))
+    tape = rng.uniform(-1, 1, (1000, n, 1)).astype(np.float32) * 0.3
+    err100 = 0.0
+    for t in range(1000):
+        obs, rew, done, _ = env.step(torch.from_numpy(tape[t]))
+        res = [o.step(tape[t, i].astype(np.float64)) for i, o in enumerate(orcs)]
+        if t == 99:
+            err100 = np.abs(obs.cpu().numpy() - np.stack([r[0] for r in res])).max()
+    oobs = np.stack([r[0] for r in res])
+    gobs = obs.cpu().numpy()
+    assert err100 < 2e-4, err100                       # 100 steps: fp32 round-off accumulates ~1e-6 per step
+    assert np.abs(gobs[:, :4] - oobs[:, :4]).max() < 5e-2, np.abs(gobs - oobs).max()   # full episode drift bound
+    assert np.isfinite(gobs).all()
+
+
+def _ks_pvalue(a, b):
+    from scipy.stats import ks_2samp
+    return ks_2samp(a, b).pvalue
+
+
+@pytest.mark.parametrize("env_id", ["HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
+                                    "AntPyBulletEnv-v0", "HumanoidPyBulletEnv-v0"])
+def test_random_policy_distributions_T4(env_id, oracle_lib):
+    """T4: episode length and return distributions under U(-1,1) actions, CUDA vs oracle (two-sample KS)."""
+    short = env_id != "AntPyBulletEnv-v0"
+    n = 1024 if short else 256
+    cap = 200 if short else 120          # Ant rarely terminates: compare the first `cap` steps' return
+    env = _mk(env_id, n=n, seed=100)
+    env.reset(floor_in_parts=True)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    ret = torch.zeros(n, device="cuda"); length = torch.zeros(n, device="cuda"); alive = torch.ones(n, device="cuda")
+    for t in range(cap):
+        a = torch.rand(n, env.action_dim, device="cuda", generator=gen) * 2 - 1
+        obs, rew, done, _ = env.step(a)
+        ret += alive * rew; length += alive
+        alive = alive * (1 - done.float())
+    g_ret, g_len = ret.cpu().numpy(), length.cpu().numpy()
+    from pybullet_gym_b200 import _lib
+    from pybullet_gym_b200.spec import SPECS
+    mc = _lib.lib().pbg_max_contacts(SPECS[env_id].kind)
+    m = 256 if short else 96
+    rng = np.random.default_rng(1)
+    o_ret, o_len = [], []
+    for i in range(m):
+        o = oracle_lib.OracleEnv(env_id, seed=200, env_index=i, max_contacts=mc)
+        o.reset(floor_in_parts=True)
+        r_sum, n_steps = 0.0, 0
+        for t in range(cap):
+            obs, r, d, _ = o.step(rng.uniform(-1, 1, env.action_dim))
+            r_sum += r; n_steps += 1
+            if d:
+                break
+        o_ret.append(r_sum); o_len.append(n_steps)
+    p_len, p_ret = _ks_pvalue(g_len, np.array(o_len)), _ks_pvalue(g_ret, np.array(o_ret))
+    assert p_len > 0.01 and p_ret > 0.01, (p_len, p_ret, g_len.mean(), np.mean(o_len), g_ret.mean(), np.mean(o_ret))
+
+
+@pytest.mark.parametrize("env_id", IDS)
+def test_golden_reference_rollout_prefix(env_id):
+    """The CUDA path replays the reset noise / actions of the golden files (recorded from the reference's
+    own Python on oracle physics): reset observation to 1e-5, first steps within fp32 drift."""
+    import glob, json, os
+    path = os.path.join(os.path.dirname(__file__), "golden", "task_%s.json" % env_id.split("PyBullet")[0])
+    g = json.load(open(path))
+    env = _mk(env_id, n=1)
+    for ei, ep in enumerate(g["episodes"]):
+        obs0 = env.reset(joint_noise=torch.tensor([ep["noise"]], dtype=torch.float32), floor_in_parts=ei > 0)
+        assert np.abs(obs0.cpu().numpy()[0] - np.array(ep["obs0"])).max() < 1e-5
+        for t, st in enumerate(ep["steps"][:3]):
+            obs, rew, done, info = env.step(torch.tensor([st["a"]], dtype=torch.float32))
+            assert np.abs(obs.cpu().numpy()[0] - np.array(st["obs"])).max() < 2e-3
+            assert abs(float(rew[0]) - st["reward"]) < 5e-3
+            assert bool(done[0]) == st["done"]

@@ -1,0 +1,138 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's full sizes, and the Gym shell.  -m gpu."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+FULL = {"HalfCheetahPyBulletEnv-v0": 4096, "HopperPyBulletEnv-v0": 4096, "Walker2DPyBulletEnv-v0": 4096,
+        "AntPyBulletEnv-v0": 16384, "HumanoidPyBulletEnv-v0": 2048, "InvertedPendulumPyBulletEnv-v0": 4096}
+
+
+def _mk(env_id, n, **kw):
+    from pybullet_gym_b200.vector_env import VectorEnv
+    return VectorEnv(env_id, n, device="cuda:0", **kw)
+
+
+@pytest.mark.parametrize("env_id", sorted(FULL))
+def test_full_size_rollout_is_deterministic_and_finite(env_id):
+    n = FULL[env_id]
+    outs = []
+    for rep in range(2):
+        env = _mk(env_id, n, seed=5)
+        env.reset()
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        acc = torch.zeros(n, device="cuda", dtype=torch.float64)
+        for t in range(60):
+            a = torch.rand(n, env.action_dim, device="cuda", generator=gen) * 2 - 1
+            obs, rew, done, info = env.step(a)
+            assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+            acc += rew.double() + obs.double().sum(dim=1)
+        outs.append((acc.cpu().numpy(), obs.cpu().numpy().copy(), env.stats()))
+        if env.spec.kind >= 2:
+            assert obs.abs().max() <= 5.0                       # np.clip(..., -5, 5)
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])   # bitwise
+    assert outs[0][2]["steps"] == 60 * n
+
+
+@pytest.mark.parametrize("env_id", ["AntPyBulletEnv-v0", "HopperPyBulletEnv-v0", "HumanoidPyBulletEnv-v0"])
+def test_envs_are_independent_of_batch_composition(env_id):
+    """env i of a big batch == the same env (same RNG stream, same actions) stepped in a small batch."""
+    n, k = 1024, 37
+    big = _mk(env_id, n, seed=9, auto_reset=True)
+    small = _mk(env_id, 64, seed=9, env_offset=k, auto_reset=True)
+    big.reset(); small.reset()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(40):
+        a = torch.rand(n, big.action_dim, device="cuda", generator=gen) * 2 - 1
+        ob, rb, db, _ = big.step(a)
+        os_, rs, ds, _ = small.step(a[k:k + 64].contiguous())
+        assert torch.equal(ob[k:k + 64], os_) and torch.equal(rb[k:k + 64], rs) and torch.equal(db[k:k + 64], ds)
+
+
+@pytest.mark.parametrize("env_id", ["HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "InvertedPendulumPyBulletEnv-v0"])
+def test_auto_reset_semantics(env_id, oracle_lib):
+    """After an env finishes, obs is the first observation of a fresh episode (oracle reset with the same
+    RNG stream), final_obs the terminal one; episode statistics add up."""
+    n = 512
+    env = _mk(env_id, n, seed=21, auto_reset=True)
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    episodes = np.ones(n, dtype=np.int64)       # reset() started episode 1 of every env
+    checked = 0
+    total_done = 0
+    for t in range(80):
+        a = torch.rand(n, env.action_dim, device="cuda", generator=gen) * 2 - 1
+        obs, rew, done, info = env.step(a)
+        d = done.cpu().numpy().astype(bool)
+        total_done += int(d.sum())
+        for i in np.where(d)[0][:3]:
+            episodes_i = episodes[i] + 1
+            o = oracle_lib.OracleEnv(env_id, seed=21, env_index=int(i))
+            for _ in range(episodes_i):
+                first = o.reset(floor_in_parts=True)
+            assert np.abs(first - obs[i].cpu().numpy()).max() < 1e-5
+            checked += 1
+        episodes[d] += 1
+    st = env.stats()
+    assert checked > 0 and st["episodes"] == total_done and st["length_sum"] <= 80 * n
+
+
+def test_time_limit_truncation():
+    from pybullet_gym_b200.spec import SPECS
+    import dataclasses
+    spec = dataclasses.replace(SPECS["AntPyBulletEnv-v0"], max_episode_steps=7)
+    env = _mk("AntPyBulletEnv-v0", 32, spec=spec, auto_reset=True)
+    env.reset()
+    a = torch.zeros(32, 8, device="cuda")
+    for t in range(7):
+        obs, rew, done, info = env.step(a)
+    assert done.all() and info["truncated"].all()
+    obs, rew, done, info = env.step(a)
+    assert not done.any()
+
+
+def test_smoke_every_backed_id():
+    """The reference's gym_sanity_check.py pattern: make, reset, one random step, for every backed id."""
+    from pybullet_gym_b200.envs import make, registry
+    from pybullet_gym_b200.spec import SPECS
+    for env_id, spec in SPECS.items():
+        if spec.kind >= 7:
+            continue
+        env = make(env_id)
+        obs = env.reset()
+        assert obs.shape == (spec.obs_dim,) and np.isfinite(obs).all()
+        obs, r, done, info = env.step(env.action_space.sample())
+        assert obs.shape == (spec.obs_dim,) and np.isfinite(obs).all() and np.isfinite(r) and info == {}
+        assert isinstance(done, bool)
+        env.close()
+    assert "AntPyBulletEnv-v0" in registry
+
+
+def test_gym_shell_attribute_surface():
+    from pybullet_gym_b200.envs import make
+    env = make("AntPyBulletEnv-v0")
+    env.seed(3)
+    obs0 = env.reset()
+    r = env.unwrapped.robot
+    assert len(r.parts) == 22 and "floor" in r.parts and len(r.ordered_joints) == 8 and len(r.feet) == 4
+    assert env.unwrapped.scene.dt == pytest.approx(0.0165) and env.unwrapped.scene.frame_skip == 4
+    obs, rew, done, info = env.step(np.zeros(8, dtype=np.float32))
+    # the host-side views agree with what the kernel reported
+    assert abs((r.body_xyz[2] - r.initial_z) - obs[0]) < 1e-5
+    assert len(env.unwrapped.rewards) == 5 and abs(sum(env.unwrapped.rewards) - rew) < 1e-5
+    assert abs(r.body_rpy[0] - obs[6]) < 1e-5 and abs(r.body_rpy[1] - obs[7]) < 1e-5
+    # same seed -> same reset noise -> same first observation
+    env2 = make("AntPyBulletEnv-v0"); env2.seed(3)
+    assert np.array_equal(env2.reset(), obs0)
+
+
+def test_step_host_round_trip():
+    env = _mk("AntPyBulletEnv-v0", 256, seed=4)
+    ref = _mk("AntPyBulletEnv-v0", 256, seed=4)
+    env.reset(); ref.reset()
+    a = (torch.rand(256, 8) * 2 - 1).pin_memory()
+    obs = torch.empty(256, 28).pin_memory(); rew = torch.empty(256).pin_memory(); done = torch.empty(256, dtype=torch.uint8).pin_memory()
+    env.step_host(a, obs, rew, done)
+    o2, r2, d2, _ = ref.step(a.cuda())
+    assert torch.equal(obs, o2.cpu()) and torch.equal(rew, r2.cpu()) and torch.equal(done, d2.cpu())
