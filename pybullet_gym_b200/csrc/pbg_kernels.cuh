@@ -37,7 +37,8 @@ struct KCfg {
     static_assert(ND + 1 <= LPE && NB <= LPE && NCAND <= 2 * LPE, "lane budget");
     // per-env state (floats)
     static constexpr int oQ = 7 * FLOATING, oU = oQ + NJ, oW = oU + ND, oT = oW + NSLOT, oF = oT + TASK_FLOATS;
-    static constexpr int SSIZE = oF + NFEET, SSTRIDE = (SSIZE + 3) / 4 * 4;
+    static constexpr int oP = oF + NFEET;          // feet flags of the last physics step, not yet seen by calc_state
+    static constexpr int SSIZE = oP + NFEET, SSTRIDE = (SSIZE + 3) / 4 * 4;
     static constexpr int CANON = 13 * FLOATING + 2 * NJ;
     // shared memory per env (floats)
     static constexpr int KS = 31;                  // R9 x3 w3 v3 al3 a3 z3 A3 (+1 pad)
@@ -908,7 +909,7 @@ struct Env {
         __syncwarp();
         if (pred) {
             for (int i = gl; i < C::oT; i += C::LPE) S[i] = 0.f;
-            for (int i = gl; i < C::NFEET; i += C::LPE) S[C::oF + i] = 0.f;
+            for (int i = gl; i < 2 * C::NFEET; i += C::LPE) S[C::oF + i] = 0.f;
         }
         __syncwarp();
         if (pred) {
@@ -1028,6 +1029,8 @@ __global__ void __launch_bounds__(C::THREADS) env_kernel(const DevModel *__restr
         for (int s = 0; s < nsub; ++s) e.substep(s == nsub - 1);
     }
     if (mode == MODE_PHYSICS) {
+        if (C::MAXC > 0 && gl < C::NFEET) S[C::oP + gl] = e.sm[C::sMISC + gl];
+        __syncwarp();
         if (valid) {
             for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
                 reinterpret_cast<float4 *>(gs)[i] = reinterpret_cast<const float4 *>(S)[i];
@@ -1042,6 +1045,7 @@ __global__ void __launch_bounds__(C::THREADS) env_kernel(const DevModel *__restr
     if (mode == MODE_OBSERVE) e.nc = 0;
     bool done = e.task(act, so_obs, so_rew, so_terms, false);
     if (mode == MODE_STEP && C::MAXC > 0 && gl < C::NFEET) S[C::oF + gl] = e.sm[C::sMISC + gl];
+    if (mode == MODE_OBSERVE && C::MAXC > 0 && gl < C::NFEET) S[C::oF + gl] = S[C::oP + gl];
     __syncwarp();
     bool trunc = false;
     if (mode == MODE_STEP) {
@@ -1083,7 +1087,7 @@ __global__ void __launch_bounds__(C::THREADS) env_kernel(const DevModel *__restr
     __syncwarp();
     if (valid) {
         if (obs) for (int i = gl; i < C::OBS; i += C::LPE) obs[i] = so_obs[i];
-        if (mode == MODE_STEP)
+        if (mode == MODE_STEP || mode == MODE_OBSERVE)      // observe persists the potential like a step would
             for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
                 reinterpret_cast<float4 *>(gs)[i] = reinterpret_cast<const float4 *>(S)[i];
     }

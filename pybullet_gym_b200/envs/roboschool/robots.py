@@ -45,7 +45,7 @@ class BodyPart:
     def __init__(self, robot, name, link_index):
         self.robot, self.name, self.link_index = robot, name, link_index
         self.bp_pose = PoseHelper(self)
-        self.bodyPartIndex = link_index - 1
+        self.bodyPartIndex = -1 if link_index is None else link_index - 1
 
     def get_pose(self):
         if self.link_index is None:      # the floor
