@@ -13,11 +13,11 @@ using namespace pbg;
 
 // kernel configurations: NB, NJ, FLOATING, NLIM, MAXC, LPE, NCAND, NPAIR, NFEET, NACT, OBS
 using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5>;
-using CfgHopper = KCfg<6, 6, 0, 3, 8, 16, 8, 0, 1, 3, 15>;
-using CfgWalker = KCfg<9, 9, 0, 6, 8, 16, 14, 0, 2, 6, 22>;
-using CfgCheetah = KCfg<9, 9, 0, 6, 8, 16, 16, 0, 6, 6, 26>;
-using CfgAnt = KCfg<9, 8, 1, 8, 8, 16, 25, 0, 4, 8, 28>;
-using CfgHumanoid = KCfg<18, 17, 1, 17, 15, 32, 30, 66, 2, 17, 44>;
+using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15>;
+using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22>;
+using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26>;
+using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28>;
+using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44>;
 
 struct KernelInfo {
     int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads;

@@ -32,34 +32,40 @@ struct KCfg {
     static constexpr int NDP = (ND + 3) / 4 * 4;
     static constexpr int LST = NDP + 4;            // row stride of L / Y: float4 rows, conflict-free
     static constexpr int EPW = 32 / LPE;
-    static constexpr int WARPS = 4, THREADS = 128, EPB = WARPS * EPW;
+    static constexpr int WARPS = 2, THREADS = 64, EPB = WARPS * EPW;
+    static constexpr int MIN_BLOCKS = LPE == 16 ? 7 : 3;   // resident blocks per SM the register budget is capped for
     static_assert(MAXR <= 2 * LPE, "at most two row slots per lane");
-    static_assert(ND + 1 <= LPE && NB <= LPE && NCAND <= 2 * LPE, "lane budget");
+    static_assert(ND + 1 <= LPE && NB <= LPE && NCAND <= 2 * LPE && NLIM <= LPE, "lane budget");
     // per-env state (floats)
     static constexpr int oQ = 7 * FLOATING, oU = oQ + NJ, oW = oU + ND, oT = oW + NSLOT, oF = oT + TASK_FLOATS;
     static constexpr int oP = oF + NFEET;          // feet flags of the last physics step, not yet seen by calc_state
     static constexpr int SSIZE = oP + NFEET, SSTRIDE = (SSIZE + 3) / 4 * 4;
     static constexpr int CANON = 13 * FLOATING + 2 * NJ;
-    // shared memory per env (floats)
+    // shared memory per env (floats).  Regions with disjoint lifetimes share storage:
+    //   {KIN, ACC, SH, F, COL} (kinematics .. Cholesky, dead once the rows are built)  |  {A} (Delassus matrix)
+    //   {Y} (constraint rows, substeps only)                                          |  {OUT} (staged outputs)
     static constexpr int KS = 31;                  // R9 x3 w3 v3 al3 a3 z3 A3 (+1 pad)
-    static constexpr int sST = 0;
-    static constexpr int sKIN = sST + SSTRIDE;
-    static constexpr int sACC = sKIN + NB * KS;
-    static constexpr int sSH = (sACC + NB * 17 + 3) / 4 * 4;
-    static constexpr int sF = sSH + ND * 12;
-    static constexpr int sL = (sF + NDP + 3) / 4 * 4;
-    static constexpr int sINV = sL + (ND + 1) * LST;
-    static constexpr int sCOL = sINV + NDP;
-    static constexpr int sY = (sCOL + 2 * (NDP + 4) + 3) / 4 * 4;
-    static constexpr int sA = sY + MAXRP * LST;
-    static constexpr int sLAM = sA + MAXRP * MAXRP;
-    static constexpr int sCT = sLAM + MAXRP;
     static constexpr int CTS = 16;                 // contact record: bodyA bodyB slot pad pA3 pB3 n3 dist mu pad
+    static constexpr int sST = 0;
+    static constexpr int sL = (sST + SSTRIDE + 3) / 4 * 4;
+    static constexpr int sINV = sL + (ND + 1) * LST;
+    static constexpr int sY = (sINV + NDP + 3) / 4 * 4;
+    static constexpr int YSZ = MAXRP * LST > 72 ? MAXRP * LST : 72;
+    static constexpr int sOUT = sY;                // staged outputs: obs[64] reward terms[5]
+    static constexpr int sLAM = sY + YSZ;
+    static constexpr int sCT = sLAM + MAXRP;
     static constexpr int sLIM = sCT + (MAXC > 0 ? MAXC : 1) * CTS;
     static constexpr int sCD = sLIM + 2 * (NLIM > 0 ? NLIM : 1);
     static constexpr int sMISC = sCD + (NSLOT > 0 ? NSLOT : 1);   // this step's feet flags
-    static constexpr int sOUT = sMISC + 8;                        // staged outputs: obs[64] reward terms[5]
-    static constexpr int ENV_FLOATS = (sOUT + 72 + 3) / 4 * 4;
+    static constexpr int sU = (sMISC + 8 + 3) / 4 * 4;
+    static constexpr int sKIN = sU;
+    static constexpr int sACC = sKIN + NB * KS;
+    static constexpr int sSH = (sACC + NB * 17 + 3) / 4 * 4;
+    static constexpr int sF = sSH + ND * 12;
+    static constexpr int sCOL = (sF + NDP + 3) / 4 * 4;
+    static constexpr int G1 = sCOL + 2 * (NDP + 4) - sU;
+    static constexpr int sA = sU;
+    static constexpr int ENV_FLOATS = (sU + (G1 > MAXRP * MAXRP + 2 * LPE ? G1 : MAXRP * MAXRP + 2 * LPE) + 3) / 4 * 4;
     static constexpr size_t SMEM_BYTES = size_t(ENV_FLOATS) * EPB * sizeof(float);
 };
 
@@ -617,7 +623,7 @@ struct Env {
                     const V3 so = ld3(SH + k * 12), sv = ld3(SH + k * 12 + 3);
                     float val = 0.f;
                     if ((ma >> k) & 1u) val += dot(d, sv + cross(so, pA));
-                    if ((mb >> k) & 1u) val -= dot(d, sv + cross(so, pB));
+                    if (C::NPAIR > 0) { if ((mb >> k) & 1u) val -= dot(d, sv + cross(so, pB)); }
                     J[k] = val;
                 }
             }
@@ -683,35 +689,57 @@ struct Env {
         __syncwarp();
 
         // --- projected Gauss-Seidel on lambda, Bullet's row order: limit rows (alternating
-        // direction), contact normals, friction rows (btMultiBodyConstraintSolver::solveSingleIteration)
-        const int niter = m->niter;
-        for (int it = 0; it < niter; ++it) {
-            for (int t = 0; t < nrmax; ++t) {
-                int i = t;
-                if (t < nl) i = (it & 1) ? t : nl - 1 - t;
-                const bool live = t < nr;
-                const int owner = i & (C::LPE - 1);
-                const bool s1 = i >= C::LPE;
-                float flo = s1 ? lo[1] : lo[0], fhi = s1 ? hi[1] : hi[0];
-                const float frhs = s1 ? rhs[1] : rhs[0], fdi = s1 ? dinv[1] : dinv[0];
-                const float fl = s1 ? lmb[1] : lmb[0], fr = s1 ? r[1] : r[0], fmu = s1 ? mu[1] : mu[0];
-                bool skip = !live;
-                {
-                    // friction rows are bounded by mu * (current normal impulse); the shuffle runs for
-                    // every row so that both env groups of the warp stay converged
-                    const bool isfr = i >= nl + nc;
-                    const int nrow = isfr ? nl + ((i - nl - nc) >> 1) : 0;
-                    const float ln = shfl((nrow >= C::LPE) ? lmb[1] : lmb[0], nrow & (C::LPE - 1));
-                    if (isfr) { if (ln > 0.f) { flo = -fmu * ln; fhi = fmu * ln; } else skip = true; }
+        // direction), contact normals, friction rows (btMultiBodyConstraintSolver::solveSingleIteration).
+        // Every lane evaluates the update of its own row from registers each step; the row whose turn
+        // it is publishes its impulse change with one shuffle and all lanes fold it into their
+        // residual r = A lambda.  Friction rows track their normal row's impulse as it changes.
+        {
+            const int niter = m->niter;
+            const bool two = nrmax > C::LPE;
+            int myn[2]; float ln[2], lo_e[2], hi_e[2]; bool fr[2];
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const int i = sl * C::LPE + gl;
+                fr[sl] = i >= nl + nc && i < nr;
+                myn[sl] = fr[sl] ? nl + ((i - nl - nc) >> 1) : -1;
+                const int src = myn[sl] < 0 ? 0 : myn[sl];
+                const float a0 = shfl(lmb[0], src & (C::LPE - 1)), a1 = shfl(lmb[1], src & (C::LPE - 1));
+                ln[sl] = fr[sl] ? (src >= C::LPE ? a1 : a0) : 1.f;
+                lo_e[sl] = fr[sl] ? -mu[sl] * ln[sl] : lo[sl];
+                hi_e[sl] = fr[sl] ? mu[sl] * ln[sl] : hi[sl];
+            }
+            const int t0end = two ? C::LPE : nrmax;
+            for (int it = 0; it < niter; ++it) {
+                // rows 0 .. LPE-1 live in register slot 0
+                for (int t = 0; t < t0end; ++t) {
+                    int i = t;
+                    if (t < nl) i = (it & 1) ? t : nl - 1 - t;
+                    const float d = fmaf(-r[0], dinv[0], rhs[0]);
+                    float cd = fminf(fmaxf(lmb[0] + d, lo_e[0]), hi_e[0]) - lmb[0];
+                    if (!(ln[0] > 0.f)) cd = 0.f;            // a friction row is skipped while its normal impulse is 0
+                    const float dl = shfl(cd, i);
+                    if (gl == i) lmb[0] += dl;
+                    const float *arow = Am + i * C::MAXRP;
+                    r[0] = fmaf(arow[gl], dl, r[0]);
+                    if (i == myn[0]) { ln[0] += dl; hi_e[0] = mu[0] * ln[0]; lo_e[0] = -hi_e[0]; }
+                    if (two) {
+                        r[1] = fmaf(arow[C::LPE + gl], dl, r[1]);
+                        if (i == myn[1]) { ln[1] += dl; hi_e[1] = mu[1] * ln[1]; lo_e[1] = -hi_e[1]; }
+                    }
                 }
-                float dl = frhs - fr * fdi;
-                const float sum = fminf(fmaxf(fl + dl, flo), fhi);
-                dl = skip ? 0.f : sum - fl;
-                if (gl == owner && !skip) { if (s1) lmb[1] = sum; else lmb[0] = sum; }
-                dl = shfl(dl, owner);
-                const float *arow = Am + i * C::MAXRP;
-                r[0] += arow[gl < C::MAXR ? gl : 0] * dl;
-                if (C::MAXR > C::LPE) r[1] += arow[(C::LPE + gl) < C::MAXR ? C::LPE + gl : 0] * dl;
+                // rows LPE .. 2 LPE-1 live in register slot 1 (never limit rows: nl <= NLIM <= LPE)
+                for (int t = C::LPE; t < nrmax; ++t) {
+                    const float d = fmaf(-r[1], dinv[1], rhs[1]);
+                    float cd = fminf(fmaxf(lmb[1] + d, lo_e[1]), hi_e[1]) - lmb[1];
+                    if (!(ln[1] > 0.f)) cd = 0.f;
+                    const float dl = shfl(cd, t - C::LPE);
+                    if (gl == t - C::LPE) lmb[1] += dl;
+                    const float *arow = Am + t * C::MAXRP;
+                    r[0] = fmaf(arow[gl], dl, r[0]);
+                    r[1] = fmaf(arow[C::LPE + gl], dl, r[1]);
+                    if (t == myn[0]) { ln[0] += dl; hi_e[0] = mu[0] * ln[0]; lo_e[0] = -hi_e[0]; }
+                    if (t == myn[1]) { ln[1] += dl; hi_e[1] = mu[1] * ln[1]; lo_e[1] = -hi_e[1]; }
+                }
             }
         }
         // --- publish lambda, store warm-start impulses
@@ -937,7 +965,7 @@ struct Env {
 
 // ---------------------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(C::THREADS) env_kernel(const DevModel *__restrict__ model, StepBuffers B, LaunchArgs la) {
+__global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const DevModel *__restrict__ model, StepBuffers B, LaunchArgs la) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Env<C> e;
@@ -1000,20 +1028,6 @@ __global__ void __launch_bounds__(C::THREADS) env_kernel(const DevModel *__restr
     float *so = e.sm + C::sOUT;
     float *so_obs = so, *so_rew = so + 64, *so_terms = so + 65;
 
-    if (mode == MODE_RESET) {
-        const bool doit = !B.mask || B.mask[env];
-        e.reset_state(la, genv, B.noise ? B.noise + env * C::NACT : nullptr, la.floor_in_parts, doit);
-        // envs that are not reset only get their observation refreshed
-        e.task(nullptr, so_obs, nullptr, nullptr, doit, true);
-        __syncwarp();
-        if (valid) {
-            if (obs) for (int i = gl; i < C::OBS; i += C::LPE) obs[i] = so_obs[i];
-            if (doit) for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
-                reinterpret_cast<float4 *>(gs)[i] = reinterpret_cast<const float4 *>(S)[i];
-        }
-        return;
-    }
-
     if (mode == MODE_STEP || mode == MODE_PHYSICS) {
         // apply_action: tau = power * power_coef * clip(a, -1, 1) (rs/robot_locomotors.py:26-29),
         // plus the joint damping torque, both held for all substeps
@@ -1039,55 +1053,68 @@ __global__ void __launch_bounds__(C::THREADS) env_kernel(const DevModel *__restr
         return;
     }
 
-    // ---- task layer.  calc_state must still see the previous step's feet flags (quirk Q2: the
-    // reference updates robot.feet_contact after calc_state / alive_bonus); this step's flags were
-    // staged by the last substep's collide() and replace them afterwards.
+    // ---- task layer, two passes through ONE task() call site (keeps the code small):
+    //   pass 0  calc_state / reward / termination of the stepped state        (STEP, OBSERVE)
+    //   pass 1  episode reset + first observation, predicated per env group   (RESET; STEP when finished)
+    // calc_state must still see the previous step's feet flags (quirk Q2: the reference updates
+    // robot.feet_contact after calc_state / alive_bonus); this step's flags were staged by the last
+    // substep's collide() and replace them after pass 0.
     if (mode == MODE_OBSERVE) e.nc = 0;
-    bool done = e.task(act, so_obs, so_rew, so_terms, false);
-    if (mode == MODE_STEP && C::MAXC > 0 && gl < C::NFEET) S[C::oF + gl] = e.sm[C::sMISC + gl];
-    if (mode == MODE_OBSERVE && C::MAXC > 0 && gl < C::NFEET) S[C::oF + gl] = S[C::oP + gl];
-    __syncwarp();
-    bool trunc = false;
-    if (mode == MODE_STEP) {
-        if (gl == 0) {
-            const int steps = __float_as_int(T[T_STEPS]) + 1;
-            T[T_STEPS] = __int_as_float(steps);
-            T[T_RETURN] += so_rew[0];
+    const bool reset_mode = mode == MODE_RESET;
+    const bool mask_on = reset_mode && (!B.mask || B.mask[env]);
+    bool store_state = mode == MODE_STEP || mode == MODE_OBSERVE;
+    bool want_reset = mask_on;
+    for (int pass = reset_mode ? 1 : 0; pass < 2; ++pass) {
+        bool rp = false, pred = true;
+        if (pass == 1) {
+            if (!reset_mode && !__any_sync(0xffffffffu, want_reset)) break;
+            __syncwarp();
+            e.reset_state(la, genv, (reset_mode && B.noise) ? B.noise + env * C::NACT : nullptr,
+                          reset_mode ? la.floor_in_parts : 1, want_reset);
+            rp = want_reset;                 // envs left out of a masked reset only get their observation refreshed
+            pred = reset_mode ? true : want_reset;
+            if (reset_mode) store_state = want_reset;
         }
+        const bool done = e.task(act, so_obs, so_rew, so_terms, rp, pred);
+        if (pass == 1) break;
+        if (mode == MODE_STEP && C::MAXC > 0 && gl < C::NFEET) S[C::oF + gl] = e.sm[C::sMISC + gl];
+        if (mode == MODE_OBSERVE && C::MAXC > 0 && gl < C::NFEET) S[C::oF + gl] = S[C::oP + gl];
         __syncwarp();
-        trunc = !done && __float_as_int(T[T_STEPS]) >= model->max_steps;
-    }
-    const bool finished = done || trunc;
-    if (valid && gl == 0) {
-        if (B.reward) B.reward[env] = so_rew[0];
-        if (B.done) B.done[env] = (done || (trunc && la.auto_reset)) ? 1 : 0;
-        if (B.truncated) B.truncated[env] = trunc ? 1 : 0;
-    }
-    if (valid && B.terms) { if (gl < 5) B.terms[env * 5 + gl] = so_terms[gl]; }
-    if (valid && B.feet_out) { if (gl < C::NFEET) B.feet_out[env * C::NFEET + gl] = S[C::oF + gl]; }
-    if (valid && B.ncontact_out && gl == 0) B.ncontact_out[env] = e.nc;
-    if (mode == MODE_STEP && finished) {
-        if (valid && gl == 0 && B.stats) {
-            atomicAdd(&B.stats[0], 1ull);
-            atomicAdd(&B.stats[1], (unsigned long long)__float_as_int(T[T_STEPS]));
-            atomicAdd(reinterpret_cast<double *>(&B.stats[2]), (double)T[T_RETURN]);
-            if (trunc) atomicAdd(&B.stats[3], 1ull);
-            if (T[T_HAVEZ] == 2.f) atomicAdd(&B.stats[4], 1ull);
+        bool trunc = false;
+        if (mode == MODE_STEP) {
+            if (gl == 0) {
+                T[T_STEPS] = __int_as_float(__float_as_int(T[T_STEPS]) + 1);
+                T[T_RETURN] += so_rew[0];
+            }
+            __syncwarp();
+            trunc = !done && __float_as_int(T[T_STEPS]) >= model->max_steps;
         }
-        if (la.auto_reset && valid && B.final_obs)
-            for (int i = gl; i < C::OBS; i += C::LPE) B.final_obs[env * C::OBS + i] = so_obs[i];
-    }
-    // in-kernel reset: the whole warp runs it when any of its envs finished, predicated per group
-    const bool do_reset = mode == MODE_STEP && finished && la.auto_reset;
-    if (__any_sync(0xffffffffu, do_reset)) {
-        __syncwarp();
-        e.reset_state(la, genv, nullptr, 1, do_reset);
-        e.task(nullptr, so_obs, nullptr, nullptr, true, do_reset);
+        const bool finished = done || trunc;
+        if (valid && gl == 0) {
+            if (B.reward) B.reward[env] = so_rew[0];
+            if (B.done) B.done[env] = (done || (trunc && la.auto_reset)) ? 1 : 0;
+            if (B.truncated) B.truncated[env] = trunc ? 1 : 0;
+            if (B.ncontact_out) B.ncontact_out[env] = e.nc;
+        }
+        if (valid && B.terms) { if (gl < 5) B.terms[env * 5 + gl] = so_terms[gl]; }
+        if (valid && B.feet_out) { if (gl < C::NFEET) B.feet_out[env * C::NFEET + gl] = S[C::oF + gl]; }
+        if (mode == MODE_STEP && finished) {
+            if (valid && gl == 0 && B.stats) {
+                atomicAdd(&B.stats[0], 1ull);
+                atomicAdd(&B.stats[1], (unsigned long long)__float_as_int(T[T_STEPS]));
+                atomicAdd(reinterpret_cast<double *>(&B.stats[2]), (double)T[T_RETURN]);
+                if (trunc) atomicAdd(&B.stats[3], 1ull);
+                if (T[T_HAVEZ] == 2.f) atomicAdd(&B.stats[4], 1ull);
+            }
+            if (la.auto_reset && valid && B.final_obs)
+                for (int i = gl; i < C::OBS; i += C::LPE) B.final_obs[env * C::OBS + i] = so_obs[i];
+        }
+        want_reset = mode == MODE_STEP && finished && la.auto_reset;
     }
     __syncwarp();
     if (valid) {
         if (obs) for (int i = gl; i < C::OBS; i += C::LPE) obs[i] = so_obs[i];
-        if (mode == MODE_STEP || mode == MODE_OBSERVE)      // observe persists the potential like a step would
+        if (store_state)
             for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
                 reinterpret_cast<float4 *>(gs)[i] = reinterpret_cast<const float4 *>(S)[i];
     }
