@@ -11,13 +11,14 @@
 
 using namespace pbg;
 
-// kernel configurations: NB, NJ, FLOATING, NLIM, MAXC, LPE, NCAND, NPAIR, NFEET, NACT, OBS
-using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5>;
-using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15>;
-using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22>;
-using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26>;
-using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28>;
-using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44>;
+// kernel configurations: NB, NJ, FLOATING, NLIM, MAXC, LPE, NCAND, NPAIR, NFEET, NACT, OBS, WARPS per CTA, CTAs per SM
+// 14 warps x 2 envs = 28 envs per CTA = one CTA per SM (7.2 KB shared memory per env): 148 CTAs hold 4144 envs.
+using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5, 4, 4>;
+using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15, 14, 1>;
+using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1>;
+using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1>;
+using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28, 14, 1>;
+using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1>;
 
 struct KernelInfo {
     int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads;
@@ -250,6 +251,14 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
 extern "C" {
 
 int pbg_version(void) { return PBG_VERSION; }
+
+// development / documentation helper: {shared memory per CTA, envs per CTA, threads per CTA, state floats per env}
+int pbg_dev_kernel_geometry(int kind, int32_t *out4) {
+    KernelInfo k;
+    if (!kernel_for_kind(kind, &k)) return PBG_ERR_UNSUPPORTED;
+    out4[0] = (int32_t)k.smem; out4[1] = k.epb; out4[2] = k.threads; out4[3] = k.sstride;
+    return PBG_OK;
+}
 
 int pbg_max_contacts(int kind) {
     KernelInfo k;

@@ -22,7 +22,7 @@
 namespace pbg {
 
 template <int NB_, int NJ_, int FLOATING_, int NLIM_, int MAXC_, int LPE_, int NCAND_, int NPAIR_, int NFEET_,
-          int NACT_, int OBS_>
+          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_>
 struct KCfg {
     static constexpr int NB = NB_, NJ = NJ_, FLOATING = FLOATING_, ND = NJ_ + 6 * FLOATING_, NLIM = NLIM_;
     static constexpr int MAXC = MAXC_, LPE = LPE_, NCAND = NCAND_, NPAIR = NPAIR_, NSLOT = NCAND_ + NPAIR_;
@@ -32,8 +32,11 @@ struct KCfg {
     static constexpr int NDP = (ND + 3) / 4 * 4;
     static constexpr int LST = NDP + 4;            // row stride of L / Y: float4 rows, conflict-free
     static constexpr int EPW = 32 / LPE;
-    static constexpr int WARPS = 2, THREADS = 64, EPB = WARPS * EPW;
-    static constexpr int MIN_BLOCKS = LPE == 16 ? 7 : 3;   // resident blocks per SM the register budget is capped for
+    // One CTA per SM: all warps of an SM run the same phase of the same substep at about the same
+    // time (block barrier per substep), so the long straight-line phases are fetched once per SM
+    // instead of once per warp -- instruction fetch was the top stall with small independent CTAs.
+    static constexpr int WARPS = WARPS_, THREADS = 32 * WARPS_, EPB = WARPS * EPW;
+    static constexpr int MIN_BLOCKS = MIN_BLOCKS_;
     static_assert(MAXR <= 2 * LPE, "at most two row slots per lane");
     static_assert(ND + 1 <= LPE && NB <= LPE && NCAND <= 2 * LPE && NLIM <= LPE, "lane budget");
     // per-env state (floats)
@@ -1040,7 +1043,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
         }
         e.tau = tq;
         const int nsub = model->nsub;
-        for (int s = 0; s < nsub; ++s) e.substep(s == nsub - 1);
+        for (int s = 0; s < nsub; ++s) {
+            if (C::WARPS > 2) __syncthreads();      // re-align the CTA's warps (instruction-cache locality)
+            e.substep(s == nsub - 1);
+        }
     }
     if (mode == MODE_PHYSICS) {
         if (C::MAXC > 0 && gl < C::NFEET) S[C::oP + gl] = e.sm[C::sMISC + gl];
