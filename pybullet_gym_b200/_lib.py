@@ -17,7 +17,7 @@ from .mjcf import compiler as mj
 from .spec import EnvSpec
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpbg_b200.so")
+LIB_PATH = os.environ.get("PBG_LIB") or os.path.join(_PKG, "libpbg_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 INCLUDE = os.path.join(_PKG, "..", "include")
 

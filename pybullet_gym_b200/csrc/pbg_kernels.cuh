@@ -1044,7 +1044,11 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
         e.tau = tq;
         const int nsub = model->nsub;
         for (int s = 0; s < nsub; ++s) {
-            if (C::WARPS > 2) __syncthreads();      // re-align the CTA's warps (instruction-cache locality)
+#ifndef PBG_SYNC_MODE
+#define PBG_SYNC_MODE 1
+#endif
+            // re-align the CTA's warps (instruction-cache locality); mode 1: every substep, 2: every other, 0: never
+            if (C::WARPS > 2 && (PBG_SYNC_MODE == 1 || (PBG_SYNC_MODE == 2 && (s & 1) == 0))) __syncthreads();
             e.substep(s == nsub - 1);
         }
     }
