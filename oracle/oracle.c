@@ -126,6 +126,9 @@ static double rng_uniform(uint64_t seed, uint64_t env, uint32_t ep, uint32_t n, 
 }
 
 /* ------------------------------------------------------------------ env */
+struct orc_env;
+static double draw(struct orc_env *e, uint32_t stream, uint32_t n, float lo, float hi);
+
 typedef struct {
     int ga, gb;         /* geom (gb = -1: floor) */
     int la, lb;         /* links */
@@ -169,8 +172,21 @@ struct orc_env {
     double torso_speed[3];
     row rows[MAXROWS];
     int last_nlim, last_nr;
+    /* Flagrun / FlagrunHarder (rs/robot_locomotors.py:195-302) */
+    double flag_timeout; int flag_count, frame, on_ground, crawl_has, attacks; double crawl_start, crawl_ign;
+    double tape[4096]; int tape_n, tape_pos;
     double last_dv[MAXU], last_ufree[MAXU], last_u0[MAXU];
 };
+
+static double draw(struct orc_env *e, uint32_t stream, uint32_t n, float lo, float hi) {
+    if (e->tape_pos < e->tape_n) return e->tape[e->tape_pos++];
+    return rng_uniform_s(e->seed, e->env_index, e->episode, stream, n, lo, hi);
+}
+void orc_set_tape(orc_env *e, const double *tape, int n) {
+    if (n > 4096) n = 4096;
+    for (int i = 0; i < n; i++) e->tape[i] = tape[i];
+    e->tape_n = n; e->tape_pos = 0;
+}
 
 int orc_num_dofs(const orc_model *m) {
     int n = 0;
@@ -750,6 +766,7 @@ static void mat_to_quat(m3 m, double q[4]) {
 }
 
 static int is_walker(int kind) { return kind >= ORC_KIND_HOPPER; }
+static double potential_leak(const orc_env *e);
 
 static double alive_bonus(orc_env *e, double z, double pitch) {
     switch (e->m.kind) {
@@ -757,8 +774,46 @@ static double alive_bonus(orc_env *e, double z, double pitch) {
     case ORC_KIND_HALFCHEETAH:
         return (fabs(pitch) < 1.0 && !e->feet_contact[1] && !e->feet_contact[2] && !e->feet_contact[4] && !e->feet_contact[5]) ? 1 : -1;
     case ORC_KIND_ANT: return z > 0.26 ? 1 : -1;
+    case ORC_KIND_FLAGRUN_HARDER:
+        /* rs/robot_locomotors.py:250-273; the cube itself is not simulated, its RNG draws are */
+        if (e->frame % 30 == 0 && e->frame > 100 && e->on_ground == 0) {
+            (void)draw(e, 2, 5u * e->attacks, -3.14f, 3.14f); (void)draw(e, 2, 5u * e->attacks + 1u, 20.f, 30.f);
+            for (int k = 0; k < 3; k++) (void)draw(e, 2, 5u * e->attacks + 2u + k, -1.f, 1.f);
+            e->attacks++;
+        }
+        if (z < 0.8) e->on_ground++; else if (e->on_ground > 0) e->on_ground--;
+        e->frame++;
+        return e->on_ground < 170 ? potential_leak(e) : -1;
     default: return z > 0.78 ? 2 : -1;
     }
+}
+
+static int is_flagrun(int kind) { return kind == ORC_KIND_FLAGRUN || kind == ORC_KIND_FLAGRUN_HARDER; }
+
+/* HumanoidFlagrun.flag_reposition (rs/robot_locomotors.py:204-218); float32 arithmetic like the device */
+static void flag_reposition(orc_env *e) {
+    const orc_model *m = &e->m;
+    int taped = e->tape_pos < e->tape_n;
+    double x = draw(e, 1, 2u * e->flag_count, -(float)m->stadium_halflen, (float)m->stadium_halflen);
+    double y = draw(e, 1, 2u * e->flag_count + 1u, -(float)m->stadium_halfwidth, (float)m->stadium_halfwidth);
+    if (taped) { e->walk_target_x = 0.5 * x; e->walk_target_y = 0.5 * y; }      /* reference: float64 */
+    else { e->walk_target_x = (double)(0.5f * (float)x); e->walk_target_y = (double)(0.5f * (float)y); }
+    e->flag_count++;
+    e->flag_timeout = 600.0 / m->nsub;
+}
+static double potential_leak(const orc_env *e) {
+    double z = e->body_xyz[2]; z = z < 0 ? 0 : (z > 0.8 ? 0.8 : z);
+    return z / 0.8 + 1.0;
+}
+/* HumanoidFlagrunHarder.calc_potential (rs/robot_locomotors.py:280-302): has side effects */
+static double harder_potential(orc_env *e) {
+    double frp = -e->walk_target_dist / e->m.dt_scene;
+    if (e->body_xyz[2] < 0.8) {
+        if (!e->crawl_has) { e->crawl_start = frp - e->crawl_ign; e->crawl_has = 1; }
+        e->crawl_ign = frp - e->crawl_start;
+        frp = e->crawl_start;
+    } else { frp -= e->crawl_ign; e->crawl_has = 0; }
+    return frp + potential_leak(e) * 100.0;
 }
 
 /* WalkerBase.calc_state (rs/robot_locomotors.py:31-64) on the current physics state */
@@ -790,6 +845,17 @@ static void walker_calc_state(orc_env *e, double *obs) {
     double ty = e->walk_target_y - e->body_xyz[1], tx = e->walk_target_x - e->body_xyz[0];
     double theta = atan2(ty, tx);
     e->walk_target_dist = sqrt(ty * ty + tx * tx);
+    if (is_flagrun(m->kind)) {
+        /* HumanoidFlagrun.calc_state (rs/robot_locomotors.py:220-227) */
+        e->flag_timeout -= 1;
+        if (e->walk_target_dist < 1 || e->flag_timeout <= 0) {
+            flag_reposition(e);
+            ty = e->walk_target_y - e->body_xyz[1]; tx = e->walk_target_x - e->body_xyz[0];
+            theta = atan2(ty, tx);
+            e->walk_target_dist = sqrt(ty * ty + tx * tx);
+            if (m->kind == ORC_KIND_FLAGRUN_HARDER) (void)harder_potential(e);   /* robot.potential: unused by the env (Q5) */
+        }
+    }
     double ang = theta - yaw;
     v3 sp; link_com_vel(e, tl, sp);
     v3cpy(e->torso_speed, sp);
@@ -810,7 +876,10 @@ static void pendulum_calc_state(orc_env *e, double *obs) {
     obs[0] = x; obs[1] = vx; obs[2] = cos(th); obs[3] = sin(th); obs[4] = thd;
 }
 
-static double calc_potential(orc_env *e) { return -e->walk_target_dist / e->m.dt_scene; }
+static double calc_potential(orc_env *e) {
+    if (e->m.kind == ORC_KIND_FLAGRUN_HARDER) return harder_potential(e);
+    return -e->walk_target_dist / e->m.dt_scene;
+}
 
 static void update_feet_contact(orc_env *e) {
     const orc_model *m = &e->m;
@@ -881,6 +950,8 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
     e->floor_in_parts = floor_in_parts;
     e->walk_target_x = m->walk_target_x; e->walk_target_y = m->walk_target_y;
     if (m->initial_z >= 0) { e->initial_z = m->initial_z; e->have_initial_z = 1; } else e->have_initial_z = 0;
+    e->flag_count = 0; e->flag_timeout = 0; e->frame = 0; e->on_ground = 0; e->crawl_has = 0; e->crawl_start = 0; e->crawl_ign = 0; e->attacks = 0;
+    if (is_flagrun(m->kind)) flag_reposition(e);
     if (is_walker(m->kind)) { walker_calc_state(e, obs); e->potential = calc_potential(e); }
     else pendulum_calc_state(e, obs);
     /* quirk Q1: the env adds the floor to robot.parts right after this first calc_state

@@ -62,6 +62,7 @@ typedef struct {
     double elec_cost, stall_cost, limit_cost, dt_scene;
     double walk_target_x, walk_target_y;
     int32_t max_episode_steps;
+    double stadium_halflen, stadium_halfwidth;   /* rs/scene_stadium.py:13-14, Flagrun target range */
 } orc_model;
 
 typedef struct orc_env orc_env;
@@ -90,6 +91,9 @@ void orc_link_state(orc_env *e, double *out /* [nl*10]: com3 quat4 vel3 */);
 int orc_get_contacts(const orc_env *e, int32_t *la, int32_t *lb, double *dist);
 void orc_set_joint(orc_env *e, int dof, double q, double qd);
 void orc_get_joint(const orc_env *e, int dof, double *q, double *qd);
+/* replay tape: when set, every random draw of the task layer (flag positions, cube attack) is read from it
+ * in order instead of the counter RNG -- used to replay the reference's np_random draws */
+void orc_set_tape(orc_env *e, const double *tape, int n);
 /* diagnostics */
 int orc_get_rows(const orc_env *e, double *out);
 int orc_num_contacts(const orc_env *e);

@@ -49,6 +49,7 @@ class OrcModel(C.Structure):
         ("elec_cost", C.c_double), ("stall_cost", C.c_double), ("limit_cost", C.c_double), ("dt_scene", C.c_double),
         ("walk_target_x", C.c_double), ("walk_target_y", C.c_double),
         ("max_episode_steps", C.c_int32),
+        ("stadium_halflen", C.c_double), ("stadium_halfwidth", C.c_double),
     ]
 
 
@@ -96,6 +97,7 @@ def lib():
         L.orc_get_rows.argtypes = [C.c_void_p, _pd]
         L.orc_get_rows.restype = C.c_int
         L.orc_get_debug.argtypes = [C.c_void_p, _pd]
+        L.orc_set_tape.argtypes = [C.c_void_p, _pd, C.c_int]
         L.orc_rollout.argtypes = [C.c_void_p, C.c_long, C.c_uint64, _pd, C.POINTER(C.c_long)]
         L.orc_rollout.restype = C.c_long
         _lib = L
@@ -182,6 +184,7 @@ class OracleModel:
         m.dt_scene = sc.dt
         m.walk_target_x, m.walk_target_y = spec.walk_target
         m.max_episode_steps = spec.max_episode_steps
+        m.stadium_halflen, m.stadium_halfwidth = sc.stadium_halflen, sc.stadium_halfwidth
         for k, v in overrides.items():
             setattr(m, k, v)
         self.c = m
@@ -271,6 +274,10 @@ class OracleEnv:
         lib().orc_get_debug(self._h, out.ctypes.data_as(_pd))
         n = self.model.nu
         return out[:n], out[64:64 + n], out[128:128 + n]
+
+    def set_tape(self, values):
+        t = _d(values)
+        lib().orc_set_tape(self._h, t.ctypes.data_as(_pd), int(t.size))
 
     def num_contacts(self):
         return lib().orc_num_contacts(self._h)

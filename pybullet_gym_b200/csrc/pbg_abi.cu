@@ -49,7 +49,7 @@ static bool kernel_for_kind(int kind, KernelInfo *out) {
     case PBG_KIND_WALKER2D: *out = info_of<CfgWalker>(); return true;
     case PBG_KIND_HALFCHEETAH: *out = info_of<CfgCheetah>(); return true;
     case PBG_KIND_ANT: *out = info_of<CfgAnt>(); return true;
-    case PBG_KIND_HUMANOID: *out = info_of<CfgHumanoid>(); return true;
+    case PBG_KIND_HUMANOID: case PBG_KIND_FLAGRUN: case PBG_KIND_FLAGRUN_HARDER: *out = info_of<CfgHumanoid>(); return true;
     default: return false;
     }
 }

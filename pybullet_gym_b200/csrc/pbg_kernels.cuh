@@ -153,6 +153,7 @@ struct Env {
     float tau;          // joint force of this dof for the current env step
     int nc, nl;         // active contacts / limit rows of this env (group-uniform)
     float *dbg;         // optional debug dump of the constraint rows (development only)
+    unsigned long long rng_seed, rng_env;   // counter-RNG key / stream of this env
 
     static constexpr unsigned FULL = 0xffffffffu;
 
@@ -845,10 +846,50 @@ struct Env {
         if (reset_pass) {
             initz = m->initial_z >= 0.f ? m->initial_z : z;
         }
-        const float tx = T[T_TX], ty = T[T_TY];
-        const double ddy = (double)ty - (double)by, ddx = (double)tx - (double)bx;
-        const float theta = atan2f(ty - by, tx - bx);
-        const double dist = sqrt(ddy * ddy + ddx * ddx);
+        float tx = T[T_TX], ty = T[T_TY];
+        double ddy = (double)ty - (double)by, ddx = (double)tx - (double)bx;
+        float theta = atan2f(ty - by, tx - bx);
+        double dist = sqrt(ddy * ddy + ddx * ddx);
+        const int kind = m->kind;
+        const bool flagrun = kind == 7 || kind == 8;
+        float flag_timeout = 0.f;
+        int flag_cnt = 0;
+        // HumanoidFlagrunHarder.calc_potential (rs/robot_locomotors.py:280-302) has side effects (crawl
+        // bookkeeping) and is evaluated once per flag move and once per step, in that order
+        const bool harder = kind == 8;
+        bool crawl_has = harder && T[T_CRAWL_HAS] != 0.f;
+        double crawl_start = harder ? __hiloint2double(__float_as_int(T[T_CRAWL_START_HI]), __float_as_int(T[T_CRAWL_START_LO])) : 0.0;
+        double crawl_ign = harder ? __hiloint2double(__float_as_int(T[T_CRAWL_IGN_HI]), __float_as_int(T[T_CRAWL_IGN_LO])) : 0.0;
+        const float leak = fminf(fmaxf(z, 0.f), 0.8f) / 0.8f + 1.0f;          // potential_leak()
+        auto harder_potential = [&](double d) {
+            double frp = -d / m->dt_scene;
+            if (z < 0.8f) {
+                if (!crawl_has) { crawl_start = frp - crawl_ign; crawl_has = true; }
+                crawl_ign = frp - crawl_start;
+                frp = crawl_start;
+            } else {
+                frp -= crawl_ign;
+                crawl_has = false;
+            }
+            return frp + (double)leak * 100.0;
+        };
+        if (flagrun) {
+            // HumanoidFlagrun.calc_state (rs/robot_locomotors.py:220-227): the flag moves when it is reached
+            // (dist < 1) or after 600 / frame_skip steps; the observation is then taken against the new flag
+            flag_timeout = T[T_FLAGTIMEOUT] - 1.f;
+            flag_cnt = __float_as_int(T[T_FLAGCNT]);
+            if (dist < 1.0 || flag_timeout <= 0.f) {
+                const unsigned ep = (unsigned)__float_as_int(T[T_EPISODE]);
+                tx = 0.5f * rng_uniform(rng_seed, rng_env, ep, 1u, 2u * flag_cnt, -m->halflen, m->halflen);
+                ty = 0.5f * rng_uniform(rng_seed, rng_env, ep, 1u, 2u * flag_cnt + 1u, -m->halfwidth, m->halfwidth);
+                flag_cnt += 1;
+                flag_timeout = 600.f / (float)m->nsub;
+                ddy = (double)ty - (double)by; ddx = (double)tx - (double)bx;
+                theta = atan2f(ty - by, tx - bx);
+                dist = sqrt(ddy * ddy + ddx * ddx);
+                if (harder) (void)harder_potential(dist);     // robot.potential = calc_potential(): value unused (quirk Q5)
+            }
+        }
         const float ang = theta - yaw;
         float sy, cy;
         sincosf(-yaw, &sy, &cy);
@@ -866,17 +907,30 @@ struct Env {
             if (gl < C::NACT) { obs_out[8 + 2 * gl] = clip5(jpos); obs_out[9 + 2 * gl] = clip5(jvel); }
             if (gl < C::NFEET) obs_out[8 + 2 * C::NACT + gl] = clip5(S[C::oF + gl]);   // previous step's flags (quirk Q2)
         }
-        const double pot_new = -dist / m->dt_scene;
         bool done = false;
+        int h_frame = 0, h_og = 0, h_att = 0;
+        float h_alive = 0.f;
+        if (harder) {
+            h_frame = __float_as_int(T[T_FRAME]); h_og = __float_as_int(T[T_ONGROUND]); h_att = __float_as_int(T[T_ATTACKS]);
+            if (!reset_pass) {
+                // alive_bonus (rs/robot_locomotors.py:250-273); it runs before the step's calc_potential
+                if (h_frame % 30 == 0 && h_frame > 100 && h_og == 0) h_att += 1;   // cube attack (cube not simulated: DESIGN.md)
+                const float zz8 = clip5(z - initz) + initz;
+                if (zz8 < 0.8f) h_og += 1; else if (h_og > 0) h_og -= 1;
+                h_frame += 1;
+                h_alive = h_og < 170 ? leak : -1.f;
+            }
+        }
+        const double pot_new = harder ? harder_potential(dist) : -dist / m->dt_scene;
         {
             // alive uses state[0] + initial_z after the float32 round trip (rs/gym_locomotion_envs.py:61)
             const float zz = (m->initial_z >= 0.f) ? (o0 + initz) : (float)((double)o0 + (double)initz);
             const float *fc = S + C::oF;
             float alive;
-            const int kind = m->kind;
             if (kind == 2 || kind == 3) alive = (zz > 0.8f && fabsf(pitch) < 1.0f) ? 1.f : -1.f;
             else if (kind == 4) alive = (fabsf(pitch) < 1.0f && fc[1] == 0.f && fc[2] == 0.f && fc[4] == 0.f && fc[5] == 0.f) ? 1.f : -1.f;
             else if (kind == 5) alive = zz > 0.26f ? 1.f : -1.f;
+            else if (kind == 8) alive = h_alive;
             else alive = zz > 0.78f ? 2.f : -1.f;
             done = alive < 0.f;
             // non-finite observation ends the episode (rs/gym_locomotion_envs.py:63-65)
@@ -896,6 +950,15 @@ struct Env {
             }
         }
         __syncwarp();
+        if (gl == 0 && pred && harder) {
+            T[T_FRAME] = __int_as_float(h_frame); T[T_ONGROUND] = __int_as_float(h_og); T[T_ATTACKS] = __int_as_float(h_att);
+            T[T_CRAWL_HAS] = crawl_has ? 1.f : 0.f;
+            T[T_CRAWL_START_LO] = __int_as_float(__double2loint(crawl_start)); T[T_CRAWL_START_HI] = __int_as_float(__double2hiint(crawl_start));
+            T[T_CRAWL_IGN_LO] = __int_as_float(__double2loint(crawl_ign)); T[T_CRAWL_IGN_HI] = __int_as_float(__double2hiint(crawl_ign));
+        }
+        if (gl == 0 && pred && flagrun) {
+            T[T_TX] = tx; T[T_TY] = ty; T[T_FLAGTIMEOUT] = flag_timeout; T[T_FLAGCNT] = __int_as_float(flag_cnt);
+        }
         if (gl == 0 && pred) {
             T[T_POT_LO] = __int_as_float(__double2loint(pot_new));
             T[T_POT_HI] = __int_as_float(__double2hiint(pot_new));
@@ -960,6 +1023,17 @@ struct Env {
                 T[T_FLOOR] = floor_in_parts ? 1.f : 0.f;
                 T[T_TX] = m->walk_tx; T[T_TY] = m->walk_ty;
                 T[T_HAVEZ] = 0.f;
+                T[T_FLAGCNT] = __int_as_float(0); T[T_FLAGTIMEOUT] = 0.f;
+                if (m->kind == 7 || m->kind == 8) {
+                    // robot_specific_reset -> flag_reposition() (rs/robot_locomotors.py:200-218)
+                    T[T_TX] = 0.5f * rng_uniform(la.seed, env, ep, 1u, 0u, -m->halflen, m->halflen);
+                    T[T_TY] = 0.5f * rng_uniform(la.seed, env, ep, 1u, 1u, -m->halfwidth, m->halfwidth);
+                    T[T_FLAGCNT] = __int_as_float(1);
+                    T[T_FLAGTIMEOUT] = 600.f / (float)m->nsub;
+                }
+                T[T_FRAME] = __int_as_float(0); T[T_ONGROUND] = __int_as_float(0); T[T_CRAWL_HAS] = 0.f;
+                T[T_CRAWL_START_LO] = T[T_CRAWL_START_HI] = T[T_CRAWL_IGN_LO] = T[T_CRAWL_IGN_HI] = 0.f;
+                T[T_ATTACKS] = __int_as_float(0);
             }
         }
         __syncwarp();
@@ -983,6 +1057,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     const unsigned long long genv = la.env_offset + (unsigned long long)env;
     const int gl = e.gl;
     e.load_lane_constants();
+    e.rng_seed = la.seed; e.rng_env = genv;
     if (B.debug && env_raw == la.debug_env) e.dbg = B.debug;
 
     float *S = e.st();

@@ -15,7 +15,7 @@ constexpr int MSUB = 32;    // max Bullet links folded into the bodies (humanoid
 constexpr int MCAND = 32;   // max ground contact candidates (humanoid: 4 spheres + 13 capsules * 2)
 constexpr int MPAIR = 72;   // max self-collision geom pairs (humanoid: 66)
 constexpr int MFEET = 8;
-constexpr int TASK_FLOATS = 16;
+constexpr int TASK_FLOATS = 24;
 
 struct DevModel {
     int nb, nj, nd, floating, ncand, npair, nact, nfeet, obs_dim, kind, maxdepth, torso_body, nlim;
@@ -49,7 +49,10 @@ struct DevModel {
 // task block of the per-env state (float slots)
 enum {
     T_POT_LO = 0, T_POT_HI = 1, T_INITZ = 2, T_STEPS = 3, T_EPISODE = 4, T_RETURN = 5, T_FLOOR = 6, T_TX = 7, T_TY = 8,
-    T_FLAGTIMEOUT = 9, T_HAVEZ = 10
+    T_FLAGTIMEOUT = 9, T_HAVEZ = 10, T_FLAGCNT = 11,
+    // HumanoidFlagrunHarder (rs/robot_locomotors.py:230-302)
+    T_FRAME = 12, T_ONGROUND = 13, T_CRAWL_HAS = 14, T_CRAWL_START_LO = 15, T_CRAWL_START_HI = 16, T_CRAWL_IGN_LO = 17,
+    T_CRAWL_IGN_HI = 18, T_ATTACKS = 19
 };
 
 struct StepBuffers {

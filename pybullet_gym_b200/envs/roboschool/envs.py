@@ -180,6 +180,32 @@ class HumanoidBulletEnv(WalkerBaseBulletEnv):
         self.stall_torque_cost = 4.25 * WalkerBaseBulletEnv.stall_torque_cost
 
 
+class HumanoidFlagrunBulletEnv(HumanoidBulletEnv):
+    random_yaw = True          # dead in the reference: the robot is built with random_yaw=False (quirk Q7)
+
+    def __init__(self, **kw):
+        self.robot = R.HumanoidFlagrun()
+        HumanoidBulletEnv.__init__(self, self.robot, **kw)
+
+    def create_single_player_scene(self, bullet_client):
+        s = HumanoidBulletEnv.create_single_player_scene(self, bullet_client)
+        s.zero_at_running_strip_start_line = False
+        return s
+
+
+class HumanoidFlagrunHarderBulletEnv(HumanoidBulletEnv):
+    random_lean = True         # dead in the reference as well (quirk Q7)
+
+    def __init__(self, **kw):
+        self.robot = R.HumanoidFlagrunHarder()
+        HumanoidBulletEnv.__init__(self, self.robot, **kw)     # the reference's `electricity_cost /= 4` is dead (quirk Q6)
+
+    def create_single_player_scene(self, bullet_client):
+        s = HumanoidBulletEnv.create_single_player_scene(self, bullet_client)
+        s.zero_at_running_strip_start_line = False
+        return s
+
+
 class InvertedPendulumBulletEnv(BaseBulletEnv):
     def __init__(self, **kw):
         self.robot = R.InvertedPendulum()
@@ -226,4 +252,6 @@ ENTRY_POINTS = {
     "HalfCheetahPyBulletEnv-v0": HalfCheetahBulletEnv,
     "AntPyBulletEnv-v0": AntBulletEnv,
     "HumanoidPyBulletEnv-v0": HumanoidBulletEnv,
+    "HumanoidFlagrunPyBulletEnv-v0": HumanoidFlagrunBulletEnv,
+    "HumanoidFlagrunHarderPyBulletEnv-v0": HumanoidFlagrunHarderBulletEnv,
 }

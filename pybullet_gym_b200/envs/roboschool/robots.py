@@ -238,6 +238,20 @@ class Humanoid(WalkerBase):
         return +2 if z > 0.78 else -1
 
 
+class HumanoidFlagrun(Humanoid):
+    def __init__(self, env_id="HumanoidFlagrunPyBulletEnv-v0"):
+        Humanoid.__init__(self, env_id)
+        self.flag = None
+        self.flag_timeout = 0
+
+
+class HumanoidFlagrunHarder(HumanoidFlagrun):
+    def __init__(self):
+        HumanoidFlagrun.__init__(self, "HumanoidFlagrunHarderPyBulletEnv-v0")
+        self.aggressive_cube = None
+        self.frame = 0
+
+
 class InvertedPendulum(MJCFBasedRobot):
     swingup = False
 

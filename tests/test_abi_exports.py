@@ -33,8 +33,6 @@ def test_model_tables_fit_their_kernels():
     from pybullet_gym_b200.spec import SPECS
     L = _lib.lib()
     for env_id, spec in SPECS.items():
-        if spec.kind >= 7:
-            continue
         t = _lib.ModelTables(spec)
         h = ctypes.c_void_p()
         rc = L.pbg_create(ctypes.byref(t.c), 8, 0, 0, 0, ctypes.byref(h))

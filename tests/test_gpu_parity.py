@@ -24,6 +24,7 @@ pytestmark = pytest.mark.gpu
 
 IDS = ["InvertedPendulumPyBulletEnv-v0", "HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
        "AntPyBulletEnv-v0", "HumanoidPyBulletEnv-v0"]
+TASK_IDS = IDS + ["HumanoidFlagrunPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0"]
 E = 48
 
 
@@ -36,7 +37,8 @@ def _oracles(oracle_lib, env_id, n, spec=None):
     from pybullet_gym_b200 import _lib
     from pybullet_gym_b200.spec import SPECS
     mc = _lib.lib().pbg_max_contacts(SPECS[env_id].kind)
-    return [oracle_lib.OracleEnv(spec if spec is not None else env_id, max_contacts=mc) for _ in range(n)]
+    # same RNG key as _mk(): seed 1, stream = env index (matters for the Flagrun target draws)
+    return [oracle_lib.OracleEnv(spec if spec is not None else env_id, seed=1, env_index=i, max_contacts=mc) for i in range(n)]
 
 
 def _rel(g, o):
@@ -58,7 +60,7 @@ def test_reset_matches_oracle(env_id, oracle_lib):
         assert np.abs(st - ost).max() < 1e-6
 
 
-@pytest.mark.parametrize("env_id", IDS)
+@pytest.mark.parametrize("env_id", TASK_IDS)
 def test_device_rng_matches_oracle_rng(env_id, oracle_lib):
     """pbg_reset's Philox draws are bit-identical to the oracle's (same seed / env index / episode)."""
     env = _mk(env_id, n=8, seed=7)
@@ -68,7 +70,7 @@ def test_device_rng_matches_oracle_rng(env_id, oracle_lib):
         assert np.abs(o.reset(floor_in_parts=True) - obs[i]).max() < 1e-5
 
 
-@pytest.mark.parametrize("env_id", IDS)
+@pytest.mark.parametrize("env_id", TASK_IDS)
 def test_observation_reward_parity_T1(env_id, oracle_lib):
     """T1: calc_state + reward terms on identical states, states sampled along oracle rollouts."""
     env = _mk(env_id)

@@ -37,6 +37,8 @@ CASES = {
     "HalfCheetahPyBulletEnv-v0": ("gym_locomotion_envs", "HalfCheetahBulletEnv", 4, 40, 1.3),
     "AntPyBulletEnv-v0": ("gym_locomotion_envs", "AntBulletEnv", 3, 60, 1.3),
     "HumanoidPyBulletEnv-v0": ("gym_locomotion_envs", "HumanoidBulletEnv", 3, 40, 1.3),
+    "HumanoidFlagrunPyBulletEnv-v0": ("gym_locomotion_envs", "HumanoidFlagrunBulletEnv", 4, 40, 1.3),
+    "HumanoidFlagrunHarderPyBulletEnv-v0": ("gym_locomotion_envs", "HumanoidFlagrunHarderBulletEnv", 2, 200, 1.0),
 }
 
 
@@ -65,14 +67,16 @@ def main():
             nlog = len(env.np_random.log)
             obs0 = env._reset()
             draws = env.np_random.log[nlog:]
-            noise = [d[3][0] for d in draws if d[0] == "uniform"]
+            flat = [v for d in draws if d[0] == "uniform" for v in d[3]]
+            noise, rec_tape = flat[:nA], None
             rec = {"noise": noise, "obs0": np.asarray(obs0, dtype=np.float64).tolist(), "steps": []}
             for t in range(max_steps):
                 a = (ascale * rng.uniform(-1, 1, nA)).astype(np.float64)   # |a| > 1 exercises quirk Q3
                 obs, rew, done, info = env._step(a)
-                st = {"a": a.tolist(), "state": env._p.orc.get_state().tolist(),
-                      "obs": np.asarray(obs, dtype=np.float64).tolist(), "reward": float(rew), "done": bool(done),
-                      "rewards": [float(r) for r in env.rewards]}
+                st = {"a": a.tolist(), "obs": np.asarray(obs, dtype=np.float64).tolist(), "reward": float(rew),
+                      "done": bool(done), "rewards": [float(r) for r in env.rewards]}
+                if t < 40:
+                    st["state"] = env._p.orc.get_state().tolist()
                 if hasattr(env.robot, "feet_contact"):
                     st["feet_contact"] = [float(f) for f in env.robot.feet_contact]
                     st["joints_at_limit"] = int(env.robot.joints_at_limit)
@@ -80,6 +84,8 @@ def main():
                 rec["steps"].append(st)
                 if done:
                     break
+            # every task-layer draw after the joint noise (flag positions, cube attacks), in order
+            rec["tape"] = [v for d in env.np_random.log[nlog:] if d[0] == "uniform" for v in d[3]][nA:]
             eps.append(rec)
         calls = dict(env._p.calls)
         out = {"env_id": env_id, "reference_class": "pybulletgym.envs.roboschool.%s:%s" % (mod, cls),
