@@ -712,37 +712,74 @@ struct Env {
                 lo_e[sl] = fr[sl] ? -mu[sl] * ln[sl] : lo[sl];
                 hi_e[sl] = fr[sl] ? mu[sl] * ln[sl] : hi[sl];
             }
-            const int t0end = two ? C::LPE : nrmax;
-            for (int it = 0; it < niter; ++it) {
-                // rows 0 .. LPE-1 live in register slot 0
-                for (int t = 0; t < t0end; ++t) {
-                    int i = t;
-                    if (t < nl) i = (it & 1) ? t : nl - 1 - t;
-                    const float d = fmaf(-r[0], dinv[0], rhs[0]);
-                    float cd = fminf(fmaxf(lmb[0] + d, lo_e[0]), hi_e[0]) - lmb[0];
-                    if (!(ln[0] > 0.f)) cd = 0.f;            // a friction row is skipped while its normal impulse is 0
-                    const float dl = shfl(cd, i);
-                    if (gl == i) lmb[0] += dl;
-                    const float *arow = Am + i * C::MAXRP;
-                    r[0] = fmaf(arow[gl], dl, r[0]);
-                    if (i == myn[0]) { ln[0] += dl; hi_e[0] = mu[0] * ln[0]; lo_e[0] = -hi_e[0]; }
-                    if (two) {
-                        r[1] = fmaf(arow[C::LPE + gl], dl, r[1]);
-                        if (i == myn[1]) { ln[1] += dl; hi_e[1] = mu[1] * ln[1]; lo_e[1] = -hi_e[1]; }
+            const int nlmax = wmax(nl);
+            const float *Ag = Am + gl;                       // this lane's column of A
+            const int myn0 = myn[0], myn1 = myn[1];
+            if (!two) {
+                // ---- every lane owns at most one row (slot 0)
+                float rhs0 = rhs[0], dinv0 = dinv[0], lam0 = lmb[0], r0 = r[0], mu0 = mu[0];
+                float lo0 = lo_e[0], hi0 = hi_e[0], ln0 = ln[0];
+                const int nrest = nr - nl;                   // contact rows of this env (normals + friction)
+                const int nrestmax = wmax(nrest);
+                for (int it = 0; it < niter; ++it) {
+                    // joint-limit rows, direction alternates per iteration
+                    for (int t = 0; t < nlmax; ++t) {
+                        const bool on = t < nl;
+                        const int i = on ? ((it & 1) ? t : nl - 1 - t) : 0;
+                        const float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
+                        float dl = shfl(cd, i);              // unconditional: both env groups of the warp take part
+                        if (!on) dl = 0.f;
+                        if (gl == i) lam0 += dl;
+                        r0 = fmaf(Ag[i * C::MAXRP], dl, r0);
+                    }
+                    // contact normals, then friction rows: row index = nl + j
+                    const float *ap = Ag + nl * C::MAXRP;
+#pragma unroll 2
+                    for (int j = 0; j < nrestmax; ++j) {
+                        const bool on = j < nrest;
+                        const int i = on ? nl + j : 0;
+                        float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
+                        if (!(ln0 > 0.f)) cd = 0.f;          // a friction row is skipped while its normal impulse is 0
+                        float dl = shfl(cd, i);
+                        if (!on) dl = 0.f;
+                        if (gl == i) lam0 += dl;
+                        r0 = fmaf(on ? ap[0] : 0.f, dl, r0);
+                        ap += C::MAXRP;
+                        if (i == myn0) { ln0 += dl; hi0 = mu0 * ln0; lo0 = -hi0; }
                     }
                 }
-                // rows LPE .. 2 LPE-1 live in register slot 1 (never limit rows: nl <= NLIM <= LPE)
-                for (int t = C::LPE; t < nrmax; ++t) {
-                    const float d = fmaf(-r[1], dinv[1], rhs[1]);
-                    float cd = fminf(fmaxf(lmb[1] + d, lo_e[1]), hi_e[1]) - lmb[1];
-                    if (!(ln[1] > 0.f)) cd = 0.f;
-                    const float dl = shfl(cd, t - C::LPE);
-                    if (gl == t - C::LPE) lmb[1] += dl;
-                    const float *arow = Am + t * C::MAXRP;
-                    r[0] = fmaf(arow[gl], dl, r[0]);
-                    r[1] = fmaf(arow[C::LPE + gl], dl, r[1]);
-                    if (t == myn[0]) { ln[0] += dl; hi_e[0] = mu[0] * ln[0]; lo_e[0] = -hi_e[0]; }
-                    if (t == myn[1]) { ln[1] += dl; hi_e[1] = mu[1] * ln[1]; lo_e[1] = -hi_e[1]; }
+                lmb[0] = lam0; r[0] = r0;
+            } else {
+                const int t0end = C::LPE;
+                for (int it = 0; it < niter; ++it) {
+                    // rows 0 .. LPE-1 live in register slot 0
+                    for (int t = 0; t < t0end; ++t) {
+                        int i = t;
+                        if (t < nl) i = (it & 1) ? t : nl - 1 - t;
+                        const float d = fmaf(-r[0], dinv[0], rhs[0]);
+                        float cd = fminf(fmaxf(lmb[0] + d, lo_e[0]), hi_e[0]) - lmb[0];
+                        if (!(ln[0] > 0.f)) cd = 0.f;
+                        const float dl = shfl(cd, i);
+                        if (gl == i) lmb[0] += dl;
+                        const float *arow = Ag + i * C::MAXRP;
+                        r[0] = fmaf(arow[0], dl, r[0]);
+                        if (i == myn0) { ln[0] += dl; hi_e[0] = mu[0] * ln[0]; lo_e[0] = -hi_e[0]; }
+                        r[1] = fmaf(arow[C::LPE], dl, r[1]);
+                        if (i == myn1) { ln[1] += dl; hi_e[1] = mu[1] * ln[1]; lo_e[1] = -hi_e[1]; }
+                    }
+                    // rows LPE .. 2 LPE-1 live in register slot 1 (never limit rows: nl <= NLIM <= LPE)
+                    for (int t = C::LPE; t < nrmax; ++t) {
+                        const float d = fmaf(-r[1], dinv[1], rhs[1]);
+                        float cd = fminf(fmaxf(lmb[1] + d, lo_e[1]), hi_e[1]) - lmb[1];
+                        if (!(ln[1] > 0.f)) cd = 0.f;
+                        const float dl = shfl(cd, t - C::LPE);
+                        if (gl == t - C::LPE) lmb[1] += dl;
+                        const float *arow = Ag + t * C::MAXRP;
+                        r[0] = fmaf(arow[0], dl, r[0]);
+                        r[1] = fmaf(arow[C::LPE], dl, r[1]);
+                        if (t == myn0) { ln[0] += dl; hi_e[0] = mu[0] * ln[0]; lo_e[0] = -hi_e[0]; }
+                        if (t == myn1) { ln[1] += dl; hi_e[1] = mu[1] * ln[1]; lo_e[1] = -hi_e[1]; }
+                    }
                 }
             }
         }
