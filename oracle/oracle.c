@@ -134,7 +134,7 @@ typedef struct {
     int la, lb;         /* links */
     int slot;           /* warm-start slot */
     v3 pa, pb, n;       /* witness points (world), normal from B to A */
-    double dist, mu;
+    double dist, mu, mu_spin, mu_roll;
 } contact;
 
 typedef struct {
@@ -443,6 +443,18 @@ static void point_jacobian(const orc_env *e, int i, const v3 pt, const v3 d, dou
     }
 }
 
+/* jacobian row: axis . (angular velocity of link i) w.r.t. u (torsional friction rows) */
+static void angular_jacobian(const orc_env *e, int i, const v3 axis, double sign, double *J) {
+    const orc_model *m = &e->m;
+    int o = m->floating ? 6 : 0, l = i;
+    while (l >= 0) {
+        int k = e->dof_of_link[l];
+        if (k >= 0) J[o + k] += sign * v3dot(axis, e->S[l]);      /* S angular part: z (revolute) / 0 (prismatic) */
+        if (m->parent[l] < 0 && m->jtype[l] == ORC_JT_FREE) for (int k2 = 0; k2 < 3; k2++) J[k2] += sign * axis[k2];
+        l = m->parent[l];
+    }
+}
+
 /* ------------------------------------------------------------------ collision */
 static void geom_world(const orc_env *e, int g, v3 a, v3 b) {
     const orc_model *m = &e->m;
@@ -492,6 +504,8 @@ static void collide(orc_env *e) {
                 v3set(ct->pa, c[0], c[1], c[2] - m->g_radius[g]);
                 v3set(ct->pb, c[0], c[1], 0.0);
                 ct->dist = dist; ct->mu = m->g_friction[g] * m->ground_friction;
+                /* btManifoldResult::calculateCombinedRolling/SpinningFriction: rollA*fricB + rollB*fricA, floor has 0 */
+                ct->mu_spin = m->torsional ? m->g_spin[g] * m->ground_friction : 0; ct->mu_roll = m->torsional ? m->g_roll[g] * m->ground_friction : 0;
             }
         }
     }
@@ -511,6 +525,8 @@ static void collide(orc_env *e) {
             for (int k = 0; k < 3; k++) ct->n[k] = d[k] / len;
             for (int k = 0; k < 3; k++) { ct->pa[k] = ca[k] - ct->n[k] * m->g_radius[ga]; ct->pb[k] = cb[k] + ct->n[k] * m->g_radius[gb]; }
             ct->dist = dist; ct->mu = m->g_friction[ga] * m->g_friction[gb];
+            ct->mu_spin = m->torsional ? m->g_spin[ga] * m->g_friction[gb] + m->g_spin[gb] * m->g_friction[ga] : 0;
+            ct->mu_roll = m->torsional ? m->g_roll[ga] * m->g_friction[gb] + m->g_roll[gb] * m->g_friction[ga] : 0;
         }
     }
     (void)nground;
@@ -640,6 +656,34 @@ static int build_rows(orc_env *e, double h) {
         r->lambda = e->warm[ct->slot] * m->warmstart;
     }
     int nnrm = nr - nrm0;
+    /* 2b. torsional friction: spinning about the normal, rolling about the two tangents (angular-only rows,
+     * bounded by coefficient * normal impulse like the lateral rows) */
+    for (int c = 0; c < e->nct && m->torsional; c++) {
+        contact *ct = &e->ct[c];
+        v3 t1, t2; const double *n = ct->n;
+        if (fabs(n[2]) > 0.7071067811865475244) {
+            double a = n[1] * n[1] + n[2] * n[2], k = 1.0 / sqrt(a);
+            v3set(t1, 0, -n[2] * k, n[1] * k); v3set(t2, a * k, -n[0] * t1[2], n[0] * t1[1]);
+        } else {
+            double a = n[0] * n[0] + n[1] * n[1], k = 1.0 / sqrt(a);
+            v3set(t1, -n[1] * k, n[0] * k, 0); v3set(t2, -n[2] * t1[1], n[2] * t1[0], a * k);
+        }
+        for (int ax = 0; ax < 3; ax++) {
+            double coef = ax == 0 ? ct->mu_spin : ct->mu_roll;
+            if (!(coef > 0)) continue;
+            const double *axis = ax == 0 ? n : (ax == 1 ? t1 : t2);
+            row *r = &e->rows[nr++];
+            memset(r, 0, sizeof(row));
+            angular_jacobian(e, ct->la, axis, 1.0, r->J);
+            if (ct->lb >= 0) angular_jacobian(e, ct->lb, axis, -1.0, r->J);
+            impulse_response(e, r->J, r->U);
+            double den = 0, rel = 0;
+            for (int k = 0; k < nu; k++) { den += r->J[k] * r->U[k]; rel += r->J[k] * u[k]; }
+            r->dinv = den > 1e-12 ? 1.0 / den : 0.0;
+            r->rhs = -rel * r->dinv;
+            r->mu = coef; r->lo = -coef; r->hi = coef; r->fric_of = nrm0 + c;
+        }
+    }
     for (int c = 0; c < e->nct; c++) {
         contact *ct = &e->ct[c];
         /* btPlaneSpace1 */

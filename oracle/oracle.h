@@ -63,6 +63,9 @@ typedef struct {
     double walk_target_x, walk_target_y;
     int32_t max_episode_steps;
     double stadium_halflen, stadium_halfwidth;   /* rs/scene_stadium.py:13-14, Flagrun target range */
+    /* torsional friction rows (spinning about the normal, rolling about the two tangents), SURVEY C1.11 / C6-9 */
+    int32_t torsional;
+    const double *g_spin, *g_roll;            /* [ng] 2nd / 3rd MJCF friction numbers */
 } orc_model;
 
 typedef struct orc_env orc_env;

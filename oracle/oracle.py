@@ -50,6 +50,7 @@ class OrcModel(C.Structure):
         ("walk_target_x", C.c_double), ("walk_target_y", C.c_double),
         ("max_episode_steps", C.c_int32),
         ("stadium_halflen", C.c_double), ("stadium_halfwidth", C.c_double),
+        ("torsional", C.c_int32), ("g_spin", _pd), ("g_roll", _pd),
     ]
 
 
@@ -135,12 +136,14 @@ class OracleModel:
         keep["damping"] = _d([l.damping for l in L])
         keep["in_parts"] = _i([1 if (l.name in part_names and (i > 0 or bm.floating)) else 0 for i, l in enumerate(L)])
         g_link, g_type, g_ground, g_rad, g_p0, g_p1, g_fr, g_thr = [], [], [], [], [], [], [], []
+        g_spin, g_roll = [], []
         filt = []
         for i, l in enumerate(L):
             for g in l.geoms:
                 g_link.append(i); g_type.append(g.gtype); g_rad.append(g.radius)
                 g_p0.append(g.p0); g_p1.append(g.p1); g_fr.append(g.friction); g_thr.append(l.contact_threshold)
                 g_ground.append(1 if ((g.contype & ~2) or (2 & g.conaffinity)) else 0)
+                g_spin.append(g.spin_friction); g_roll.append(g.roll_friction)
                 filt.append((g.contype, g.conaffinity))
         ng = len(g_link)
         pa, pb = [], []
@@ -157,6 +160,7 @@ class OracleModel:
         keep["g_link"], keep["g_type"], keep["g_ground"] = _i(g_link), _i(g_type), _i(g_ground)
         keep["g_radius"], keep["g_p0"], keep["g_p1"] = _d(g_rad), _d(g_p0).reshape(-1), _d(g_p1).reshape(-1)
         keep["g_friction"], keep["g_threshold"] = _d(g_fr), _d(g_thr)
+        keep["g_spin"], keep["g_roll"] = _d(g_spin), _d(g_roll)
         keep["pair_a"], keep["pair_b"] = _i(pa), _i(pb)
         oj = bm.ordered_joints()
         names = [L[i].joint_name for i in oj]
@@ -185,6 +189,7 @@ class OracleModel:
         m.walk_target_x, m.walk_target_y = spec.walk_target
         m.max_episode_steps = spec.max_episode_steps
         m.stadium_halflen, m.stadium_halfwidth = sc.stadium_halflen, sc.stadium_halfwidth
+        m.torsional = int(getattr(sc, 'torsional_friction', False))
         for k, v in overrides.items():
             setattr(m, k, v)
         self.c = m

@@ -115,6 +115,8 @@ class Geom:
     contype: int
     conaffinity: int
     multisphere: bool = True       # fromto capsule (tight AABB) vs pos/quat capsule
+    spin_friction: float = 0.0     # 2nd / 3rd number of the MJCF friction attribute (C1.11)
+    roll_friction: float = 0.0
 
 
 @dataclass
@@ -200,7 +202,10 @@ def _parse_geom(elem, dflt: _Defaults, rules: ImporterRules, angle_scale):
     a.update(elem.attrib)
     gtype = a.get("type", "sphere")
     size = _vec(a.get("size"), None, [0.0])
-    fric = _vec(a.get("friction"), None, [1.0, 0.005, 0.0001])[0]
+    fr3 = _vec(a.get("friction"), None, [1.0, 0.0, 0.0])
+    fric = fr3[0]
+    spin = fr3[1] if len(fr3) > 1 else 0.0
+    roll = fr3[2] if len(fr3) > 2 else 0.0
     contype = int(a.get("contype", 1))
     conaff = int(a.get("conaffinity", 1))
     name = a.get("name", "")
@@ -222,6 +227,7 @@ def _parse_geom(elem, dflt: _Defaults, rules: ImporterRules, angle_scale):
         g = Geom(name, G_BOX, 0.0, pos.copy(), np.array(size[:3], float), rot, fric, contype, conaff)
     else:
         raise NotImplementedError("geom type %s" % gtype)
+    g.spin_friction, g.roll_friction = float(spin), float(roll)
     return g, shift
 
 
@@ -447,6 +453,8 @@ class ReducedModel:
     geom_p0: np.ndarray             # [ng,3]
     geom_p1: np.ndarray             # [ng,3]
     geom_friction: np.ndarray
+    geom_spin: np.ndarray           # spinning / rolling friction coefficients (torsional friction rows)
+    geom_roll: np.ndarray
     geom_threshold: np.ndarray      # contact breaking threshold of the owning link
     geom_ground: np.ndarray         # 1 if it collides with the floor plane
     pair_a: np.ndarray              # self-collision geom pairs
@@ -557,7 +565,7 @@ def reduce_model(model: BulletModel, action_joint_names: Optional[List[str]] = N
             else:
                 g1 = Rb[b].T @ (p0[i] + R0[i] @ g.p1 - com_w[b])
             geom_rows.append((b, si, g.gtype, g.radius, g0, g1, g.friction, l.contact_threshold, g.contype,
-                              g.conaffinity, i))
+                              g.conaffinity, i, g.spin_friction, g.roll_friction))
 
     q0 = np.zeros((nb, 4))
     anchor_p = np.zeros((nb, 3))
@@ -625,6 +633,7 @@ def reduce_model(model: BulletModel, action_joint_names: Optional[List[str]] = N
         geom_p0=np.array([g[4] for g in geom_rows]).reshape(-1, 3),
         geom_p1=np.array([g[5] for g in geom_rows]).reshape(-1, 3),
         geom_friction=np.array([g[6] for g in geom_rows]), geom_threshold=np.array([g[7] for g in geom_rows]),
+        geom_spin=np.array([g[11] for g in geom_rows]), geom_roll=np.array([g[12] for g in geom_rows]),
         geom_ground=geom_ground, pair_a=np.array(pair_a, np.int32), pair_b=np.array(pair_b, np.int32),
         base_link_off=base_link_off, link_damping=model.rules.link_damping)
 

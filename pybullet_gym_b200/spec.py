@@ -41,6 +41,7 @@ class SceneSpec:
     limit_max_impulse: float = 100.0
     limit_split_impulse: bool = False   # see DESIGN.md "limit rows"
     split_impulse_threshold: float = -0.04
+    torsional_friction: bool = False     # spinning / rolling friction rows (C1.11, C6-9)
 
     @property
     def dt(self) -> float:

@@ -32,8 +32,10 @@ for c in sel:
     print(c, {n: run(n,r,s) for n in names}, flush=True)
 
 # torque-scale probe
+import sys
+if "torque" not in sys.argv: sys.argv.append("skiptorque")
 print("--- torque scale")
-for sc in (0.25, 0.5, 2.0):
+for sc in ((0.25, 0.5, 2.0) if "torque" in sys.argv else ()):
     res = {}
     for n in names:
         eid=n+"PyBulletEnv-v0"; w=np.load("tests/golden/policy_%s.npz"%n)
@@ -47,3 +49,7 @@ for sc in (0.25, 0.5, 2.0):
             out.append((round(score),k))
         res[n]=out
     print("power x%.2f"%sc, res, flush=True)
+
+print("--- torsional friction rows")
+for kw in (dict(torsional_friction=True), dict(torsional_friction=True, warmstarting_factor=0.85)):
+    print(kw, {n: run(n, None, kw, eps=3) for n in names}, flush=True)
