@@ -16,7 +16,7 @@
 
 #define MAXL 48
 #define MAXD 32
-#define MAXU (MAXD + 6)
+#define MAXU (MAXD + 12)        /* base 6 + joints + cube 6 */
 #define MAXG 32
 #define MAXCAND 160
 #define MAXROWS 256
@@ -129,9 +129,11 @@ static double rng_uniform(uint64_t seed, uint64_t env, uint32_t ep, uint32_t n, 
 struct orc_env;
 static double draw(struct orc_env *e, uint32_t stream, uint32_t n, float lo, float hi);
 
+#define LINK_FLOOR (-1)
+#define LINK_CUBE (-2)
 typedef struct {
-    int ga, gb;         /* geom (gb = -1: floor) */
-    int la, lb;         /* links */
+    int ga, gb;         /* geom (gb = -1: floor or cube) */
+    int la, lb;         /* links; LINK_FLOOR, LINK_CUBE for the other bodies */
     int slot;           /* warm-start slot */
     v3 pa, pb, n;       /* witness points (world), normal from B to A */
     double dist, mu, mu_spin, mu_roll;
@@ -148,7 +150,9 @@ struct orc_env {
     orc_model m;
     uint64_t seed, env_index;
     uint32_t episode;
-    int nd, nu;                 /* joint dofs, total generalized velocities */
+    int nd, nu;                 /* joint dofs, generalized velocities of the robot */
+    int nut;                    /* nu + 6 when the world holds the cube */
+    double xp[3], xq[4], xw[3], xv[3];   /* cube: COM position, orientation (xyzw), angular / linear velocity */
     int dof_of_link[MAXL], link_of_dof[MAXD];
     /* state */
     double bpos[3], bquat[4], bomega[3], bvel[3];
@@ -193,7 +197,7 @@ int orc_num_dofs(const orc_model *m) {
     for (int i = 0; i < m->nl; i++) if (m->jtype[i] == ORC_JT_REVOLUTE || m->jtype[i] == ORC_JT_PRISMATIC) n++;
     return n;
 }
-int orc_state_size(const orc_model *m) { return (m->floating ? 13 : 0) + 2 * orc_num_dofs(m); }
+int orc_state_size(const orc_model *m) { return (m->floating ? 13 : 0) + 2 * orc_num_dofs(m) + (m->cube ? 13 : 0); }
 
 orc_env *orc_create(const orc_model *m, uint64_t seed, uint64_t env_index) {
     orc_env *e = (orc_env *)calloc(1, sizeof(orc_env));
@@ -205,7 +209,9 @@ orc_env *orc_create(const orc_model *m, uint64_t seed, uint64_t env_index) {
         if (m->jtype[i] == ORC_JT_REVOLUTE || m->jtype[i] == ORC_JT_PRISMATIC) { e->dof_of_link[i] = n; e->link_of_dof[n] = i; n++; }
     }
     e->nd = n; e->nu = n + (m->floating ? 6 : 0);
-    e->bquat[3] = 1.0;
+    e->nut = e->nu + (m->cube ? 6 : 0);
+    e->bquat[3] = 1.0; e->xq[3] = 1.0;
+    for (int k = 0; k < 3; k++) e->xp[k] = m->cube_pos0[k];
     e->walk_target_x = m->walk_target_x; e->walk_target_y = m->walk_target_y;
     return e;
 }
@@ -221,6 +227,12 @@ void orc_get_state(const orc_env *e, double *s) {
     }
     for (int i = 0; i < e->nd; i++) s[o++] = e->q[i];
     for (int i = 0; i < e->nd; i++) s[o++] = e->qd[i];
+    if (e->m.cube) {
+        for (int i = 0; i < 3; i++) s[o++] = e->xp[i];
+        for (int i = 0; i < 4; i++) s[o++] = e->xq[i];
+        for (int i = 0; i < 3; i++) s[o++] = e->xw[i];
+        for (int i = 0; i < 3; i++) s[o++] = e->xv[i];
+    }
 }
 void orc_set_state(orc_env *e, const double *s) {
     int o = 0;
@@ -232,6 +244,12 @@ void orc_set_state(orc_env *e, const double *s) {
     }
     for (int i = 0; i < e->nd; i++) e->q[i] = s[o++];
     for (int i = 0; i < e->nd; i++) e->qd[i] = s[o++];
+    if (e->m.cube) {
+        for (int i = 0; i < 3; i++) e->xp[i] = s[o++];
+        for (int i = 0; i < 4; i++) e->xq[i] = s[o++];
+        for (int i = 0; i < 3; i++) e->xw[i] = s[o++];
+        for (int i = 0; i < 3; i++) e->xv[i] = s[o++];
+    }
     memset(e->warm, 0, sizeof(e->warm));
 }
 
@@ -419,6 +437,10 @@ static void impulse_response(orc_env *e, const double *f, double *du) {
         o = 6;
     }
     for (int d = 0; d < e->nd; d++) du[o + d] = qdd[d];
+    if (m->cube) {
+        /* the cube is a btMultiBody without links: M^-1 = diag(1/I, 1/m) (isotropic box inertia) */
+        for (int k = 0; k < 3; k++) { du[e->nu + k] = f[e->nu + k] / m->cube_inertia; du[e->nu + 3 + k] = f[e->nu + 3 + k] / m->cube_mass; }
+    }
 }
 
 /* jacobian row: d . (velocity of world point pt rigidly attached to link i) w.r.t. u */
@@ -426,6 +448,11 @@ static void point_jacobian(const orc_env *e, int i, const v3 pt, const v3 d, dou
     const orc_model *m = &e->m;
     int o = m->floating ? 6 : 0;
     int l = i;
+    if (i == LINK_CUBE) {
+        v3 r, rd; v3sub(r, pt, e->xp); v3cross(rd, r, d);
+        for (int k = 0; k < 3; k++) { J[e->nu + k] += sign * rd[k]; J[e->nu + 3 + k] += sign * d[k]; }
+        return;
+    }
     while (l >= 0) {
         int k = e->dof_of_link[l];
         if (k >= 0) {
@@ -447,6 +474,7 @@ static void point_jacobian(const orc_env *e, int i, const v3 pt, const v3 d, dou
 static void angular_jacobian(const orc_env *e, int i, const v3 axis, double sign, double *J) {
     const orc_model *m = &e->m;
     int o = m->floating ? 6 : 0, l = i;
+    if (i == LINK_CUBE) { for (int k = 0; k < 3; k++) J[e->nu + k] += sign * axis[k]; return; }
     while (l >= 0) {
         int k = e->dof_of_link[l];
         if (k >= 0) J[o + k] += sign * v3dot(axis, e->S[l]);      /* S angular part: z (revolute) / 0 (prismatic) */
@@ -485,6 +513,29 @@ static void closest_seg_seg(const v3 p1, const v3 q1, const v3 p2, const v3 q2, 
     for (int k = 0; k < 3; k++) { c1[k] = p1[k] + d1[k] * s; c2[k] = p2[k] + d2[k] * t; }
 }
 
+/* Closest points of the segment p0-p1 and an origin-centred box with half extents h, everything in
+ * the box frame.  The squared distance of the segment point P(t) to the box is convex and piecewise
+ * quadratic in t; its derivative is monotone, so 32 bisection steps on t in [0,1] pin the minimiser
+ * (the CUDA kernel runs the same iteration in fp32).  Bullet uses GJK/EPA for box-vs-multisphere; this
+ * is the exact closest-point pair GJK converges to for separated shapes. */
+static void closest_seg_box(const v3 p0, const v3 p1, double h, v3 cs, v3 cb) {
+    v3 d; v3sub(d, p1, p0);
+    double lo = 0.0, hi = 1.0;
+    for (int it = 0; it < 32; it++) {
+        double t = 0.5 * (lo + hi), g = 0.0;
+        for (int k = 0; k < 3; k++) {
+            double x = p0[k] + t * d[k], c = x < -h ? -h : (x > h ? h : x);
+            g += (x - c) * d[k];
+        }
+        if (g < 0.0) lo = t; else hi = t;
+    }
+    double t = 0.5 * (lo + hi);
+    for (int k = 0; k < 3; k++) {
+        double x = p0[k] + t * d[k];
+        cs[k] = x; cb[k] = x < -h ? -h : (x > h ? h : x);
+    }
+}
+
 static void collide(orc_env *e) {
     const orc_model *m = &e->m;
     static __thread contact all[MAXCAND];
@@ -509,6 +560,19 @@ static void collide(orc_env *e) {
             }
         }
     }
+    /* cube corners against the floor (box-vs-plane manifold: the corners within the breaking threshold) */
+    m3 Rx; q2m(Rx, e->xq);
+    if (m->cube) for (int k = 0; k < 8; k++, slot++) {
+        e->cand_active[slot] = 0;
+        v3 cl = {(k & 1) ? m->cube_half : -m->cube_half, (k & 2) ? m->cube_half : -m->cube_half, (k & 4) ? m->cube_half : -m->cube_half};
+        v3 c; m3mulv(c, Rx, cl); v3add(c, c, e->xp);
+        if (c[2] < m->cube_threshold) {
+            contact *ct = &all[n++];
+            ct->ga = -1; ct->gb = -1; ct->la = LINK_CUBE; ct->lb = LINK_FLOOR; ct->slot = slot;
+            v3set(ct->n, 0, 0, 1); v3cpy(ct->pa, c); v3set(ct->pb, c[0], c[1], 0.0);
+            ct->dist = c[2]; ct->mu = m->cube_friction * m->ground_friction; ct->mu_spin = 0; ct->mu_roll = 0;
+        }
+    }
     int nground = n;
     for (int pi = 0; pi < m->npair; pi++, slot++) {
         e->cand_active[slot] = 0;
@@ -527,6 +591,25 @@ static void collide(orc_env *e) {
             ct->dist = dist; ct->mu = m->g_friction[ga] * m->g_friction[gb];
             ct->mu_spin = m->torsional ? m->g_spin[ga] * m->g_friction[gb] + m->g_spin[gb] * m->g_friction[ga] : 0;
             ct->mu_roll = m->torsional ? m->g_roll[ga] * m->g_friction[gb] + m->g_roll[gb] * m->g_friction[ga] : 0;
+        }
+    }
+    /* robot geoms against the cube (default URDF filter: group 1, mask all -> every contype-1 geom collides) */
+    if (m->cube) for (int g = 0; g < m->ng; g++, slot++) {
+        e->cand_active[slot] = 0;
+        v3 a, b, al, bl, t, cs, cb; geom_world(e, g, a, b);
+        m3 Rxt; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rxt[i][j] = Rx[j][i];
+        v3sub(t, a, e->xp); m3mulv(al, Rxt, t); v3sub(t, b, e->xp); m3mulv(bl, Rxt, t);
+        closest_seg_box(al, bl, m->cube_half, cs, cb);
+        v3 dl, d; v3sub(dl, cs, cb); m3mulv(d, Rx, dl);
+        double len = v3norm(d), dist = len - m->g_radius[g];
+        double thr = m->g_threshold[g] < m->cube_threshold ? m->g_threshold[g] : m->cube_threshold;
+        if (dist < thr && len > 1e-9) {
+            contact *ct = &all[n++];
+            ct->ga = g; ct->gb = -1; ct->la = m->g_link[g]; ct->lb = LINK_CUBE; ct->slot = slot;
+            v3 csw, cbw; m3mulv(csw, Rx, cs); v3add(csw, csw, e->xp); m3mulv(cbw, Rx, cb); v3add(cbw, cbw, e->xp);
+            for (int k = 0; k < 3; k++) ct->n[k] = d[k] / len;
+            for (int k = 0; k < 3; k++) { ct->pa[k] = csw[k] - ct->n[k] * m->g_radius[g]; ct->pb[k] = cbw[k]; }
+            ct->dist = dist; ct->mu = m->g_friction[g] * m->cube_friction; ct->mu_spin = 0; ct->mu_roll = 0;
         }
     }
     (void)nground;
@@ -554,16 +637,22 @@ static void clamp_u(orc_env *e) {
         if (e->bvel[k] > mv) e->bvel[k] = mv; if (e->bvel[k] < -mv) e->bvel[k] = -mv;
     }
     for (int d = 0; d < e->nd; d++) { if (e->qd[d] > mv) e->qd[d] = mv; if (e->qd[d] < -mv) e->qd[d] = -mv; }
+    if (e->m.cube) for (int k = 0; k < 3; k++) {
+        if (e->xw[k] > mv) e->xw[k] = mv; if (e->xw[k] < -mv) e->xw[k] = -mv;
+        if (e->xv[k] > mv) e->xv[k] = mv; if (e->xv[k] < -mv) e->xv[k] = -mv;
+    }
 }
 static void get_u(const orc_env *e, double *u) {
     int o = 0;
     if (e->m.floating) { for (int k = 0; k < 3; k++) { u[k] = e->bomega[k]; u[3 + k] = e->bvel[k]; } o = 6; }
     for (int d = 0; d < e->nd; d++) u[o + d] = e->qd[d];
+    if (e->m.cube) for (int k = 0; k < 3; k++) { u[e->nu + k] = e->xw[k]; u[e->nu + 3 + k] = e->xv[k]; }
 }
 static void add_u(orc_env *e, const double *du, double s) {
     int o = 0;
     if (e->m.floating) { for (int k = 0; k < 3; k++) { e->bomega[k] += s * du[k]; e->bvel[k] += s * du[3 + k]; } o = 6; }
     for (int d = 0; d < e->nd; d++) e->qd[d] += s * du[o + d];
+    if (e->m.cube) for (int k = 0; k < 3; k++) { e->xw[k] += s * du[e->nu + k]; e->xv[k] += s * du[e->nu + 3 + k]; }
     clamp_u(e);
 }
 
@@ -608,12 +697,20 @@ static void forward_dynamics(orc_env *e, double h) {
         o = 6;
     }
     for (int d = 0; d < e->nd; d++) du[o + d] = qdd[d];
+    if (m->cube) {
+        /* free body with isotropic inertia: gravity + Bullet's base damping; no gyroscopic term */
+        double vn = v3norm(e->xv), wn = v3norm(e->xw);
+        for (int k = 0; k < 3; k++) {
+            du[e->nu + k] = -e->xw[k] * (kd + kd * wn);
+            du[e->nu + 3 + k] = -e->xv[k] * (kd + kd * vn) - (k == 2 ? m->gravity : 0.0);
+        }
+    }
     add_u(e, du, h);
 }
 
 static int build_rows(orc_env *e, double h) {
     const orc_model *m = &e->m;
-    int nr = 0, nu = e->nu, o = m->floating ? 6 : 0;
+    int nr = 0, nu = e->nut, o = m->floating ? 6 : 0;
     double u[MAXU]; get_u(e, u);
     /* 1. joint limits (btMultiBodyJointLimitConstraint): only violated sides produce a row */
     for (int d = 0; d < e->nd; d++) {
@@ -644,7 +741,7 @@ static int build_rows(orc_env *e, double h) {
         row *r = &e->rows[nr++];
         memset(r, 0, sizeof(row));
         point_jacobian(e, ct->la, ct->pa, ct->n, 1.0, r->J);
-        if (ct->lb >= 0) point_jacobian(e, ct->lb, ct->pb, ct->n, -1.0, r->J);
+        if (ct->lb != LINK_FLOOR) point_jacobian(e, ct->lb, ct->pb, ct->n, -1.0, r->J);
         impulse_response(e, r->J, r->U);
         double den = 0, rel = 0;
         for (int k = 0; k < nu; k++) { den += r->J[k] * r->U[k]; rel += r->J[k] * u[k]; }
@@ -675,7 +772,7 @@ static int build_rows(orc_env *e, double h) {
             row *r = &e->rows[nr++];
             memset(r, 0, sizeof(row));
             angular_jacobian(e, ct->la, axis, 1.0, r->J);
-            if (ct->lb >= 0) angular_jacobian(e, ct->lb, axis, -1.0, r->J);
+            if (ct->lb != LINK_FLOOR) angular_jacobian(e, ct->lb, axis, -1.0, r->J);
             impulse_response(e, r->J, r->U);
             double den = 0, rel = 0;
             for (int k = 0; k < nu; k++) { den += r->J[k] * r->U[k]; rel += r->J[k] * u[k]; }
@@ -700,7 +797,7 @@ static int build_rows(orc_env *e, double h) {
             row *r = &e->rows[nr++];
             memset(r, 0, sizeof(row));
             point_jacobian(e, ct->la, ct->pa, t, 1.0, r->J);
-            if (ct->lb >= 0) point_jacobian(e, ct->lb, ct->pb, t, -1.0, r->J);
+            if (ct->lb != LINK_FLOOR) point_jacobian(e, ct->lb, ct->pb, t, -1.0, r->J);
             impulse_response(e, r->J, r->U);
             double den = 0, rel = 0;
             for (int k = 0; k < nu; k++) { den += r->J[k] * r->U[k]; rel += r->J[k] * u[k]; }
@@ -714,7 +811,7 @@ static int build_rows(orc_env *e, double h) {
 }
 
 static void solve_rows(orc_env *e, int packed) {
-    int nlim = packed >> 16, nr = packed & 0xffff, nu = e->nu;
+    int nlim = packed >> 16, nr = packed & 0xffff, nu = e->nut;
     e->last_nlim = nlim; e->last_nr = nr;
     int nnrm = e->nct, nrm0 = nlim, fr0 = nlim + nnrm;
     double dv[MAXU];
@@ -743,19 +840,27 @@ static void solve_rows(orc_env *e, int packed) {
     for (int c = 0; c < e->nct; c++) e->warm[e->ct[c].slot] = e->rows[nrm0 + c].lambda;
 }
 
+/* btMultiBody::stepPositionsMultiDof quaternion update (exponential map of omega*h) */
+static void integrate_quat(double quat[4], const double omega[3], double h) {
+    double w = v3norm(omega), ax[3];
+    if (w * h > 0.25 * M_PI) w = 0.5 * (0.5 * M_PI) / h;
+    double sc;
+    if (w < 0.001) sc = 0.5 * h - h * h * h * 0.020833333333 * w * w; else sc = sin(0.5 * w * h) / w;
+    for (int k = 0; k < 3; k++) ax[k] = omega[k] * sc;
+    double dq[4] = {ax[0], ax[1], ax[2], cos(0.5 * w * h)}, qn[4];
+    qmul(qn, dq, quat);
+    double nn = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+    for (int k = 0; k < 4; k++) quat[k] = qn[k] / nn;
+}
+
 static void integrate(orc_env *e, double h) {
     if (e->m.floating) {
         for (int k = 0; k < 3; k++) e->bpos[k] += e->bvel[k] * h;
-        /* btMultiBody::stepPositionsMultiDof quaternion update (exponential map of omega*h) */
-        double w = v3norm(e->bomega), ax[3];
-        if (w * h > 0.25 * M_PI) w = 0.5 * (0.5 * M_PI) / h;
-        double sc;
-        if (w < 0.001) sc = 0.5 * h - h * h * h * 0.020833333333 * w * w; else sc = sin(0.5 * w * h) / w;
-        for (int k = 0; k < 3; k++) ax[k] = e->bomega[k] * sc;
-        double dq[4] = {ax[0], ax[1], ax[2], cos(0.5 * w * h)}, qn[4];
-        qmul(qn, dq, e->bquat);
-        double nn = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
-        for (int k = 0; k < 4; k++) e->bquat[k] = qn[k] / nn;
+        integrate_quat(e->bquat, e->bomega, h);
+    }
+    if (e->m.cube) {
+        for (int k = 0; k < 3; k++) e->xp[k] += e->xv[k] * h;
+        integrate_quat(e->xq, e->xw, h);
     }
     for (int d = 0; d < e->nd; d++) e->q[d] += e->qd[d] * h;
 }
@@ -819,11 +924,18 @@ static double alive_bonus(orc_env *e, double z, double pitch) {
         return (fabs(pitch) < 1.0 && !e->feet_contact[1] && !e->feet_contact[2] && !e->feet_contact[4] && !e->feet_contact[5]) ? 1 : -1;
     case ORC_KIND_ANT: return z > 0.26 ? 1 : -1;
     case ORC_KIND_FLAGRUN_HARDER:
-        /* rs/robot_locomotors.py:250-273; the cube itself is not simulated, its RNG draws are */
+        /* rs/robot_locomotors.py:250-273: every 30 frames after frame 100 the cube is thrown at the spot the
+         * robot will be at when it arrives */
         if (e->frame % 30 == 0 && e->frame > 100 && e->on_ground == 0) {
-            (void)draw(e, 2, 5u * e->attacks, -3.14f, 3.14f); (void)draw(e, 2, 5u * e->attacks + 1u, 20.f, 30.f);
-            for (int k = 0; k < 3; k++) (void)draw(e, 2, 5u * e->attacks + 2u + k, -1.f, 1.f);
+            double angle = draw(e, 2, 5u * e->attacks, -3.14f, 3.14f), speed = draw(e, 2, 5u * e->attacks + 1u, 20.f, 30.f);
+            double ttt = 4.0 / speed, tgt[3], pos[3], vel[3], nrm = 0;
+            for (int k = 0; k < 3; k++) tgt[k] = e->body_xyz[k] + e->torso_speed[k] * ttt;
+            pos[0] = tgt[0] + 4.0 * cos(angle); pos[1] = tgt[1] + 4.0 * sin(angle); pos[2] = tgt[2] + 1.0;
+            for (int k = 0; k < 3; k++) { vel[k] = tgt[k] - pos[k]; nrm += vel[k] * vel[k]; }
+            nrm = sqrt(nrm);
+            for (int k = 0; k < 3; k++) vel[k] = vel[k] * (speed / nrm) + draw(e, 2, 5u * e->attacks + 2u + k, -1.f, 1.f);
             e->attacks++;
+            if (e->m.cube) for (int k = 0; k < 3; k++) { e->xp[k] = pos[k]; e->xv[k] = vel[k]; e->xw[k] = 0; }   /* orientation kept */
         }
         if (z < 0.8) e->on_ground++; else if (e->on_ground > 0) e->on_ground--;
         e->frame++;
@@ -929,7 +1041,7 @@ static void update_feet_contact(orc_env *e) {
     const orc_model *m = &e->m;
     for (int f = 0; f < m->nfeet; f++) {
         double v = 0;
-        for (int c = 0; c < e->nct; c++) if (e->ct[c].gb < 0 && e->ct[c].la == m->foot_link[f]) v = 1.0;
+        for (int c = 0; c < e->nct; c++) if (e->ct[c].lb == LINK_FLOOR && e->ct[c].la == m->foot_link[f]) v = 1.0;
         e->feet_contact[f] = v;
     }
 }
@@ -989,6 +1101,11 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
     } else {
         e->q[1] = noise[0] + (m->kind == ORC_KIND_PENDULUM_SWINGUP ? 3.1415 : 0.0);
     }
+    if (m->cube) {
+        /* restoreState + resetBasePositionAndOrientation(cube, [-1.5,0,0.05], identity) (rs/robot_locomotors.py:240-243) */
+        for (int k = 0; k < 3; k++) { e->xp[k] = m->cube_pos0[k]; e->xw[k] = 0; e->xv[k] = 0; e->xq[k] = 0; }
+        e->xq[3] = 1.0;
+    }
     for (int f = 0; f < MAXFEET; f++) e->feet_contact[f] = 0;
     e->steps = 0; e->nct = 0;
     e->floor_in_parts = floor_in_parts;
@@ -1042,6 +1159,14 @@ int orc_get_contacts(const orc_env *e, int32_t *la, int32_t *lb, double *dist) {
 }
 void orc_set_joint(orc_env *e, int dof, double q, double qd) { e->q[dof] = q; e->qd[dof] = qd; }
 void orc_get_joint(const orc_env *e, int dof, double *q, double *qd) { *q = e->q[dof]; *qd = e->qd[dof]; }
+void orc_set_cube(orc_env *e, const double *pos, const double *quat, const double *omega, const double *vel) {
+    for (int k = 0; k < 3; k++) { if (pos) e->xp[k] = pos[k]; if (omega) e->xw[k] = omega[k]; if (vel) e->xv[k] = vel[k]; }
+    if (quat) for (int k = 0; k < 4; k++) e->xq[k] = quat[k];
+}
+void orc_get_cube(const orc_env *e, double *pos, double *quat, double *omega, double *vel) {
+    for (int k = 0; k < 3; k++) { if (pos) pos[k] = e->xp[k]; if (omega) omega[k] = e->xw[k]; if (vel) vel[k] = e->xv[k]; }
+    if (quat) for (int k = 0; k < 4; k++) quat[k] = e->xq[k];
+}
 
 /* rows of the last substep: out = [nlim, nct, then per row rhs, dinv, lambda]; returns the row count */
 int orc_get_rows(const orc_env *e, double *out) {
@@ -1071,7 +1196,7 @@ void orc_mass_matrix_inv(orc_env *e, double *Minv) {
     int nu = e->nu;
     for (int k = 0; k < nu; k++) {
         double f[MAXU], du[MAXU];
-        for (int i = 0; i < nu; i++) f[i] = 0;
+        for (int i = 0; i < MAXU; i++) f[i] = 0;
         f[k] = 1.0;
         impulse_response(e, f, du);
         for (int i = 0; i < nu; i++) Minv[i * nu + k] = du[i];

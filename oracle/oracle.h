@@ -66,11 +66,17 @@ typedef struct {
     /* torsional friction rows (spinning about the normal, rolling about the two tangents), SURVEY C1.11 / C6-9 */
     int32_t torsional;
     const double *g_spin, *g_roll;            /* [ng] 2nd / 3rd MJCF friction numbers */
+    /* HumanoidFlagrunHarder's aggressive cube: a second free body (rs/robot_locomotors.py:236-266,
+     * gym_utils.py:9-16, assets/things/cube_small.urdf).  cube = 0: absent */
+    int32_t cube;
+    double cube_half, cube_mass, cube_inertia, cube_friction, cube_threshold;
+    double cube_pos0[3];
 } orc_model;
 
 typedef struct orc_env orc_env;
 
-/* canonical state: [base pos(3) quat(4 xyzw) omega(3) vel(3)] (floating only) + q[nd] + qd[nd] */
+/* canonical state: [base pos(3) quat(4 xyzw) omega(3) vel(3)] (floating only) + q[nd] + qd[nd]
+ * + [cube pos(3) quat(4) omega(3) vel(3)] (models with a cube only) */
 int orc_state_size(const orc_model *m);
 int orc_num_dofs(const orc_model *m);
 
@@ -94,6 +100,10 @@ void orc_link_state(orc_env *e, double *out /* [nl*10]: com3 quat4 vel3 */);
 int orc_get_contacts(const orc_env *e, int32_t *la, int32_t *lb, double *dist);
 void orc_set_joint(orc_env *e, int dof, double q, double qd);
 void orc_get_joint(const orc_env *e, int dof, double *q, double *qd);
+/* cube pose / velocity access (resetBasePositionAndOrientation / resetBaseVelocity / getBasePositionAndOrientation
+ * on the cube body); NULL arguments are left unchanged / not written */
+void orc_set_cube(orc_env *e, const double *pos, const double *quat, const double *omega, const double *vel);
+void orc_get_cube(const orc_env *e, double *pos, double *quat, double *omega, double *vel);
 /* replay tape: when set, every random draw of the task layer (flag positions, cube attack) is read from it
  * in order instead of the counter RNG -- used to replay the reference's np_random draws */
 void orc_set_tape(orc_env *e, const double *tape, int n);

@@ -51,6 +51,9 @@ class OrcModel(C.Structure):
         ("max_episode_steps", C.c_int32),
         ("stadium_halflen", C.c_double), ("stadium_halfwidth", C.c_double),
         ("torsional", C.c_int32), ("g_spin", _pd), ("g_roll", _pd),
+        ("cube", C.c_int32),
+        ("cube_half", C.c_double), ("cube_mass", C.c_double), ("cube_inertia", C.c_double),
+        ("cube_friction", C.c_double), ("cube_threshold", C.c_double), ("cube_pos0", C.c_double * 3),
     ]
 
 
@@ -95,6 +98,8 @@ def lib():
         L.orc_get_contacts.restype = C.c_int
         L.orc_set_joint.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         L.orc_get_joint.argtypes = [C.c_void_p, C.c_int, _pd, _pd]
+        L.orc_set_cube.argtypes = [C.c_void_p, _pd, _pd, _pd, _pd]
+        L.orc_get_cube.argtypes = [C.c_void_p, _pd, _pd, _pd, _pd]
         L.orc_get_rows.argtypes = [C.c_void_p, _pd]
         L.orc_get_rows.restype = C.c_int
         L.orc_get_debug.argtypes = [C.c_void_p, _pd]
@@ -190,6 +195,14 @@ class OracleModel:
         m.max_episode_steps = spec.max_episode_steps
         m.stadium_halflen, m.stadium_halfwidth = sc.stadium_halflen, sc.stadium_halfwidth
         m.torsional = int(getattr(sc, 'torsional_friction', False))
+        cube = spec.cube
+        m.cube = 1 if cube is not None else 0
+        if cube is not None:
+            m.cube_half, m.cube_mass, m.cube_inertia = cube.half_extent, cube.mass, cube.inertia
+            m.cube_friction = cube.friction
+            m.cube_threshold = (cube.contact_threshold if bm.rules.relative_breaking_threshold else cube.breaking_threshold)
+            for i in range(3):
+                m.cube_pos0[i] = cube.pos0[i]
         for k, v in overrides.items():
             setattr(m, k, v)
         self.c = m
@@ -268,6 +281,15 @@ class OracleEnv:
         q, qd = C.c_double(0), C.c_double(0)
         lib().orc_get_joint(self._h, int(dof), C.byref(q), C.byref(qd))
         return q.value, qd.value
+
+    def set_cube(self, pos=None, quat=None, omega=None, vel=None):
+        arrs = [None if a is None else _d(a) for a in (pos, quat, omega, vel)]
+        lib().orc_set_cube(self._h, *[None if a is None else a.ctypes.data_as(_pd) for a in arrs])
+
+    def get_cube(self):
+        p, q, w, v = np.zeros(3), np.zeros(4), np.zeros(3), np.zeros(3)
+        lib().orc_get_cube(self._h, *[a.ctypes.data_as(_pd) for a in (p, q, w, v)])
+        return p, q, w, v
 
     def rows(self):
         out = np.zeros(2 + 3 * 256)

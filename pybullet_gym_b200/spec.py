@@ -49,6 +49,30 @@ class SceneSpec:
 
 
 @dataclass(frozen=True)
+class CubeSpec:
+    """HumanoidFlagrunHarder's `aggressive_cube` (robot_locomotors.py:236-243, gym_utils.py:9-16).
+
+    assets/things/cube_small.urdf: box 0.05 m, lateral friction 1.0; `changeDynamics(mass=1.2)`.
+    [EXT] changeDynamics(mass=...) recomputes the inertia from the collision box (m/12 (ly^2+lz^2)), which
+    discards the URDF's inertia_scaling; the contact breaking threshold follows the compiler's relative rule
+    (0.02 x angular-motion disc of the box)."""
+    half_extent: float = 0.025
+    mass: float = 1.2
+    friction: float = 1.0
+    pos0: Tuple[float, float, float] = (-1.5, 0.0, 0.05)
+    breaking_threshold: float = 0.02
+
+    @property
+    def inertia(self) -> float:
+        side = 2.0 * self.half_extent
+        return self.mass / 12.0 * 2.0 * side * side
+
+    @property
+    def contact_threshold(self) -> float:
+        return self.breaking_threshold * (3.0 ** 0.5) * self.half_extent
+
+
+@dataclass(frozen=True)
 class EnvSpec:
     id: str
     kind: int
@@ -68,6 +92,7 @@ class EnvSpec:
     reward_threshold: Optional[float] = None
     walk_target: Tuple[float, float] = (1e3, 0.0)
     entry_point: str = ""
+    cube: Optional[CubeSpec] = None
 
     def torque_scale(self, ordered_joint_names: List[str]) -> List[float]:
         """tau_max per ordered joint = power * power_coef (robot_locomotors.py:29,189)."""
@@ -117,6 +142,7 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
     EnvSpec("HumanoidFlagrunHarderPyBulletEnv-v0", KIND_FLAGRUN_HARDER, "humanoid_symmetric.xml", "torso", 17, 44,
             0.41, power_coef=_HUMANOID_POWER, foot_list=("right_foot", "left_foot"), initial_z=0.8,
             electricity_cost=4.25 * -2.0, stall_torque_cost=4.25 * -0.1,   # quirk Q6: the `/= 4` is dead
+            cube=CubeSpec(),
             entry_point=_RS + "gym_locomotion_envs:HumanoidFlagrunHarderBulletEnv"),
 ]}
 

@@ -29,10 +29,22 @@ def test_oracle_reproduces_reference_task_layer(path, oracle_lib):
             env.set_tape(ep["tape"])       # the reference's np_random draws for flag moves / cube attacks
         obs0 = env.reset(noise=ep["noise"], floor_in_parts=ei > 0)
         assert np.abs(obs0 - np.array(ep["obs0"])).max() < TOL
+        s_reset = env.get_state().copy()
         for t, st in enumerate(ep["steps"]):
+            if g.get("held"):
+                # scripted hold of tools/gen_golden_task.py: robot back to the reset pose, drifting in x; the cube is free
+                s_now = env.get_state()
+                nrob = s_now.size - 13
+                s_now[:nrob] = s_reset[:nrob]
+                s_now[0] += 0.01 * t
+                s_now[10] = 0.6
+                env.set_state(s_now)
             obs, rew, done, terms = env.step(st["a"])
             if "state" in st:
-                assert np.abs(env.get_state() - np.array(st["state"])).max() == 0.0, "physics replay diverged"
+                # bit for bit -- except once the cube has been thrown: numpy's pairwise mean in the reference's body_xyz
+                # differs from the oracle's running sum by ulps, and that seeds the cube's launch position
+                bar = 1e-7 if g.get("held") else 0.0
+                assert np.abs(env.get_state() - np.array(st["state"])).max() <= bar, "physics replay diverged"
             d_obs = np.abs(obs - np.array(st["obs"])).max()
             worst = max(worst, d_obs)
             assert d_obs < TOL, (ei, t, obs, st["obs"])

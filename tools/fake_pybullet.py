@@ -118,6 +118,10 @@ class FakeBulletClient:
     def loadURDF(self, path, basePosition=None, **kw):
         self.bodies.append({"kind": "misc", "base": b"baseLink", "name": os.path.basename(path).encode(),
                             "pos": list(basePosition or [0, 0, 0])})
+        # HumanoidFlagrunHarder's aggressive cube (gym_utils.py:9-16) is a simulated body of the oracle
+        if os.path.basename(path) == "cube_small.urdf" and FakeBulletClient.current_spec.cube is not None:
+            self.bodies[-1]["kind"] = "cube"
+            self.orc.set_cube(pos=list(basePosition), quat=[0, 0, 0, 1], omega=[0, 0, 0], vel=[0, 0, 0])
         return len(self.bodies) - 1
 
     # ---- structure queries
@@ -147,10 +151,14 @@ class FakeBulletClient:
         if self.bodies[body]["kind"] == "misc":
             self.bodies[body]["pos"] = list(pos)
             return
+        if self.bodies[body]["kind"] == "cube":
+            self.orc.set_cube(pos=list(pos), quat=list(orn))       # velocities are left as they are
+            return
         raise NotImplementedError
 
-    def resetBaseVelocity(self, *a, **k):
-        pass
+    def resetBaseVelocity(self, body, linearVelocity=(0, 0, 0), angularVelocity=(0, 0, 0)):
+        if self.bodies[body]["kind"] == "cube":
+            self.orc.set_cube(omega=list(angularVelocity), vel=list(linearVelocity))
 
     def stepSimulation(self):
         self._count("stepSimulation")
@@ -173,6 +181,9 @@ class FakeBulletClient:
             return (0.0, 0.0, 0.0), (0.0, 0.0, 0.0, 1.0)
         if b["kind"] == "misc":
             return tuple(b.get("pos", [0, 0, 0])), (0.0, 0.0, 0.0, 1.0)
+        if b["kind"] == "cube":
+            p, q, _, _ = self.orc.get_cube()
+            return tuple(p), tuple(q)
         s = self._link(0)
         return tuple(s[0:3]), tuple(s[3:7])
 

@@ -39,6 +39,10 @@ CASES = {
     "HumanoidPyBulletEnv-v0": ("gym_locomotion_envs", "HumanoidBulletEnv", 3, 40, 1.3),
     "HumanoidFlagrunPyBulletEnv-v0": ("gym_locomotion_envs", "HumanoidFlagrunBulletEnv", 4, 40, 1.3),
     "HumanoidFlagrunHarderPyBulletEnv-v0": ("gym_locomotion_envs", "HumanoidFlagrunHarderBulletEnv", 2, 200, 1.0),
+    # "#held": before every step the robot part of the physics state is put back to the reset pose with a
+    # small scripted drift, so that the humanoid is still standing at frame 120 / 150 / ... and the reference's
+    # cube attack (rs/robot_locomotors.py:251-266) fires; the cube itself keeps flying / colliding freely
+    "HumanoidFlagrunHarderPyBulletEnv-v0#held": ("gym_locomotion_envs", "HumanoidFlagrunHarderBulletEnv", 1, 230, 0.2),
 }
 
 
@@ -48,7 +52,9 @@ def main():
     sys.path.insert(0, REF)
     import importlib
     os.makedirs(OUT, exist_ok=True)
-    for env_id, (mod, cls, episodes, max_steps, ascale) in CASES.items():
+    for case_id, (mod, cls, episodes, max_steps, ascale) in CASES.items():
+        env_id, _, variant = case_id.partition("#")
+        held = variant == "held"
         spec = SPECS[env_id]
         fp.FakeBulletClient.current_spec = spec
         fp.FakeBulletClient.max_contacts = 0
@@ -70,12 +76,20 @@ def main():
             flat = [v for d in draws if d[0] == "uniform" for v in d[3]]
             noise, rec_tape = flat[:nA], None
             rec = {"noise": noise, "obs0": np.asarray(obs0, dtype=np.float64).tolist(), "steps": []}
+            s_reset = env._p.orc.get_state().copy()
             for t in range(max_steps):
                 a = (ascale * rng.uniform(-1, 1, nA)).astype(np.float64)   # |a| > 1 exercises quirk Q3
+                if held:
+                    s_now = env._p.orc.get_state()
+                    nrob = s_now.size - 13
+                    s_now[:nrob] = s_reset[:nrob]
+                    s_now[0] += 0.01 * t                  # base x drifts, base velocity 0.6 m/s: the attack leads its target
+                    s_now[10] = 0.6
+                    env._p.orc.set_state(s_now)
                 obs, rew, done, info = env._step(a)
                 st = {"a": a.tolist(), "obs": np.asarray(obs, dtype=np.float64).tolist(), "reward": float(rew),
                       "done": bool(done), "rewards": [float(r) for r in env.rewards]}
-                if t < 40:
+                if t < 40 or held:
                     st["state"] = env._p.orc.get_state().tolist()
                 if hasattr(env.robot, "feet_contact"):
                     st["feet_contact"] = [float(f) for f in env.robot.feet_contact]
@@ -91,12 +105,14 @@ def main():
         out = {"env_id": env_id, "reference_class": "pybulletgym.envs.roboschool.%s:%s" % (mod, cls),
                "parts": sorted(env.robot.parts.keys()), "ordered_joints": [j.joint_name for j in env.robot.ordered_joints],
                "episodes": eps}
-        path = os.path.join(OUT, "task_%s.json" % env_id.split("PyBullet")[0])
+        if held:
+            out["held"] = True
+        path = os.path.join(OUT, "task_%s%s.json" % (env_id.split("PyBullet")[0], "Held" if held else ""))
         with open(path, "w") as f:
             json.dump(out, f)
         nsteps = sum(len(e["steps"]) for e in eps)
         print("%-40s episodes=%d steps=%d parts=%d calls/step=%.1f -> %s" % (
-            env_id, episodes, nsteps, len(out["parts"]),
+            case_id, episodes, nsteps, len(out["parts"]),
             sum(v for k, v in calls.items()) / max(1, calls.get("stepSimulation", 1)), os.path.basename(path)))
 
 
