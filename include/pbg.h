@@ -94,6 +94,13 @@ typedef struct pbg_model {
     double electricity_cost, stall_torque_cost, joints_at_limit_cost;
     double walk_target_x, walk_target_y;
     double stadium_halflen, stadium_halfwidth;
+    /* HumanoidFlagrunHarder's aggressive cube (rs/robot_locomotors.py:236-266, gym_utils.py:9-16,
+     * assets/things/cube_small.urdf): a free box thrown at the robot every 30 frames.  cube = 0: none.
+     * Replaces loadURDF(cube_small.urdf) + changeDynamics(mass=1.2) + resetBasePositionAndOrientation /
+     * resetBaseVelocity on the cube body. */
+    int32_t cube;
+    double cube_half, cube_mass, cube_inertia, cube_friction, cube_threshold;
+    double cube_pos0[3];
 } pbg_model;
 
 typedef struct pbg_handle pbg_handle;
@@ -122,7 +129,8 @@ const char *pbg_last_error(const pbg_handle *h);   /* h may be NULL: error of th
 int pbg_num_envs(const pbg_handle *h);
 int pbg_obs_dim(const pbg_handle *h);
 int pbg_action_dim(const pbg_handle *h);
-int pbg_state_dim(const pbg_handle *h);     /* canonical state: [pos3 quat4(xyzw) omega3 vel3] (floating) + q[nj] + qd[nj] */
+int pbg_state_dim(const pbg_handle *h);     /* canonical state: [pos3 quat4(xyzw) omega3 vel3] (floating) + q[nj] + qd[nj]
+                                               + [cube pos3 quat4 omega3 vel3] (worlds with the cube) */
 
 /* Episode reset (rs/gym_locomotion_envs.py:22-39, rs/robot_locomotors.py:16-24): restores the
  * MJCF pose, draws U(-0.1,0.1) joint noise from the counter RNG, returns the first observation.

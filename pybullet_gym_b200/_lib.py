@@ -62,6 +62,9 @@ class PbgModel(C.Structure):
         ("electricity_cost", C.c_double), ("stall_torque_cost", C.c_double), ("joints_at_limit_cost", C.c_double),
         ("walk_target_x", C.c_double), ("walk_target_y", C.c_double),
         ("stadium_halflen", C.c_double), ("stadium_halfwidth", C.c_double),
+        ("cube", C.c_int32),
+        ("cube_half", C.c_double), ("cube_mass", C.c_double), ("cube_inertia", C.c_double),
+        ("cube_friction", C.c_double), ("cube_threshold", C.c_double), ("cube_pos0", C.c_double * 3),
     ]
 
 
@@ -189,6 +192,13 @@ class ModelTables:
         m.joints_at_limit_cost = spec.joints_at_limit_cost
         m.walk_target_x, m.walk_target_y = spec.walk_target
         m.stadium_halflen, m.stadium_halfwidth = sc.stadium_halflen, sc.stadium_halfwidth
+        cube = spec.cube
+        m.cube = 1 if cube is not None else 0
+        if cube is not None:
+            m.cube_half, m.cube_mass, m.cube_inertia, m.cube_friction = cube.half_extent, cube.mass, cube.inertia, cube.friction
+            m.cube_threshold = cube.contact_threshold if bm.rules.relative_breaking_threshold else cube.breaking_threshold
+            for i in range(3):
+                m.cube_pos0[i] = cube.pos0[i]
         self.c = m
 
 

@@ -19,9 +19,11 @@ using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1>;
 using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1>;
 using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28, 14, 1>;
 using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1>;
+// HumanoidFlagrunHarder: the humanoid + the cube (one more free body, 8 corner candidates, 17 geom-vs-cube pairs)
+using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17>;
 
 struct KernelInfo {
-    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads;
+    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet;
     size_t smem;
     void (*launch)(const DevModel *, const StepBuffers &, const LaunchArgs &, cudaStream_t);
     cudaError_t (*prepare)();
@@ -39,7 +41,7 @@ static cudaError_t prepare_cfg() {
 template <class C>
 static KernelInfo info_of() {
     return KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
 }
 
 static bool kernel_for_kind(int kind, KernelInfo *out) {
@@ -49,7 +51,8 @@ static bool kernel_for_kind(int kind, KernelInfo *out) {
     case PBG_KIND_WALKER2D: *out = info_of<CfgWalker>(); return true;
     case PBG_KIND_HALFCHEETAH: *out = info_of<CfgCheetah>(); return true;
     case PBG_KIND_ANT: *out = info_of<CfgAnt>(); return true;
-    case PBG_KIND_HUMANOID: case PBG_KIND_FLAGRUN: case PBG_KIND_FLAGRUN_HARDER: *out = info_of<CfgHumanoid>(); return true;
+    case PBG_KIND_HUMANOID: case PBG_KIND_FLAGRUN: *out = info_of<CfgHumanoid>(); return true;
+    case PBG_KIND_FLAGRUN_HARDER: *out = info_of<CfgHarder>(); return true;
     default: return false;
     }
 }
@@ -99,11 +102,12 @@ static void quat_to_mat(const double *q, float *R) {
 static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, DevModel *d) {
     char buf[256];
     memset(d, 0, sizeof(DevModel));
-    if (pm->nb != k.nb || pm->nj != k.nj || pm->floating != k.floating) {
+    if (pm->nb != k.nb - k.hasx || pm->nj != k.nj || pm->floating != k.floating) {
         snprintf(buf, sizeof buf, "model has nb=%d nj=%d floating=%d, kernel for kind %d expects %d/%d/%d", pm->nb, pm->nj,
-                 pm->floating, pm->kind, k.nb, k.nj, k.floating);
+                 pm->floating, pm->kind, k.nb - k.hasx, k.nj, k.floating);
         return buf;
     }
+    if ((pm->cube != 0) != (k.hasx != 0)) return "the kernel of this env kind and the model disagree about the cube";
     if (pm->action_dim != k.nact || pm->obs_dim != k.obs || pm->nfeet != k.nfeet) return "action/obs/feet dims do not match the kernel";
     if (pm->ns > MSUB) return "too many Bullet links";
     if (pm->max_contacts != k.maxc) {
@@ -111,7 +115,7 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
         return buf;
     }
     const int F = pm->floating ? 6 : 0;
-    d->nb = pm->nb; d->nj = pm->nj; d->nd = pm->nj + F; d->floating = pm->floating;
+    d->nb = pm->nb + k.hasx; d->nj = pm->nj; d->nd = pm->nj + F + 6 * k.hasx; d->floating = pm->floating;
     d->nact = pm->action_dim; d->nfeet = pm->nfeet; d->obs_dim = pm->obs_dim; d->kind = pm->kind;
     int jidx = 0, nlim = 0;
     for (int b = 0; b < pm->nb; ++b) {
@@ -161,9 +165,20 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
         }
         d->anc[b] = mask;
     }
-    for (int kk = 0; kk < d->nd; ++kk) {
+    const int XD0 = pm->nj + F, XB = pm->nb;       // first cube dof / the cube's body index
+    for (int kk = 0; kk < XD0; ++kk) {
         const int body = (pm->floating && kk < 6) ? 0 : d->jbody[kk - F];
         d->up[kk] = d->anc[body];
+    }
+    if (k.hasx) {
+        // the cube: a second root.  Inertia of the collision box (isotropic), identity rest frame.
+        d->parent[XB] = -1; d->jtype[XB] = 4; d->depth[XB] = 0; d->dof[XB] = XD0;
+        d->q0m[XB][0] = d->q0m[XB][4] = d->q0m[XB][8] = 1.f;
+        d->mass[XB] = (float)pm->cube_mass;
+        d->inertia[XB][0] = d->inertia[XB][1] = d->inertia[XB][2] = (float)pm->cube_inertia;
+        d->anc[XB] = 0x3fu << XD0;
+        for (int c = 0; c < 6; ++c) d->up[XD0 + c] = d->anc[XB];
+        for (int i = 0; i < 3; ++i) d->cube_pos0[i] = (float)pm->cube_pos0[i];
     }
     for (int kk = 0; kk < d->nd; ++kk) {
         unsigned dn = 0;
@@ -171,7 +186,7 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
         d->down[kk] = dn;
     }
     // Bullet links: parts membership and damping entries grouped by body
-    std::vector<std::vector<int>> by_body(pm->nb);
+    std::vector<std::vector<int>> by_body(d->nb);
     for (int s = 0; s < pm->ns; ++s) {
         const int b = pm->sub_body[s];
         if (b < 0 || b >= pm->nb) return "sub_body out of range";
@@ -190,7 +205,14 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
             ++nds;
         }
     }
-    for (int b = pm->nb; b <= MB; ++b) d->ds_begin[b] = nds;
+    if (k.hasx) {
+        if (nds >= MSUB) return "too many damping entries";
+        d->ds_begin[XB] = nds;
+        d->ds_mass[nds] = (float)pm->cube_mass;
+        for (int i = 0; i < 3; ++i) d->ds_inertia[nds][i] = (float)pm->cube_inertia;
+        ++nds;
+    }
+    for (int b = d->nb; b <= MB; ++b) d->ds_begin[b] = nds;
     if (pm->torso_sub < 0 || pm->torso_sub >= pm->ns) return "torso_sub out of range";
     d->torso_body = pm->sub_body[pm->torso_sub];
     for (int i = 0; i < 3; ++i) d->torso_off[i] = (float)pm->sub_off[3 * pm->torso_sub + i];
@@ -220,9 +242,33 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
             ++nc;
         }
     }
+    if (k.hasx) {
+        // cube corners against the floor, slots right after the robot's candidates (oracle.c collide)
+        for (int c = 0; c < 8; ++c) {
+            if (nc >= MCAND || nc >= k.ncand) return "too many ground contact candidates for the kernel";
+            d->c_body[nc] = XB; d->c_foot[nc] = -1;
+            for (int i = 0; i < 3; ++i) d->c_p[nc][i] = (float)(((c >> i) & 1) ? pm->cube_half : -pm->cube_half);
+            d->c_rad[nc] = 0.f;
+            d->c_thr[nc] = (float)pm->cube_threshold;
+            d->c_mu[nc] = (float)(pm->cube_friction * pm->ground_friction);
+            ++nc;
+        }
+    }
     d->ncand = nc;
-    if (pm->npair > k.npair || pm->npair > MPAIR) return "too many self-collision pairs for the kernel";
-    d->npair = pm->npair;
+    const int nxp = k.hasx ? pm->ng : 0;
+    if (pm->npair + nxp > k.npair || pm->npair + nxp > MPAIR) return "too many geom pairs for the kernel";
+    d->npair = pm->npair + nxp;
+    for (int g = 0; g < nxp; ++g) {
+        const int p = pm->npair + g;
+        d->p_ba[p] = pm->geom_body[g]; d->p_bb[p] = XB; d->p_box[p] = 1;
+        for (int i = 0; i < 3; ++i) {
+            d->p_a0[p][i] = (float)pm->geom_p0[3 * g + i]; d->p_a1[p][i] = (float)pm->geom_p1[3 * g + i];
+            d->p_b0[p][i] = (float)pm->cube_half;
+        }
+        d->p_ra[p] = (float)pm->geom_radius[g]; d->p_rb[p] = 0.f;
+        d->p_thr[p] = (float)std::fmin(pm->geom_threshold[g], pm->cube_threshold);
+        d->p_mu[p] = (float)(pm->geom_friction[g] * pm->cube_friction);
+    }
     for (int p = 0; p < pm->npair; ++p) {
         const int a = pm->pair_a[p], b = pm->pair_b[p];
         d->p_ba[p] = pm->geom_body[a]; d->p_bb[p] = pm->geom_body[b];
@@ -419,8 +465,7 @@ int pbg_get_feet_contact(pbg_handle *h, float *out_dev, void *stream) {
     if (h->k.nfeet == 0) return PBG_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
     // feet flags are the last NFEET floats before the padded end of the state row
-    const int F = h->k.floating ? 1 : 0;
-    const int off = 7 * F + h->k.nj + (h->k.nj + 6 * F) + (h->k.ncand + h->k.npair) + TASK_FLOATS;
+    const int off = h->k.off_feet;
     const int n = h->E * h->k.nfeet;
     gather_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, h->k.sstride, off, h->k.nfeet, out_dev, h->E);
     CUDA_TRY(h, cudaGetLastError());

@@ -21,11 +21,16 @@
 
 namespace pbg {
 
+// XP_ > 0: the world also holds HumanoidFlagrunHarder's cube (rs/robot_locomotors.py:236-266), a second free
+// body that is the last body / the last six dofs / the last eight ground candidates / the last XP_ pairs.
 template <int NB_, int NJ_, int FLOATING_, int NLIM_, int MAXC_, int LPE_, int NCAND_, int NPAIR_, int NFEET_,
-          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_>
+          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0>
 struct KCfg {
-    static constexpr int NB = NB_, NJ = NJ_, FLOATING = FLOATING_, ND = NJ_ + 6 * FLOATING_, NLIM = NLIM_;
-    static constexpr int MAXC = MAXC_, LPE = LPE_, NCAND = NCAND_, NPAIR = NPAIR_, NSLOT = NCAND_ + NPAIR_;
+    static constexpr int HASX = XP_ > 0 ? 1 : 0;
+    static constexpr int NB = NB_ + HASX, NJ = NJ_, FLOATING = FLOATING_, NLIM = NLIM_;
+    static constexpr int XD0 = NJ_ + 6 * FLOATING_;            // first cube dof
+    static constexpr int ND = XD0 + 6 * HASX;
+    static constexpr int MAXC = MAXC_, LPE = LPE_, NCAND = NCAND_ + 8 * HASX, NPAIR = NPAIR_ + XP_, NSLOT = NCAND + NPAIR;
     static constexpr int NFEET = NFEET_, NACT = NACT_, OBS = OBS_;
     static constexpr int MAXR = NLIM + 3 * MAXC;
     static constexpr int MAXRP = MAXR > 0 ? MAXR : 1;
@@ -40,10 +45,10 @@ struct KCfg {
     static_assert(MAXR <= 2 * LPE, "at most two row slots per lane");
     static_assert(ND + 1 <= LPE && NB <= LPE && NCAND <= 2 * LPE && NLIM <= LPE, "lane budget");
     // per-env state (floats)
-    static constexpr int oQ = 7 * FLOATING, oU = oQ + NJ, oW = oU + ND, oT = oW + NSLOT, oF = oT + TASK_FLOATS;
+    static constexpr int oQ = 7 * FLOATING, oX = oQ + NJ, oU = oX + 7 * HASX, oW = oU + ND, oT = oW + NSLOT, oF = oT + TASK_FLOATS;
     static constexpr int oP = oF + NFEET;          // feet flags of the last physics step, not yet seen by calc_state
     static constexpr int SSIZE = oP + NFEET, SSTRIDE = (SSIZE + 3) / 4 * 4;
-    static constexpr int CANON = 13 * FLOATING + 2 * NJ;
+    static constexpr int CANON = 13 * FLOATING + 2 * NJ + 13 * HASX;   // [base 13][q][qd][cube pos3 quat4 omega3 vel3]
     // shared memory per env (floats).  Regions with disjoint lifetimes share storage:
     //   {KIN, ACC, SH, F, COL} (kinematics .. Cholesky, dead once the rows are built)  |  {A} (Delassus matrix)
     //   {Y} (constraint rows, substeps only)                                          |  {OUT} (staged outputs)
@@ -210,9 +215,11 @@ struct Env {
                     xp = wp = vp = alp = ap = mk(0, 0, 0);
                 }
                 V3 zw = mk(0, 0, 0), A = mk(0, 0, 0);
-                if (bjtype == 3) {   // floating root
-                    quat2mat(S + 3, R);
-                    x = ld3(S); w = ld3(S + C::oU); v = ld3(S + C::oU + 3);
+                if (bjtype == 3 || (C::HASX && bjtype == 4)) {   // floating root / the cube
+                    const float *P = (C::HASX && bjtype == 4) ? S + C::oX : S;
+                    const float *U = S + C::oU + ((C::HASX && bjtype == 4) ? C::XD0 : 0);
+                    quat2mat(P + 3, R);
+                    x = ld3(P); w = ld3(U); v = ld3(U + 3);
                     al = a = mk(0, 0, 0);
                 } else {
                     float Rq[9];
@@ -301,6 +308,30 @@ struct Env {
                 const int pi = s - C::NCAND;
                 const float *ka = kin(m->p_ba[pi]), *kb = kin(m->p_bb[pi]);
                 const V3 p1 = ld3(ka + 9) + mulR(ka, ld3(m->p_a0[pi])), q1 = ld3(ka + 9) + mulR(ka, ld3(m->p_a1[pi]));
+                if (C::HASX && m->p_box[pi]) {
+                    // capsule / sphere against the cube: closest points of the segment and the box, in the box
+                    // frame.  d/dt of the squared distance is monotone in t: 32 bisection steps (oracle.c closest_seg_box)
+                    const V3 xb = ld3(kb + 9);
+                    const V3 a0 = mulRt(kb, p1 - xb), dd = mulRt(kb, q1 - xb) - a0;
+                    const float hh = m->p_b0[pi][0];
+                    float lo_t = 0.f, hi_t = 1.f;
+                    for (int it = 0; it < 32; ++it) {
+                        const float t = 0.5f * (lo_t + hi_t);
+                        const V3 xx = a0 + t * dd;
+                        const V3 cc = mk(fminf(fmaxf(xx.x, -hh), hh), fminf(fmaxf(xx.y, -hh), hh), fminf(fmaxf(xx.z, -hh), hh));
+                        const float gsl = dot(xx - cc, dd);
+                        if (gsl < 0.f) lo_t = t; else hi_t = t;
+                    }
+                    const float t = 0.5f * (lo_t + hi_t);
+                    const V3 xx = a0 + t * dd;
+                    const V3 cc = mk(fminf(fmaxf(xx.x, -hh), hh), fminf(fmaxf(xx.y, -hh), hh), fminf(fmaxf(xx.z, -hh), hh));
+                    const V3 d = mulR(kb, xx - cc);
+                    const float len = sqrtf(dot(d, d)), ra = m->p_ra[pi];
+                    dist[p] = len - ra;
+                    act[p] = dist[p] < m->p_thr[pi] && len > 1e-9f;
+                    const V3 n = (1.f / fmaxf(len, 1e-20f)) * d;
+                    nn[p] = n; pa[p] = xb + mulR(kb, xx) - ra * n; pb[p] = xb + mulR(kb, cc);
+                } else {
                 const V3 p2 = ld3(kb + 9) + mulR(kb, ld3(m->p_b0[pi])), q2 = ld3(kb + 9) + mulR(kb, ld3(m->p_b1[pi]));
                 const V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
                 const float aa = dot(d1, d1), ee = dot(d2, d2), f = dot(d2, r);
@@ -325,6 +356,7 @@ struct Env {
                 act[p] = dist[p] < m->p_thr[pi] && len > 1e-9f;
                 const V3 n = (1.f / fmaxf(len, 1e-20f)) * d;
                 nn[p] = n; pa[p] = ca - ra * n; pb[p] = cb + rb * n;
+                }
             }
             if (s < C::NSLOT) cd[s] = act[p] ? dist[p] : CUDART_INF_F;
             total += __popc(gballot(act[p]));
@@ -439,7 +471,9 @@ struct Env {
                 F = F - Fd;
                 N = N - Nd - cross(ro, Fd);
             }
-            const V3 r = x - xref;
+            // the cube's dofs are referenced to its own centre (it may be far from the robot: a common reference
+            // point would bury its 5e-4 kg m^2 inertia under m r^2 in fp32)
+            const V3 r = (C::HASX && gl == C::NB - 1) ? mk(0.f, 0.f, 0.f) : x - xref;
             float *ab = acc + gl * 17;
             const float rr = dot(r, r);
             ab[0] = bmass;
@@ -473,6 +507,10 @@ struct Env {
                 const V3 e = mk(gl % 3 == 0, gl % 3 == 1, gl % 3 == 2);
                 if (gl < 3) { Sk[0] = e.x; Sk[1] = e.y; Sk[2] = e.z; const V3 sv = cross(r0, e); Sk[3] = sv.x; Sk[4] = sv.y; Sk[5] = sv.z; }
                 else { Sk[3] = e.x; Sk[4] = e.y; Sk[5] = e.z; }
+            } else if (C::HASX && gl >= C::XD0) {
+                body = C::NB - 1;
+                const int c = gl - C::XD0;
+                Sk[c] = 1.f;                         // (omega, v) of the cube about its own centre
             } else {
                 const int j = gl - 6 * C::FLOATING;
                 body = m->jbody[j];
@@ -622,12 +660,15 @@ struct Env {
                 mu[sl] = ct[14];
                 const V3 pA = ld3(ct + 4), pB = ld3(ct + 7);
                 const unsigned ma = m->anc[ba], mb = bb >= 0 ? m->anc[bb] : 0u;
+                V3 pAx = pA, pBx = pB;               // the same points seen from the cube's centre
+                if (C::HASX) { const V3 rc = ld3(kin(C::NB - 1) + 9) - xref; pAx = pA - rc; pBx = pB - rc; }
 #pragma unroll
                 for (int k = 0; k < C::ND; ++k) {
                     const V3 so = ld3(SH + k * 12), sv = ld3(SH + k * 12 + 3);
+                    const bool xk = C::HASX && k >= C::XD0;
                     float val = 0.f;
-                    if ((ma >> k) & 1u) val += dot(d, sv + cross(so, pA));
-                    if (C::NPAIR > 0) { if ((mb >> k) & 1u) val -= dot(d, sv + cross(so, pB)); }
+                    if ((ma >> k) & 1u) val += dot(d, sv + cross(so, xk ? pAx : pA));
+                    if (C::NPAIR > 0) { if ((mb >> k) & 1u) val -= dot(d, sv + cross(so, xk ? pBx : pB)); }
                     J[k] = val;
                 }
             }
@@ -812,23 +853,26 @@ struct Env {
         __syncwarp();
         // --- semi-implicit Euler (btMultiBody::stepPositionsMultiDof)
         if (gl < C::NJ) S[C::oQ + gl] += h * u[6 * C::FLOATING + gl];
-        if (C::FLOATING && gl == C::LPE - 1) {
-            const V3 om = ld3(u);
+        if ((C::FLOATING && gl == C::LPE - 1) || (C::HASX && gl == C::LPE - 2)) {
+            const bool cube = C::HASX && gl == C::LPE - 2;
+            float *Q = cube ? S + C::oX + 3 : S + 3;
+            const V3 om = ld3(cube ? u + C::XD0 : u);
             float wn = sqrtf(dot(om, om));
             if (wn * h > 0.25f * CUDART_PI_F) wn = 0.5f * (0.5f * CUDART_PI_F) / h;
             float sc;
             if (wn < 0.001f) sc = 0.5f * h - h * h * h * 0.020833333333f * wn * wn;
             else sc = sinf(0.5f * wn * h) / wn;
             const float ax = om.x * sc, ay = om.y * sc, az = om.z * sc, aw = cosf(0.5f * wn * h);
-            const float bx = S[3], by = S[4], bz = S[5], bw = S[6];
+            const float bx = Q[0], by = Q[1], bz = Q[2], bw = Q[3];
             float qx = aw * bx + ax * bw + ay * bz - az * by;
             float qy = aw * by - ax * bz + ay * bw + az * bx;
             float qz = aw * bz + ax * by - ay * bx + az * bw;
             float qw = aw * bw - ax * bx - ay * by - az * bz;
             const float nn = rsqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
-            S[3] = qx * nn; S[4] = qy * nn; S[5] = qz * nn; S[6] = qw * nn;
+            Q[0] = qx * nn; Q[1] = qy * nn; Q[2] = qz * nn; Q[3] = qw * nn;
         }
         if (C::FLOATING && gl < 3) S[gl] += h * u[3 + gl];
+        if (C::HASX && gl >= 3 && gl < 6) S[C::oX + gl - 3] += h * u[C::XD0 + gl];
         __syncwarp();
     }
 
@@ -951,7 +995,29 @@ struct Env {
             h_frame = __float_as_int(T[T_FRAME]); h_og = __float_as_int(T[T_ONGROUND]); h_att = __float_as_int(T[T_ATTACKS]);
             if (!reset_pass) {
                 // alive_bonus (rs/robot_locomotors.py:250-273); it runs before the step's calc_potential
-                if (h_frame % 30 == 0 && h_frame > 100 && h_og == 0) h_att += 1;   // cube attack (cube not simulated: DESIGN.md)
+                if (h_frame % 30 == 0 && h_frame > 100 && h_og == 0) {
+                    // cube attack (rs/robot_locomotors.py:251-266): thrown from 4 m away, 1 m up, at where the robot
+                    // will be when it arrives; the cube keeps its orientation, its spin is zeroed
+                    if (C::HASX && gl == 0 && pred) {
+                        const unsigned ep = (unsigned)__float_as_int(T[T_EPISODE]);
+                        const float angle = rng_uniform(rng_seed, rng_env, ep, 2u, 5u * h_att, -3.14f, 3.14f);
+                        const float speed = rng_uniform(rng_seed, rng_env, ep, 2u, 5u * h_att + 1u, 20.f, 30.f);
+                        const float ttt = 4.0f / speed;
+                        const V3 tgt = mk(bx + tsp.x * ttt, by + tsp.y * ttt, z + tsp.z * ttt);
+                        float sa_, ca_;
+                        sincosf(angle, &sa_, &ca_);
+                        const V3 pos = mk(tgt.x + 4.0f * ca_, tgt.y + 4.0f * sa_, tgt.z + 1.0f);
+                        const V3 dv = tgt - pos;
+                        const float sc = speed * rsqrtf(dot(dv, dv));
+                        float *X = S + C::oX, *XU = S + C::oU + C::XD0;
+                        X[0] = pos.x; X[1] = pos.y; X[2] = pos.z;
+                        XU[0] = 0.f; XU[1] = 0.f; XU[2] = 0.f;
+                        XU[3] = dv.x * sc + rng_uniform(rng_seed, rng_env, ep, 2u, 5u * h_att + 2u, -1.f, 1.f);
+                        XU[4] = dv.y * sc + rng_uniform(rng_seed, rng_env, ep, 2u, 5u * h_att + 3u, -1.f, 1.f);
+                        XU[5] = dv.z * sc + rng_uniform(rng_seed, rng_env, ep, 2u, 5u * h_att + 4u, -1.f, 1.f);
+                    }
+                    h_att += 1;
+                }
                 const float zz8 = clip5(z - initz) + initz;
                 if (zz8 < 0.8f) h_og += 1; else if (h_og > 0) h_og -= 1;
                 h_frame += 1;
@@ -1048,6 +1114,11 @@ struct Env {
                 if (gl < 3) S[gl] = m->base_pos0[gl];
                 if (gl < 4) S[3 + gl] = m->base_quat0[gl];
             }
+            if (C::HASX) {
+                // restoreState + resetBasePositionAndOrientation(cube, [-1.5, 0, 0.05], identity) (rs/robot_locomotors.py:240-243)
+                if (gl < 3) S[C::oX + gl] = m->cube_pos0[gl];
+                if (gl == 3) S[C::oX + 6] = 1.f;
+            }
             if (gl < C::NACT) {
                 const float nz = noise ? noise[gl] : rng_uniform(la.seed, env, ep, 0u, (unsigned)gl, -0.1f, 0.1f);
                 if (m->kind <= 1) { if (gl == 0) S[C::oQ + 1] = nz + (m->kind == 1 ? 3.1415f : 0.f); }
@@ -1117,6 +1188,11 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
                 cs[13 * C::FLOATING + j] = S[C::oQ + j];
                 cs[13 * C::FLOATING + C::NJ + j] = S[C::oU + 6 * C::FLOATING + j];
             }
+            if (C::HASX) {
+                float *cx = cs + 13 * C::FLOATING + 2 * C::NJ;
+                if (gl < 7) cx[gl] = S[C::oX + gl];
+                if (gl < 6) cx[7 + gl] = S[C::oU + C::XD0 + gl];
+            }
         }
         return;
     }
@@ -1129,6 +1205,11 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
         for (int j = gl; j < C::NJ; j += C::LPE) {
             S[C::oQ + j] = cs[13 * C::FLOATING + j];
             S[C::oU + 6 * C::FLOATING + j] = cs[13 * C::FLOATING + C::NJ + j];
+        }
+        if (C::HASX) {
+            const float *cx = cs + 13 * C::FLOATING + 2 * C::NJ;
+            if (gl < 7) S[C::oX + gl] = cx[gl];
+            if (gl < 6) S[C::oU + C::XD0 + gl] = cx[7 + gl];
         }
         for (int i = gl; i < C::NSLOT; i += C::LPE) S[C::oW + i] = 0.f;
         __syncwarp();
@@ -1147,7 +1228,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
         // apply_action: tau = power * power_coef * clip(a, -1, 1) (rs/robot_locomotors.py:26-29),
         // plus the joint damping torque, both held for all substeps
         float tq = 0.f;
-        if (gl >= 6 * C::FLOATING && gl < C::ND) {
+        if (gl >= 6 * C::FLOATING && gl < C::XD0) {
             const int j = gl - 6 * C::FLOATING;
             tq = -model->jdamp[j] * S[C::oU + gl];
             const int ai = model->jact[j];

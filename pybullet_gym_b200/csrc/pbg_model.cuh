@@ -12,8 +12,8 @@ namespace pbg {
 constexpr int MB = 20;      // max bodies of the reduced tree (humanoid: 18)
 constexpr int MJ = 24;      // max joint dofs
 constexpr int MSUB = 32;    // max Bullet links folded into the bodies (humanoid: 30)
-constexpr int MCAND = 32;   // max ground contact candidates (humanoid: 4 spheres + 13 capsules * 2)
-constexpr int MPAIR = 72;   // max self-collision geom pairs (humanoid: 66)
+constexpr int MCAND = 40;   // max ground contact candidates (humanoid: 4 spheres + 13 capsules * 2, + 8 cube corners)
+constexpr int MPAIR = 84;   // max geom pairs (humanoid: 66 self-collision pairs + 17 geoms against the cube)
 constexpr int MFEET = 8;
 constexpr int TASK_FLOATS = 24;
 
@@ -35,6 +35,8 @@ struct DevModel {
     int p_ba[MPAIR], p_bb[MPAIR];
     float p_a0[MPAIR][3], p_a1[MPAIR][3], p_b0[MPAIR][3], p_b1[MPAIR][3], p_ra[MPAIR], p_rb[MPAIR], p_thr[MPAIR],
         p_mu[MPAIR];
+    int p_box[MPAIR];                         // 1: body B is the cube, p_b0 = half extents
+    float cube_pos0[3];
     float torso_off[3];
     float base_pos0[3], base_quat0[4];
     // scene
