@@ -38,7 +38,7 @@ typedef enum {
 enum {
     PBG_KIND_PENDULUM = 0, PBG_KIND_PENDULUM_SWINGUP = 1, PBG_KIND_HOPPER = 2, PBG_KIND_WALKER2D = 3,
     PBG_KIND_HALFCHEETAH = 4, PBG_KIND_ANT = 5, PBG_KIND_HUMANOID = 6, PBG_KIND_FLAGRUN = 7,
-    PBG_KIND_FLAGRUN_HARDER = 8
+    PBG_KIND_FLAGRUN_HARDER = 8, PBG_KIND_DOUBLE_PENDULUM = 9
 };
 
 enum { PBG_JT_FIXED = 0, PBG_JT_REVOLUTE = 1, PBG_JT_PRISMATIC = 2, PBG_JT_FREE = 3 };
@@ -129,6 +129,7 @@ const char *pbg_last_error(const pbg_handle *h);   /* h may be NULL: error of th
 int pbg_num_envs(const pbg_handle *h);
 int pbg_obs_dim(const pbg_handle *h);
 int pbg_action_dim(const pbg_handle *h);
+int pbg_noise_dim(const pbg_handle *h);     /* reset draws per env that pbg_reset_with injects */
 int pbg_state_dim(const pbg_handle *h);     /* canonical state: [pos3 quat4(xyzw) omega3 vel3] (floating) + q[nj] + qd[nj]
                                                + [cube pos3 quat4 omega3 vel3] (worlds with the cube) */
 
@@ -137,7 +138,8 @@ int pbg_state_dim(const pbg_handle *h);     /* canonical state: [pos3 quat4(xyzw
  * mask_dev: uint8[num_envs] or NULL (= all).  floor_in_parts: reference quirk Q1 -- 0 reproduces the
  * very first reset of an env's life (floor not yet in robot.parts), 1 every later reset. */
 int pbg_reset(pbg_handle *h, const uint8_t *mask_dev, int32_t floor_in_parts, float *obs_dev, void *stream);
-/* Same, with the joint noise given by the caller (float[num_envs, action_dim]), for parity tests. */
+/* Same, with the reset draws given by the caller (float[num_envs, pbg_noise_dim]: one per actuated joint for
+ * the walkers, the hinge for the pendulum, hinge + hinge2 for the double pendulum), for parity tests. */
 int pbg_reset_with(pbg_handle *h, const float *joint_noise_dev, int32_t floor_in_parts, float *obs_dev, void *stream);
 
 /* One env step for every env: apply_action + stepSimulation + calc_state + reward/termination

@@ -914,7 +914,7 @@ static void mat_to_quat(m3 m, double q[4]) {
     }
 }
 
-static int is_walker(int kind) { return kind >= ORC_KIND_HOPPER; }
+static int is_walker(int kind) { return kind >= ORC_KIND_HOPPER && kind <= ORC_KIND_FLAGRUN_HARDER; }
 static double potential_leak(const orc_env *e);
 
 static double alive_bonus(orc_env *e, double z, double pitch) {
@@ -1029,6 +1029,16 @@ static void walker_calc_state(orc_env *e, double *obs) {
 static void pendulum_calc_state(orc_env *e, double *obs) {
     /* rs/robot_pendula.py:27-51: slider = dof 0, hinge = dof 1 */
     double x = e->q[0], vx = e->qd[0], th = e->q[1], thd = e->qd[1];
+    if (e->m.kind == ORC_KIND_DOUBLE_PENDULUM) {
+        /* InvertedDoublePendulum.calc_state (rs/robot_pendula.py:75-87): pole2 = last link, its COM is the
+         * middle of the second pole (rs/gym_pendulum_envs.py:73-74) */
+        fk(e);
+        double ga = e->q[2], gad = e->qd[2];
+        e->body_xyz[0] = e->c[e->m.nl - 1][0]; e->body_xyz[2] = e->c[e->m.nl - 1][2];
+        obs[0] = x; obs[1] = vx; obs[2] = e->body_xyz[0]; obs[3] = cos(th); obs[4] = sin(th); obs[5] = thd;
+        obs[6] = cos(ga); obs[7] = sin(ga); obs[8] = gad;
+        return;
+    }
     obs[0] = x; obs[1] = vx; obs[2] = cos(th); obs[3] = sin(th); obs[4] = thd;
 }
 
@@ -1053,9 +1063,17 @@ int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double
     if (!is_walker(m->kind)) {
         pendulum_calc_state(e, obs);
         double th = e->q[1];
+        if (m->kind == ORC_KIND_DOUBLE_PENDULUM) {
+            /* InvertedDoublePendulumBulletEnv._step (rs/gym_pendulum_envs.py:69-83) */
+            double px = e->body_xyz[0], py = e->body_xyz[2];
+            t5[0] = 10.0; t5[1] = -(0.01 * px * px + (py + 0.3 - 2) * (py + 0.3 - 2)); t5[2] = -0.0;
+            done = py + 0.3 <= 1;
+            *reward = t5[0] + t5[1] + t5[2];
+        } else {
         if (m->kind == ORC_KIND_PENDULUM_SWINGUP) { t5[0] = cos(th); done = 0; }
         else { t5[0] = 1.0; done = fabs(th) > 0.2; }
         *reward = t5[0];
+        }
     } else {
         walker_calc_state(e, obs);
         double zz;
@@ -1100,6 +1118,7 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
         for (int n = 0; n < m->nact; n++) e->q[e->dof_of_link[m->act_link[n]]] = noise[n];
     } else {
         e->q[1] = noise[0] + (m->kind == ORC_KIND_PENDULUM_SWINGUP ? 3.1415 : 0.0);
+        if (m->kind == ORC_KIND_DOUBLE_PENDULUM) e->q[2] = noise[1];       /* rs/robot_pendula.py:66-68 */
     }
     if (m->cube) {
         /* restoreState + resetBasePositionAndOrientation(cube, [-1.5,0,0.05], identity) (rs/robot_locomotors.py:240-243) */
@@ -1128,7 +1147,7 @@ void orc_reset_with(orc_env *e, const double *noise, int floor_in_parts, double 
 void orc_reset(orc_env *e, int floor_in_parts, double *obs) {
     double noise[MAXD];
     e->episode++;
-    int n = is_walker(e->m.kind) ? e->m.nact : 1;
+    int n = is_walker(e->m.kind) ? e->m.nact : (e->m.kind == ORC_KIND_DOUBLE_PENDULUM ? 2 : 1);
     for (int k = 0; k < n; k++) noise[k] = rng_uniform(e->seed, e->env_index, e->episode, (uint32_t)k, -0.1f, 0.1f);
     reset_common(e, noise, floor_in_parts, obs);
 }

@@ -30,7 +30,7 @@ enum { ORC_JT_FIXED = 0, ORC_JT_REVOLUTE = 1, ORC_JT_PRISMATIC = 2, ORC_JT_FREE 
 enum { ORC_G_SPHERE = 0, ORC_G_CAPSULE = 1, ORC_G_BOX = 2 };
 enum { ORC_KIND_PENDULUM = 0, ORC_KIND_PENDULUM_SWINGUP = 1, ORC_KIND_HOPPER = 2, ORC_KIND_WALKER2D = 3,
        ORC_KIND_HALFCHEETAH = 4, ORC_KIND_ANT = 5, ORC_KIND_HUMANOID = 6, ORC_KIND_FLAGRUN = 7,
-       ORC_KIND_FLAGRUN_HARDER = 8 };
+       ORC_KIND_FLAGRUN_HARDER = 8, ORC_KIND_DOUBLE_PENDULUM = 9 };
 
 /* Bullet-shaped model + scene + task constants.  All arrays are owned by the caller. */
 typedef struct {
@@ -84,7 +84,8 @@ orc_env *orc_create(const orc_model *m, uint64_t seed, uint64_t env_index);
 void orc_destroy(orc_env *e);
 /* reset: MJCF pose, every actuated joint <- U(-0.1,0.1) from the counter RNG; floor_in_parts: quirk Q1 */
 void orc_reset(orc_env *e, int floor_in_parts, double *obs);
-/* reset with injected joint noise (ordered-joint order); used to replay reference-style resets */
+/* reset with injected joint noise (ordered-joint order; double pendulum: hinge, hinge2); used to replay
+ * reference-style resets */
 void orc_reset_with(orc_env *e, const double *joint_noise, int floor_in_parts, double *obs);
 /* one env step: returns done; terms = [alive, progress, electricity, joints_at_limit, feet_collision] */
 int orc_step(orc_env *e, const double *action, double *obs, double *reward, double *terms);

@@ -111,7 +111,7 @@ def lib():
     L.pbg_destroy.argtypes = [vp]
     L.pbg_last_error.argtypes = [vp]
     L.pbg_last_error.restype = C.c_char_p
-    for f in ("pbg_num_envs", "pbg_obs_dim", "pbg_action_dim", "pbg_state_dim"):
+    for f in ("pbg_num_envs", "pbg_obs_dim", "pbg_action_dim", "pbg_state_dim", "pbg_noise_dim"):
         getattr(L, f).argtypes = [vp]
     L.pbg_reset.argtypes = [vp, vp, C.c_int32, vp, vp]
     L.pbg_reset_with.argtypes = [vp, vp, C.c_int32, vp, vp]
@@ -133,7 +133,7 @@ def lib():
 
 
 EXPORTS = ["pbg_version", "pbg_create", "pbg_destroy", "pbg_last_error", "pbg_num_envs", "pbg_obs_dim",
-           "pbg_action_dim", "pbg_state_dim", "pbg_reset", "pbg_reset_with", "pbg_step", "pbg_step_host",
+           "pbg_action_dim", "pbg_state_dim", "pbg_noise_dim", "pbg_reset", "pbg_reset_with", "pbg_step", "pbg_step_host",
            "pbg_set_auto_reset", "pbg_get_state", "pbg_set_state", "pbg_physics_step", "pbg_physics_step_counts",
            "pbg_max_contacts", "pbg_measure_fp32_peak", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count"]
 

@@ -14,6 +14,7 @@ using namespace pbg;
 // kernel configurations: NB, NJ, FLOATING, NLIM, MAXC, LPE, NCAND, NPAIR, NFEET, NACT, OBS, WARPS per CTA, CTAs per SM
 // 14 warps x 2 envs = 28 envs per CTA = one CTA per SM (7.2 KB shared memory per env): 148 CTAs hold 4144 envs.
 using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5, 4, 4>;
+using CfgDoublePendulum = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 9, 4, 4, 0, 2>;
 using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15, 14, 1>;
 using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1>;
 using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1>;
@@ -23,7 +24,7 @@ using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1>;
 using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17>;
 
 struct KernelInfo {
-    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet;
+    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet, nnoise;
     size_t smem;
     void (*launch)(const DevModel *, const StepBuffers &, const LaunchArgs &, cudaStream_t);
     cudaError_t (*prepare)();
@@ -41,12 +42,13 @@ static cudaError_t prepare_cfg() {
 template <class C>
 static KernelInfo info_of() {
     return KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
 }
 
 static bool kernel_for_kind(int kind, KernelInfo *out) {
     switch (kind) {
     case PBG_KIND_PENDULUM: case PBG_KIND_PENDULUM_SWINGUP: *out = info_of<CfgPendulum>(); return true;
+    case PBG_KIND_DOUBLE_PENDULUM: *out = info_of<CfgDoublePendulum>(); return true;
     case PBG_KIND_HOPPER: *out = info_of<CfgHopper>(); return true;
     case PBG_KIND_WALKER2D: *out = info_of<CfgWalker>(); return true;
     case PBG_KIND_HALFCHEETAH: *out = info_of<CfgCheetah>(); return true;
@@ -365,6 +367,7 @@ int pbg_num_envs(const pbg_handle *h) { return h ? h->E : PBG_ERR_INVALID; }
 int pbg_obs_dim(const pbg_handle *h) { return h ? h->k.obs : PBG_ERR_INVALID; }
 int pbg_action_dim(const pbg_handle *h) { return h ? h->k.nact : PBG_ERR_INVALID; }
 int pbg_state_dim(const pbg_handle *h) { return h ? h->k.canon : PBG_ERR_INVALID; }
+int pbg_noise_dim(const pbg_handle *h) { return h ? h->k.nnoise : PBG_ERR_INVALID; }
 int64_t pbg_launch_count(const pbg_handle *h) { return h ? h->launches : 0; }
 
 static int launch(pbg_handle *h, int mode, StepBuffers &b, int floor_in_parts, void *stream) {

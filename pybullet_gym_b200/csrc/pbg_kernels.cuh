@@ -24,8 +24,9 @@ namespace pbg {
 // XP_ > 0: the world also holds HumanoidFlagrunHarder's cube (rs/robot_locomotors.py:236-266), a second free
 // body that is the last body / the last six dofs / the last eight ground candidates / the last XP_ pairs.
 template <int NB_, int NJ_, int FLOATING_, int NLIM_, int MAXC_, int LPE_, int NCAND_, int NPAIR_, int NFEET_,
-          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0>
+          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_>
 struct KCfg {
+    static constexpr int NNOISE = NNOISE_;                     // injectable reset draws per env (pbg_reset_with)
     static constexpr int HASX = XP_ > 0 ? 1 : 0;
     static constexpr int NB = NB_ + HASX, NJ = NJ_, FLOATING = FLOATING_, NLIM = NLIM_;
     static constexpr int XD0 = NJ_ + 6 * FLOATING_;            // first cube dof
@@ -1077,6 +1078,28 @@ struct Env {
         const float xx = S[C::oQ], th = S[C::oQ + 1], vx = S[C::oU], thd = S[C::oU + 1];
         float s, c;
         sincosf(th, &s, &c);
+        if (m->kind == 9) {
+            // InvertedDoublePendulum (rs/robot_pendula.py:57-87, rs/gym_pendulum_envs.py:50-83): pole2's link COM is
+            // the middle of the second pole; reward = 10 - 0.01 x^2 - (y + 0.3 - 2)^2, done when y + 0.3 <= 1
+            fk(false);
+            const float *k2 = kin(C::NB - 1);
+            const float px = k2[9], py = k2[11];
+            const float ga = S[C::oQ + 2], gad = S[C::oU + 2];
+            float s2, c2;
+            sincosf(ga, &s2, &c2);
+            const float dist = 0.01f * px * px + (py + 0.3f - 2.f) * (py + 0.3f - 2.f);
+            if (gl == 0 && pred) {
+                if (obs_out) {
+                    obs_out[0] = xx; obs_out[1] = vx; obs_out[2] = px; obs_out[3] = c; obs_out[4] = s; obs_out[5] = thd;
+                    obs_out[6] = c2; obs_out[7] = s2; obs_out[8] = gad;
+                }
+                if (!reset_pass) {
+                    if (rew_out) *rew_out = 10.f - dist;
+                    if (terms_out) { terms_out[0] = 10.f; terms_out[1] = -dist; terms_out[2] = 0.f; terms_out[3] = 0.f; terms_out[4] = 0.f; }
+                }
+            }
+            return !reset_pass && py + 0.3f <= 1.f;
+        }
         if (gl == 0 && pred) {
             if (obs_out) { obs_out[0] = xx; obs_out[1] = vx; obs_out[2] = c; obs_out[3] = s; obs_out[4] = thd; }
             if (!reset_pass) {
@@ -1092,7 +1115,7 @@ struct Env {
     // while only some of its env groups need it (no divergent __syncwarp / shuffles).
     __device__ bool task(const float *act, float *obs_out, float *rew_out, float *terms_out, bool reset_pass,
                          bool pred = true) {
-        if (m->kind <= 1) return pendulum_task(obs_out, rew_out, terms_out, reset_pass, pred);
+        if (m->kind <= 1 || m->kind == 9) return pendulum_task(obs_out, rew_out, terms_out, reset_pass, pred);
         return walker_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
     }
 
@@ -1119,9 +1142,10 @@ struct Env {
                 if (gl < 3) S[C::oX + gl] = m->cube_pos0[gl];
                 if (gl == 3) S[C::oX + 6] = 1.f;
             }
-            if (gl < C::NACT) {
+            if (gl < C::NNOISE) {
                 const float nz = noise ? noise[gl] : rng_uniform(la.seed, env, ep, 0u, (unsigned)gl, -0.1f, 0.1f);
                 if (m->kind <= 1) { if (gl == 0) S[C::oQ + 1] = nz + (m->kind == 1 ? 3.1415f : 0.f); }
+                else if (m->kind == 9) S[C::oQ + 1 + gl] = nz;          // hinge, hinge2 (rs/robot_pendula.py:66-68)
                 else S[C::oQ + m->act_joint[gl]] = nz;
             }
             if (gl == 0) {
@@ -1272,7 +1296,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
         if (pass == 1) {
             if (!reset_mode && !__any_sync(0xffffffffu, want_reset)) break;
             __syncwarp();
-            e.reset_state(la, genv, (reset_mode && B.noise) ? B.noise + env * C::NACT : nullptr,
+            e.reset_state(la, genv, (reset_mode && B.noise) ? B.noise + env * C::NNOISE : nullptr,
                           reset_mode ? la.floor_in_parts : 1, want_reset);
             rp = want_reset;                 // envs left out of a masked reset only get their observation refreshed
             pred = reset_mode ? true : want_reset;

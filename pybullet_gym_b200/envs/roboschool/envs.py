@@ -244,8 +244,43 @@ class InvertedPendulumSwingupBulletEnv(InvertedPendulumBulletEnv):
         self.stateId = -1
 
 
+class InvertedDoublePendulumBulletEnv(BaseBulletEnv):
+    """gym_pendulum_envs.py:50-86."""
+
+    def __init__(self, **kw):
+        self.robot = R.InvertedDoublePendulum()
+        BaseBulletEnv.__init__(self, self.robot, **kw)
+        self.stateId = -1
+
+    def create_single_player_scene(self, bullet_client):
+        return SingleRobotEmptyScene(self.robot.spec.scene)
+
+    def _draw_reset_noise(self):
+        return list(self.np_random.uniform(low=-.1, high=.1, size=[2]))     # robot_pendula.py:66
+
+    def _finish_reset(self, obs):
+        self.robot._invalidate()
+        self.robot.pos_x, _, self.robot.pos_y = self.robot.pole2.pose().xyz()
+        self.stateId = 0
+        return obs.astype(np.float64)
+
+    def _step(self, a):
+        a = np.asarray(a, dtype=np.float32)
+        assert np.isfinite(a).all()
+        obs, rew, done, info = self._backend.step(torch.from_numpy(a.reshape(1, -1)))
+        state = obs[0].cpu().numpy().astype(np.float64)
+        self.robot._invalidate()
+        self.robot.pos_x, _, self.robot.pos_y = self.robot.pole2.pose().xyz()
+        terms = info["reward_terms"][0].cpu().numpy()
+        self.rewards = [float(terms[0]), float(terms[1]), float(terms[2])]     # alive_bonus, -dist_penalty, -vel_penalty
+        d = bool(done[0])
+        self.HUD(state, a, d)
+        return state, sum(self.rewards), d, {}
+
+
 ENTRY_POINTS = {
     "InvertedPendulumPyBulletEnv-v0": InvertedPendulumBulletEnv,
+    "InvertedDoublePendulumPyBulletEnv-v0": InvertedDoublePendulumBulletEnv,
     "InvertedPendulumSwingupPyBulletEnv-v0": InvertedPendulumSwingupBulletEnv,
     "HopperPyBulletEnv-v0": HopperBulletEnv,
     "Walker2DPyBulletEnv-v0": Walker2DBulletEnv,

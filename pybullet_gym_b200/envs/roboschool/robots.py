@@ -263,6 +263,18 @@ class InvertedPendulum(MJCFBasedRobot):
         self.theta = 0.0
 
 
+class InvertedDoublePendulum(MJCFBasedRobot):
+    """robot_pendula.py:57-87."""
+
+    def __init__(self):
+        MJCFBasedRobot.__init__(self, "InvertedDoublePendulumPyBulletEnv-v0")
+        self.pole2 = self.parts["pole2"]
+        self.slider = self.jdict["slider"]
+        self.j1 = self.jdict["hinge"]
+        self.j2 = self.jdict["hinge2"]
+        self.pos_x, self.pos_y = 0.0, 0.0
+
+
 class InvertedPendulumSwingup(InvertedPendulum):
     swingup = True
 

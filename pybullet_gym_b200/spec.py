@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 KIND_PENDULUM, KIND_PENDULUM_SWINGUP, KIND_HOPPER, KIND_WALKER2D, KIND_HALFCHEETAH, KIND_ANT, KIND_HUMANOID, \
-    KIND_FLAGRUN, KIND_FLAGRUN_HARDER = range(9)
+    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM = range(10)
 
 
 @dataclass(frozen=True)
@@ -94,11 +94,23 @@ class EnvSpec:
     entry_point: str = ""
     cube: Optional[CubeSpec] = None
 
+    @property
+    def noise_dim(self) -> int:
+        """Reset draws per episode that the caller may inject (pbg_reset_with): one per actuated joint for the
+        walkers (robot_locomotors.py:18-19), the hinge for the pendulum (robot_pendula.py:16), both hinges for the
+        double pendulum (robot_pendula.py:66-68)."""
+        if self.kind == KIND_DOUBLE_PENDULUM:
+            return 2
+        return self.action_dim
+
     def torque_scale(self, ordered_joint_names: List[str]) -> List[float]:
         """tau_max per ordered joint = power * power_coef (robot_locomotors.py:29,189)."""
         if self.kind in (KIND_PENDULUM, KIND_PENDULUM_SWINGUP):
             # robot_pendula.py:25: only the slider is driven, 100 * clip(a)
             return [100.0 if n == "slider" else 0.0 for n in ordered_joint_names]
+        if self.kind == KIND_DOUBLE_PENDULUM:
+            # robot_pendula.py:73: 200 * clip(a) on the slider
+            return [200.0 if n == "slider" else 0.0 for n in ordered_joint_names]
         return [self.power * self.power_coef.get(n, 100.0) for n in ordered_joint_names]
 
 
@@ -119,6 +131,9 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
     EnvSpec("InvertedPendulumSwingupPyBulletEnv-v0", KIND_PENDULUM_SWINGUP, "inverted_pendulum.xml", "cart", 1, 5,
             1.0, scene=_PENDULUM_SCENE, reward_threshold=800.0,
             entry_point=_RS + "gym_pendulum_envs:InvertedPendulumSwingupBulletEnv"),
+    EnvSpec("InvertedDoublePendulumPyBulletEnv-v0", KIND_DOUBLE_PENDULUM, "inverted_double_pendulum.xml", "cart", 1, 9,
+            1.0, scene=_PENDULUM_SCENE, reward_threshold=9100.0,
+            entry_point=_RS + "gym_pendulum_envs:InvertedDoublePendulumBulletEnv"),
     EnvSpec("HopperPyBulletEnv-v0", KIND_HOPPER, "hopper.xml", "torso", 3, 15, 0.75, foot_list=("foot",),
             reward_threshold=2500.0, entry_point=_RS + "gym_locomotion_envs:HopperBulletEnv"),
     EnvSpec("Walker2DPyBulletEnv-v0", KIND_WALKER2D, "walker2d.xml", "torso", 6, 22, 0.40,
@@ -148,7 +163,7 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
 
 # ids the reference registers (envs/__init__.py) that this backend does not implement
 UNBACKED_IDS = (
-    "InvertedDoublePendulumPyBulletEnv-v0", "ReacherPyBulletEnv-v0", "PusherPyBulletEnv-v0",
+    "ReacherPyBulletEnv-v0", "PusherPyBulletEnv-v0",
     "ThrowerPyBulletEnv-v0", "StrikerPyBulletEnv-v0", "AtlasPyBulletEnv-v0",
     "InvertedPendulumMuJoCoEnv-v0", "InvertedDoublePendulumMuJoCoEnv-v0", "Walker2DMuJoCoEnv-v0",
     "HalfCheetahMuJoCoEnv-v0", "AntMuJoCoEnv-v0", "HopperMuJoCoEnv-v0", "HumanoidMuJoCoEnv-v0",

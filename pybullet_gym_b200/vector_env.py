@@ -55,6 +55,7 @@ class VectorEnv:
         self.obs_dim = self._L.pbg_obs_dim(h)
         self.action_dim = self._L.pbg_action_dim(h)
         self.state_dim = self._L.pbg_state_dim(h)
+        self.noise_dim = self._L.pbg_noise_dim(h)
         self.auto_reset = auto_reset
         self._L.pbg_set_auto_reset(h, int(auto_reset))
         E, dev = self.num_envs, self.device
@@ -102,6 +103,8 @@ class VectorEnv:
         with torch.cuda.device(self.device):
             if joint_noise is not None:
                 nz = joint_noise.to(device=self.device, dtype=torch.float32).contiguous()
+                if nz.shape != (self.num_envs, self.noise_dim):
+                    raise ValueError("joint_noise must have shape %s" % ((self.num_envs, self.noise_dim),))
                 rc = self._L.pbg_reset_with(self._h, _ptr(nz), int(floor_in_parts), _ptr(self.obs), self._stream())
             else:
                 m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()

@@ -47,6 +47,13 @@ def test_contact_free_policies_reach_reward_threshold(name, threshold, oracle_li
     assert min(s for s, _ in res) >= threshold, res
 
 
+def test_double_pendulum_policy_balances(oracle_lib):
+    """reward_threshold 9100 (pybulletgym/envs/__init__.py:15): most episodes keep both poles up for 1000 steps."""
+    res = rollout(oracle_lib, "InvertedDoublePendulum", episodes=5)
+    good = [s for s, n in res if n == 1000 and s >= 9100.0]
+    assert len(good) >= 3, res
+
+
 def test_hopper_policy_runs_full_episodes(oracle_lib):
     res = rollout(oracle_lib, "Hopper")
     assert all(n == 1000 for _, n in res) and min(s for s, _ in res) > 1500.0, res     # reward_threshold is 2500
@@ -61,7 +68,8 @@ def test_report_other_policies(oracle_lib, capsys):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,floor", [("InvertedPendulum", 950.0), ("InvertedPendulumSwingup", 800.0), ("Hopper", 1500.0)])
+@pytest.mark.parametrize("name,floor", [("InvertedPendulum", 950.0), ("InvertedPendulumSwingup", 800.0),
+                                        ("InvertedDoublePendulum", 9100.0), ("Hopper", 1500.0)])
 def test_policies_on_the_cuda_path(name, floor):
     torch = pytest.importorskip("torch")
     from pybullet_gym_b200.vector_env import VectorEnv

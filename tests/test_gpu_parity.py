@@ -22,7 +22,7 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-IDS = ["InvertedPendulumPyBulletEnv-v0", "HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
+IDS = ["InvertedPendulumPyBulletEnv-v0", "InvertedDoublePendulumPyBulletEnv-v0", "HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
        "AntPyBulletEnv-v0", "HumanoidPyBulletEnv-v0"]
 TASK_IDS = IDS + ["HumanoidFlagrunPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0"]
 E = 48
@@ -49,7 +49,7 @@ def _rel(g, o):
 def test_reset_matches_oracle(env_id, oracle_lib):
     env = _mk(env_id)
     rng = np.random.default_rng(0)
-    noise = rng.uniform(-0.1, 0.1, (E, env.action_dim)).astype(np.float32)
+    noise = rng.uniform(-0.1, 0.1, (E, env.noise_dim)).astype(np.float32)
     for floor in (False, True):
         obs = env.reset(joint_noise=torch.from_numpy(noise), floor_in_parts=floor).cpu().numpy()
         orcs = _oracles(oracle_lib, env_id, E)
@@ -76,7 +76,7 @@ def test_observation_reward_parity_T1(env_id, oracle_lib):
     env = _mk(env_id)
     rng = np.random.default_rng(3)
     nA = env.action_dim
-    noise = rng.uniform(-0.1, 0.1, (E, nA)).astype(np.float32)
+    noise = rng.uniform(-0.1, 0.1, (E, env.noise_dim)).astype(np.float32)
     env.reset(joint_noise=torch.from_numpy(noise), floor_in_parts=True)
     orcs = _oracles(oracle_lib, env_id, E)
     for i, o in enumerate(orcs):
@@ -101,7 +101,7 @@ def test_observation_reward_parity_T1(env_id, oracle_lib):
         body = slice(0, oobs.shape[1] - nf) if nf else slice(None)
         worst_obs = max(worst_obs, np.abs(gobs[:, body] - oobs[:, body]).max())
         worst_terms = max(worst_terms, np.abs(gterms[:, [0, 2, 3, 4]] - oterms[:, [0, 2, 3, 4]]).max())
-        if env.spec.kind >= 2:
+        if 2 <= env.spec.kind <= 8:
             x = np.abs(ost[:, 0] if env.spec.kind >= 5 else ost[:, 0])
             worst_prog = max(worst_prog, (np.abs(gterms[:, 1] - oterms[:, 1]) / (1.0 + x)).max())
             # alive / done decisions agree except within float32 round-off of a threshold
@@ -119,7 +119,7 @@ def test_single_substep_and_step_parity_T2(env_id, oracle_lib):
     env4, env1 = _mk(env_id), _mk(env_id, spec=spec1)
     rng = np.random.default_rng(5)
     nA = env4.action_dim
-    noise = rng.uniform(-0.1, 0.1, (E, nA)).astype(np.float32)
+    noise = rng.uniform(-0.1, 0.1, (E, env4.noise_dim)).astype(np.float32)
     env4.reset(joint_noise=torch.from_numpy(noise)); env1.reset(joint_noise=torch.from_numpy(noise))
     orcs = _oracles(oracle_lib, env_id, E)
     orcs1 = _oracles(oracle_lib, env_id, E, spec=spec1)
@@ -149,7 +149,7 @@ def test_single_substep_and_step_parity_T2(env_id, oracle_lib):
     assert np.median(e1) < 2e-5 and np.quantile(e1, 0.99) < 5e-3, (np.median(e1), np.quantile(e1, 0.99), e1.max())
     # one env step = 4 sub-steps
     assert np.median(e4) < 1e-4 and np.quantile(e4, 0.95) < 2e-2, (np.median(e4), np.quantile(e4, 0.95), e4.max())
-    if env_id in ("InvertedPendulumPyBulletEnv-v0", "AntPyBulletEnv-v0") and fr.any():
+    if env_id in ("InvertedPendulumPyBulletEnv-v0", "InvertedDoublePendulumPyBulletEnv-v0", "AntPyBulletEnv-v0") and fr.any():
         # contact-free env steps (pendulum always; Ant while airborne) are held to a max-norm bound
         assert e4[fr].max() < 1e-4, e4[fr].max()
 

@@ -96,12 +96,16 @@ class FakeBulletClient:
         assert os.path.basename(path) == spec.xml, (path, spec.xml)
         self.bm = mj.parse_mjcf(path)      # parses the *reference's* file
         self.orc = OracleEnv(spec, bm=self.bm, max_contacts=FakeBulletClient.max_contacts)
-        self.orc.reset(noise=np.zeros(spec.action_dim))
+        self.orc.reset(noise=np.zeros(spec.noise_dim))
         self.tau = np.zeros(self.orc.model.nd)
         self.dof_of_link = {li: k for k, li in enumerate(self.bm.dof_links())}
         ids = []
-        if os.path.basename(path) == "inverted_pendulum.xml":
-            # world-level geom "rail": separate static body, loaded first
+        if os.path.basename(path) in ("inverted_pendulum.xml", "inverted_double_pendulum.xml"):
+            # world-level geoms ("floor" plane of the double pendulum, "rail"): separate static bodies, loaded
+            # first
+            if os.path.basename(path) == "inverted_double_pendulum.xml":
+                self.bodies.append({"kind": "misc", "base": b"floor", "name": b"floor"})
+                ids.append(len(self.bodies) - 1)
             self.bodies.append({"kind": "misc", "base": b"rail", "name": b"rail"})
             ids.append(len(self.bodies) - 1)
         self.bodies.append({"kind": "robot", "base": self.bm.links[0].name.encode(), "name": self.bm.name.encode()})

@@ -32,6 +32,7 @@ CASES = {
     # env id -> (module, class, episodes, max steps per episode, action scale)
     "InvertedPendulumPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedPendulumBulletEnv", 3, 40, 1.0),
     "InvertedPendulumSwingupPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedPendulumSwingupBulletEnv", 2, 40, 1.0),
+    "InvertedDoublePendulumPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedDoublePendulumBulletEnv", 3, 60, 0.3),
     "HopperPyBulletEnv-v0": ("gym_locomotion_envs", "HopperBulletEnv", 4, 40, 1.3),
     "Walker2DPyBulletEnv-v0": ("gym_locomotion_envs", "Walker2DBulletEnv", 4, 40, 1.3),
     "HalfCheetahPyBulletEnv-v0": ("gym_locomotion_envs", "HalfCheetahBulletEnv", 4, 40, 1.3),
@@ -74,7 +75,8 @@ def main():
             obs0 = env._reset()
             draws = env.np_random.log[nlog:]
             flat = [v for d in draws if d[0] == "uniform" for v in d[3]]
-            noise, rec_tape = flat[:nA], None
+            nN = spec.noise_dim
+            noise, rec_tape = flat[:nN], None
             rec = {"noise": noise, "obs0": np.asarray(obs0, dtype=np.float64).tolist(), "steps": []}
             s_reset = env._p.orc.get_state().copy()
             for t in range(max_steps):
@@ -99,7 +101,7 @@ def main():
                 if done:
                     break
             # every task-layer draw after the joint noise (flag positions, cube attacks), in order
-            rec["tape"] = [v for d in env.np_random.log[nlog:] if d[0] == "uniform" for v in d[3]][nA:]
+            rec["tape"] = [v for d in env.np_random.log[nlog:] if d[0] == "uniform" for v in d[3]][nN:]
             eps.append(rec)
         calls = dict(env._p.calls)
         out = {"env_id": env_id, "reference_class": "pybulletgym.envs.roboschool.%s:%s" % (mod, cls),
