@@ -38,7 +38,7 @@ typedef enum {
 enum {
     PBG_KIND_PENDULUM = 0, PBG_KIND_PENDULUM_SWINGUP = 1, PBG_KIND_HOPPER = 2, PBG_KIND_WALKER2D = 3,
     PBG_KIND_HALFCHEETAH = 4, PBG_KIND_ANT = 5, PBG_KIND_HUMANOID = 6, PBG_KIND_FLAGRUN = 7,
-    PBG_KIND_FLAGRUN_HARDER = 8, PBG_KIND_DOUBLE_PENDULUM = 9
+    PBG_KIND_FLAGRUN_HARDER = 8, PBG_KIND_DOUBLE_PENDULUM = 9, PBG_KIND_REACHER = 10
 };
 
 enum { PBG_JT_FIXED = 0, PBG_JT_REVOLUTE = 1, PBG_JT_PRISMATIC = 2, PBG_JT_FREE = 3 };
@@ -101,6 +101,9 @@ typedef struct pbg_model {
     int32_t cube;
     double cube_half, cube_mass, cube_inertia, cube_friction, cube_threshold;
     double cube_pos0[3];
+    /* links (indices into sub_*) whose COM the task layer reads besides torso_sub: Reacher's fingertip and
+     * target (rs/robot_manipulators.py:17-18,33); -1: unused */
+    int32_t aux_sub[2];
 } pbg_model;
 
 typedef struct pbg_handle pbg_handle;

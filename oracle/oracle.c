@@ -1026,6 +1026,21 @@ static void walker_calc_state(orc_env *e, double *obs) {
     for (int k = 0; k < o; k++) { if (obs[k] < -5) obs[k] = -5; if (obs[k] > 5) obs[k] = 5; }
 }
 
+/* Reacher.calc_state (rs/robot_manipulators.py:28-47): dofs joint0, joint1, target_x, target_y */
+static void reacher_calc_state(orc_env *e, double *obs) {
+    const orc_model *m = &e->m;
+    fk(e);
+    double theta = e->q[0], theta_dot = 0.1 * e->qd[0];        /* joint0 is unlimited: raw position */
+    int l1 = e->link_of_dof[1];
+    double gamma = 2 * (e->q[1] - 0.5 * (m->lower[l1] + m->upper[l1])) / (m->upper[l1] - m->lower[l1]), gamma_dot = 0.1 * e->qd[1];
+    const double *ft = e->c[m->aux_link[0]], *tg = e->c[m->aux_link[1]];
+    for (int k = 0; k < 3; k++) e->body_xyz[k] = ft[k] - tg[k];       /* to_target_vec */
+    e->joint_speeds[0] = theta_dot; e->joint_speeds[1] = gamma_dot; e->body_rpy[0] = gamma;
+    obs[0] = e->q[2]; obs[1] = e->q[3]; obs[2] = e->body_xyz[0]; obs[3] = e->body_xyz[1];
+    obs[4] = cos(theta); obs[5] = sin(theta); obs[6] = theta_dot; obs[7] = gamma; obs[8] = gamma_dot;
+}
+static double reacher_potential(const orc_env *e) { return -100.0 * v3norm(e->body_xyz); }
+
 static void pendulum_calc_state(orc_env *e, double *obs) {
     /* rs/robot_pendula.py:27-51: slider = dof 0, hinge = dof 1 */
     double x = e->q[0], vx = e->qd[0], th = e->q[1], thd = e->qd[1];
@@ -1060,7 +1075,17 @@ int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double
     const orc_model *m = &e->m;
     double t5[5] = {0, 0, 0, 0, 0};
     int done = 0;
-    if (!is_walker(m->kind)) {
+    if (m->kind == ORC_KIND_REACHER) {
+        /* ReacherBulletEnv._step (rs/gym_manipulator_envs.py:15-32): never done */
+        reacher_calc_state(e, obs);
+        double pold = e->potential;
+        e->potential = reacher_potential(e);
+        double td = e->joint_speeds[0], gd = e->joint_speeds[1], gamma = e->body_rpy[0];
+        t5[0] = e->potential - pold;
+        t5[1] = -0.10 * (fabs(a[0] * td) + fabs(a[1] * gd)) - 0.01 * (fabs(a[0]) + fabs(a[1]));
+        t5[2] = fabs(fabs(gamma) - 1) < 0.01 ? -0.1 : 0.0;
+        *reward = t5[0] + t5[1] + t5[2];
+    } else if (!is_walker(m->kind)) {
         pendulum_calc_state(e, obs);
         double th = e->q[1];
         if (m->kind == ORC_KIND_DOUBLE_PENDULUM) {
@@ -1116,6 +1141,9 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
     }
     if (is_walker(m->kind)) {
         for (int n = 0; n < m->nact; n++) e->q[e->dof_of_link[m->act_link[n]]] = noise[n];
+    } else if (m->kind == ORC_KIND_REACHER) {
+        /* rs/robot_manipulators.py:12-21: target_x, target_y, joint0, joint1 in this draw order */
+        e->q[2] = noise[0]; e->q[3] = noise[1]; e->q[0] = noise[2]; e->q[1] = noise[3];
     } else {
         e->q[1] = noise[0] + (m->kind == ORC_KIND_PENDULUM_SWINGUP ? 3.1415 : 0.0);
         if (m->kind == ORC_KIND_DOUBLE_PENDULUM) e->q[2] = noise[1];       /* rs/robot_pendula.py:66-68 */
@@ -1133,6 +1161,7 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
     e->flag_count = 0; e->flag_timeout = 0; e->frame = 0; e->on_ground = 0; e->crawl_has = 0; e->crawl_start = 0; e->crawl_ign = 0; e->attacks = 0;
     if (is_flagrun(m->kind)) flag_reposition(e);
     if (is_walker(m->kind)) { walker_calc_state(e, obs); e->potential = calc_potential(e); }
+    else if (m->kind == ORC_KIND_REACHER) { reacher_calc_state(e, obs); e->potential = reacher_potential(e); }
     else pendulum_calc_state(e, obs);
     /* quirk Q1: the env adds the floor to robot.parts right after this first calc_state
      * (rs/gym_locomotion_envs.py:30-31), so every later calc_state of the episode averages it in */
@@ -1149,6 +1178,8 @@ void orc_reset(orc_env *e, int floor_in_parts, double *obs) {
     e->episode++;
     int n = is_walker(e->m.kind) ? e->m.nact : (e->m.kind == ORC_KIND_DOUBLE_PENDULUM ? 2 : 1);
     for (int k = 0; k < n; k++) noise[k] = rng_uniform(e->seed, e->env_index, e->episode, (uint32_t)k, -0.1f, 0.1f);
+    if (e->m.kind == ORC_KIND_REACHER)
+        for (int k = 0; k < 4; k++) { float r = k < 2 ? 0.27f : 3.14f; noise[k] = rng_uniform(e->seed, e->env_index, e->episode, (uint32_t)k, -r, r); }
     reset_common(e, noise, floor_in_parts, obs);
 }
 

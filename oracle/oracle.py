@@ -54,6 +54,7 @@ class OrcModel(C.Structure):
         ("cube", C.c_int32),
         ("cube_half", C.c_double), ("cube_mass", C.c_double), ("cube_inertia", C.c_double),
         ("cube_friction", C.c_double), ("cube_threshold", C.c_double), ("cube_pos0", C.c_double * 3),
+        ("aux_link", C.c_int32 * 2),
     ]
 
 
@@ -195,6 +196,8 @@ class OracleModel:
         m.max_episode_steps = spec.max_episode_steps
         m.stadium_halflen, m.stadium_halfwidth = sc.stadium_halflen, sc.stadium_halfwidth
         m.torsional = int(getattr(sc, 'torsional_friction', False))
+        for i in range(2):
+            m.aux_link[i] = bm.link_index(spec.aux_links[i]) if i < len(spec.aux_links) else -1
         cube = spec.cube
         m.cube = 1 if cube is not None else 0
         if cube is not None:

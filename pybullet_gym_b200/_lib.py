@@ -65,6 +65,7 @@ class PbgModel(C.Structure):
         ("cube", C.c_int32),
         ("cube_half", C.c_double), ("cube_mass", C.c_double), ("cube_inertia", C.c_double),
         ("cube_friction", C.c_double), ("cube_threshold", C.c_double), ("cube_pos0", C.c_double * 3),
+        ("aux_sub", C.c_int32 * 2),
     ]
 
 
@@ -192,6 +193,8 @@ class ModelTables:
         m.joints_at_limit_cost = spec.joints_at_limit_cost
         m.walk_target_x, m.walk_target_y = spec.walk_target
         m.stadium_halflen, m.stadium_halfwidth = sc.stadium_halflen, sc.stadium_halfwidth
+        for i in range(2):
+            m.aux_sub[i] = rm.sub_names.index(spec.aux_links[i]) if i < len(spec.aux_links) else -1
         cube = spec.cube
         m.cube = 1 if cube is not None else 0
         if cube is not None:

@@ -1111,11 +1111,47 @@ struct Env {
         return !reset_pass && m->kind == 0 && fabsf(th) > 0.2f;
     }
 
+    // Reacher (rs/robot_manipulators.py:28-50, rs/gym_manipulator_envs.py:15-32): dofs joint0, joint1, target_x, target_y.
+    // Never done; reward = potential change + electricity + stuck-joint cost.
+    __device__ bool reacher_task(const float *act, float *obs_out, float *rew_out, float *terms_out, bool reset_pass, bool pred) {
+        float *S = st();
+        float *T = S + C::oT;
+        fk(false);
+        const float *kf = kin(m->aux_body[0]), *kt = kin(m->aux_body[1]);
+        const V3 d = (ld3(kf + 9) + mulR(kf, ld3(m->aux_off[0]))) - (ld3(kt + 9) + mulR(kt, ld3(m->aux_off[1])));
+        const float theta = S[C::oQ], theta_dot = 0.1f * S[C::oU];
+        const float lo = m->jlo[1], hi = m->jhi[1];
+        const float gamma = 2.f * (S[C::oQ + 1] - 0.5f * (lo + hi)) / (hi - lo), gamma_dot = 0.1f * S[C::oU + 1];
+        float st_, ct_;
+        sincosf(theta, &st_, &ct_);
+        const double pot_new = -100.0 * sqrt((double)d.x * d.x + (double)d.y * d.y + (double)d.z * d.z);
+        if (gl == 0 && pred) {
+            if (obs_out) {
+                obs_out[0] = S[C::oQ + 2]; obs_out[1] = S[C::oQ + 3]; obs_out[2] = d.x; obs_out[3] = d.y;
+                obs_out[4] = ct_; obs_out[5] = st_; obs_out[6] = theta_dot; obs_out[7] = gamma; obs_out[8] = gamma_dot;
+            }
+            if (!reset_pass) {
+                const double pot_old = __hiloint2double(__float_as_int(T[T_POT_HI]), __float_as_int(T[T_POT_LO]));
+                const float a0 = act ? act[0] : 0.f, a1 = act ? act[1] : 0.f;
+                const float progress = (float)(pot_new - pot_old);
+                const float elec = -0.10f * (fabsf(a0 * theta_dot) + fabsf(a1 * gamma_dot)) - 0.01f * (fabsf(a0) + fabsf(a1));
+                const float stuck = fabsf(fabsf(gamma) - 1.f) < 0.01f ? -0.1f : 0.f;
+                if (rew_out) *rew_out = progress + elec + stuck;
+                if (terms_out) { terms_out[0] = progress; terms_out[1] = elec; terms_out[2] = stuck; terms_out[3] = 0.f; terms_out[4] = 0.f; }
+            }
+            T[T_POT_LO] = __int_as_float(__double2loint(pot_new));
+            T[T_POT_HI] = __int_as_float(__double2hiint(pot_new));
+        }
+        __syncwarp();
+        return false;
+    }
+
     // `pred` guards every persistent write, so that a whole warp can run the task / reset code
     // while only some of its env groups need it (no divergent __syncwarp / shuffles).
     __device__ bool task(const float *act, float *obs_out, float *rew_out, float *terms_out, bool reset_pass,
                          bool pred = true) {
         if (m->kind <= 1 || m->kind == 9) return pendulum_task(obs_out, rew_out, terms_out, reset_pass, pred);
+        if (m->kind == 10) return reacher_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
         return walker_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
     }
 
@@ -1143,9 +1179,12 @@ struct Env {
                 if (gl == 3) S[C::oX + 6] = 1.f;
             }
             if (gl < C::NNOISE) {
-                const float nz = noise ? noise[gl] : rng_uniform(la.seed, env, ep, 0u, (unsigned)gl, -0.1f, 0.1f);
+                // draw ranges: U(-0.1, 0.1) per joint; Reacher: target_x/y U(+-0.27), joint0/1 U(+-3.14) (rs/robot_manipulators.py:12-21)
+                const float rr = m->kind == 10 ? (gl < 2 ? 0.27f : 3.14f) : 0.1f;
+                const float nz = noise ? noise[gl] : rng_uniform(la.seed, env, ep, 0u, (unsigned)gl, -rr, rr);
                 if (m->kind <= 1) { if (gl == 0) S[C::oQ + 1] = nz + (m->kind == 1 ? 3.1415f : 0.f); }
                 else if (m->kind == 9) S[C::oQ + 1 + gl] = nz;          // hinge, hinge2 (rs/robot_pendula.py:66-68)
+                else if (m->kind == 10) S[C::oQ + (gl ^ 2)] = nz;        // draws: target_x, target_y, joint0, joint1 -> dofs 2, 3, 0, 1
                 else S[C::oQ + m->act_joint[gl]] = nz;
             }
             if (gl == 0) {

@@ -37,6 +37,8 @@ struct DevModel {
         p_mu[MPAIR];
     int p_box[MPAIR];                         // 1: body B is the cube, p_b0 = half extents
     float cube_pos0[3];
+    int aux_body[2];                          // Reacher: fingertip / target bodies and their link-COM offsets
+    float aux_off[2][3];
     float torso_off[3];
     float base_pos0[3], base_quat0[4];
     // scene

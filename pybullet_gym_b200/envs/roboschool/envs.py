@@ -278,8 +278,43 @@ class InvertedDoublePendulumBulletEnv(BaseBulletEnv):
         return state, sum(self.rewards), d, {}
 
 
+class ReacherBulletEnv(BaseBulletEnv):
+    """gym_manipulator_envs.py:7-38."""
+
+    def __init__(self, **kw):
+        self.robot = R.Reacher()
+        BaseBulletEnv.__init__(self, self.robot, **kw)
+
+    def create_single_player_scene(self, bullet_client):
+        return SingleRobotEmptyScene(self.robot.spec.scene)
+
+    def _draw_reset_noise(self):
+        # robot_manipulators.py:12-21: target_x, target_y, joint0, joint1 -- in this order
+        r, lim = self.np_random, self.robot.TARG_LIMIT
+        return [r.uniform(low=-lim, high=lim), r.uniform(low=-lim, high=lim),
+                r.uniform(low=-3.14, high=3.14), r.uniform(low=-3.14, high=3.14)]
+
+    def _finish_reset(self, obs):
+        self.robot._update_views()
+        self.potential = self.robot.calc_potential()
+        return obs.astype(np.float64)
+
+    def _step(self, a):
+        a = np.asarray(a, dtype=np.float32)
+        assert np.isfinite(a).all()
+        obs, rew, done, info = self._backend.step(torch.from_numpy(a.reshape(1, -1)))
+        state = obs[0].cpu().numpy().astype(np.float64)
+        self.robot._update_views()
+        self.potential = self.robot.calc_potential()
+        terms = info["reward_terms"][0].cpu().numpy()
+        self.rewards = [float(terms[0]), float(terms[1]), float(terms[2])]     # progress, electricity_cost, stuck_joint_cost
+        self.HUD(state, a, False)
+        return state, sum(self.rewards), False, {}
+
+
 ENTRY_POINTS = {
     "InvertedPendulumPyBulletEnv-v0": InvertedPendulumBulletEnv,
+    "ReacherPyBulletEnv-v0": ReacherBulletEnv,
     "InvertedDoublePendulumPyBulletEnv-v0": InvertedDoublePendulumBulletEnv,
     "InvertedPendulumSwingupPyBulletEnv-v0": InvertedPendulumSwingupBulletEnv,
     "HopperPyBulletEnv-v0": HopperBulletEnv,

@@ -275,6 +275,29 @@ class InvertedDoublePendulum(MJCFBasedRobot):
         self.pos_x, self.pos_y = 0.0, 0.0
 
 
+class Reacher(MJCFBasedRobot):
+    """robot_manipulators.py:5-50."""
+    TARG_LIMIT = 0.27
+
+    def __init__(self):
+        MJCFBasedRobot.__init__(self, "ReacherPyBulletEnv-v0")
+        self.fingertip = self.parts["fingertip"]
+        self.target = self.parts["target"]
+        self.central_joint = self.jdict["joint0"]
+        self.elbow_joint = self.jdict["joint1"]
+        self.theta_dot = self.gamma = self.gamma_dot = 0.0
+        self.to_target_vec = np.zeros(3)
+
+    def _update_views(self):
+        self._invalidate()
+        _, self.theta_dot = self.central_joint.current_relative_position()
+        self.gamma, self.gamma_dot = self.elbow_joint.current_relative_position()
+        self.to_target_vec = np.array(self.fingertip.pose().xyz()) - np.array(self.target.pose().xyz())
+
+    def calc_potential(self):
+        return -100 * np.linalg.norm(self.to_target_vec)
+
+
 class InvertedPendulumSwingup(InvertedPendulum):
     swingup = True
 

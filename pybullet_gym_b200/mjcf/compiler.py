@@ -301,8 +301,8 @@ def parse_mjcf(path_or_name: str, rules: Optional[ImporterRules] = None) -> Bull
             dflt.geom = dict(d.find("geom").attrib)
     wb = root.find("worldbody")
     top = [b for b in wb.findall("body")]
-    if len(top) != 1:
-        raise NotImplementedError("exactly one top-level body expected")
+    if len(top) != 1 and any(not b.findall("joint") for b in top):
+        raise NotImplementedError("several top-level bodies are supported only when each has joints (fixed bases)")
     links: List[Link] = []
     counter = [0]
 
@@ -320,8 +320,11 @@ def parse_mjcf(path_or_name: str, rules: Optional[ImporterRules] = None) -> Bull
         cur_pos, cur_quat = bpos, bq            # pose of the *body frame* in the current parent frame
         floating_root = is_root and not joints
         if is_root and joints:
-            # massless fixed base at the world origin (C1.2)
-            links.append(Link("base", -1, "", JT_FIXED, np.zeros(3), np.zeros(3), np.array([0, 0, 0, 1.0])))
+            # massless fixed base at the world origin (C1.2).  Bullet makes every top-level body its own multibody
+            # (Reacher: the arm and the target); their fixed massless bases coincide with the world, so one shared
+            # base link carries all of them here -- the trees stay dynamically independent.
+            if not links:
+                links.append(Link("base", -1, "", JT_FIXED, np.zeros(3), np.zeros(3), np.array([0, 0, 0, 1.0])))
             cur_parent = 0
         for j in joints:
             a = dict(dflt.joint)
@@ -372,10 +375,17 @@ def parse_mjcf(path_or_name: str, rules: Optional[ImporterRules] = None) -> Bull
         for ch in elem.findall("body"):
             add_body(ch, me, False)
 
-    add_body(top[0], -1, True)
+    body_first_link = []
+    for t in top:
+        body_first_link.append(len(links) if links else 1)
+        add_body(t, -1, True)
     floating = links[0].jtype == JT_FREE
     name = root.get("model", os.path.basename(path))
-    return BulletModel(name, links, floating, rules)
+    bm = BulletModel(name, links, floating, rules)
+    # link ranges of the top-level bodies (one pybullet multibody each): [first non-base link, end)
+    ends = body_first_link[1:] + [len(links)]
+    bm.multibody_links = [(a, b) for a, b in zip(body_first_link, ends)]
+    return bm
 
 
 # ----------------------------------------------------------------------------------------------

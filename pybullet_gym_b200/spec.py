@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 KIND_PENDULUM, KIND_PENDULUM_SWINGUP, KIND_HOPPER, KIND_WALKER2D, KIND_HALFCHEETAH, KIND_ANT, KIND_HUMANOID, \
-    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM = range(10)
+    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM, KIND_REACHER = range(11)
 
 
 @dataclass(frozen=True)
@@ -93,6 +93,7 @@ class EnvSpec:
     walk_target: Tuple[float, float] = (1e3, 0.0)
     entry_point: str = ""
     cube: Optional[CubeSpec] = None
+    aux_links: Tuple[str, ...] = ()          # links whose COM the task layer reads besides robot_name (Reacher: fingertip, target)
 
     @property
     def noise_dim(self) -> int:
@@ -101,7 +102,16 @@ class EnvSpec:
         double pendulum (robot_pendula.py:66-68)."""
         if self.kind == KIND_DOUBLE_PENDULUM:
             return 2
+        if self.kind == KIND_REACHER:
+            return 4            # target_x, target_y, joint0, joint1 (robot_manipulators.py:12-21)
         return self.action_dim
+
+    @property
+    def noise_ranges(self) -> List[Tuple[float, float]]:
+        """(low, high) of every reset draw, in draw order."""
+        if self.kind == KIND_REACHER:
+            return [(-0.27, 0.27), (-0.27, 0.27), (-3.14, 3.14), (-3.14, 3.14)]
+        return [(-0.1, 0.1)] * self.noise_dim
 
     def torque_scale(self, ordered_joint_names: List[str]) -> List[float]:
         """tau_max per ordered joint = power * power_coef (robot_locomotors.py:29,189)."""
@@ -111,6 +121,9 @@ class EnvSpec:
         if self.kind == KIND_DOUBLE_PENDULUM:
             # robot_pendula.py:73: 200 * clip(a) on the slider
             return [200.0 if n == "slider" else 0.0 for n in ordered_joint_names]
+        if self.kind == KIND_REACHER:
+            # robot_manipulators.py:23-26: 0.05 * clip(a) on the two arm hinges
+            return [0.05 if n in ("joint0", "joint1") else 0.0 for n in ordered_joint_names]
         return [self.power * self.power_coef.get(n, 100.0) for n in ordered_joint_names]
 
 
@@ -134,6 +147,9 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
     EnvSpec("InvertedDoublePendulumPyBulletEnv-v0", KIND_DOUBLE_PENDULUM, "inverted_double_pendulum.xml", "cart", 1, 9,
             1.0, scene=_PENDULUM_SCENE, reward_threshold=9100.0,
             entry_point=_RS + "gym_pendulum_envs:InvertedDoublePendulumBulletEnv"),
+    EnvSpec("ReacherPyBulletEnv-v0", KIND_REACHER, "reacher.xml", "body0", 2, 9, 1.0,
+            scene=SceneSpec(gravity=0.0, timestep=0.0165, frame_skip=1), max_episode_steps=150, reward_threshold=18.0,
+            aux_links=("fingertip", "target"), entry_point=_RS + "gym_manipulator_envs:ReacherBulletEnv"),
     EnvSpec("HopperPyBulletEnv-v0", KIND_HOPPER, "hopper.xml", "torso", 3, 15, 0.75, foot_list=("foot",),
             reward_threshold=2500.0, entry_point=_RS + "gym_locomotion_envs:HopperBulletEnv"),
     EnvSpec("Walker2DPyBulletEnv-v0", KIND_WALKER2D, "walker2d.xml", "torso", 6, 22, 0.40,
@@ -163,7 +179,7 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
 
 # ids the reference registers (envs/__init__.py) that this backend does not implement
 UNBACKED_IDS = (
-    "ReacherPyBulletEnv-v0", "PusherPyBulletEnv-v0",
+    "PusherPyBulletEnv-v0",
     "ThrowerPyBulletEnv-v0", "StrikerPyBulletEnv-v0", "AtlasPyBulletEnv-v0",
     "InvertedPendulumMuJoCoEnv-v0", "InvertedDoublePendulumMuJoCoEnv-v0", "Walker2DMuJoCoEnv-v0",
     "HalfCheetahMuJoCoEnv-v0", "AntMuJoCoEnv-v0", "HopperMuJoCoEnv-v0", "HumanoidMuJoCoEnv-v0",

@@ -59,4 +59,4 @@ def test_unbacked_ids_raise():
     from pybullet_gym_b200.envs import make, registry
     assert "AntPyBulletEnv-v0" in registry and registry["AntPyBulletEnv-v0"]["max_episode_steps"] == 1000
     with pytest.raises(NotImplementedError):
-        make("ReacherPyBulletEnv-v0")
+        make("PusherPyBulletEnv-v0")

@@ -22,7 +22,7 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-IDS = ["InvertedPendulumPyBulletEnv-v0", "InvertedDoublePendulumPyBulletEnv-v0", "HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
+IDS = ["InvertedPendulumPyBulletEnv-v0", "InvertedDoublePendulumPyBulletEnv-v0", "ReacherPyBulletEnv-v0", "HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
        "AntPyBulletEnv-v0", "HumanoidPyBulletEnv-v0"]
 TASK_IDS = IDS + ["HumanoidFlagrunPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0"]
 E = 48
@@ -149,7 +149,8 @@ def test_single_substep_and_step_parity_T2(env_id, oracle_lib):
     assert np.median(e1) < 2e-5 and np.quantile(e1, 0.99) < 5e-3, (np.median(e1), np.quantile(e1, 0.99), e1.max())
     # one env step = 4 sub-steps
     assert np.median(e4) < 1e-4 and np.quantile(e4, 0.95) < 2e-2, (np.median(e4), np.quantile(e4, 0.95), e4.max())
-    if env_id in ("InvertedPendulumPyBulletEnv-v0", "InvertedDoublePendulumPyBulletEnv-v0", "AntPyBulletEnv-v0") and fr.any():
+    if env_id in ("InvertedPendulumPyBulletEnv-v0", "InvertedDoublePendulumPyBulletEnv-v0", "ReacherPyBulletEnv-v0",
+                  "AntPyBulletEnv-v0") and fr.any():
         # contact-free env steps (pendulum always; Ant while airborne) are held to a max-norm bound
         assert e4[fr].max() < 1e-4, e4[fr].max()
 

@@ -7,7 +7,7 @@ pytestmark = pytest.mark.gpu
 
 FULL = {"HalfCheetahPyBulletEnv-v0": 4096, "HopperPyBulletEnv-v0": 4096, "Walker2DPyBulletEnv-v0": 4096,
         "AntPyBulletEnv-v0": 16384, "HumanoidPyBulletEnv-v0": 2048, "InvertedPendulumPyBulletEnv-v0": 4096,
-        "InvertedDoublePendulumPyBulletEnv-v0": 4096, "HumanoidFlagrunHarderPyBulletEnv-v0": 2048}
+        "InvertedDoublePendulumPyBulletEnv-v0": 4096, "ReacherPyBulletEnv-v0": 4096, "HumanoidFlagrunHarderPyBulletEnv-v0": 2048}
 
 
 def _mk(env_id, n, **kw):

@@ -19,6 +19,7 @@ FILES = {
     "InvertedPendulumPyBulletEnv-v0": "enjoy_TF_InvertedPendulumPyBulletEnv_v0_2017may.py",
     "InvertedPendulumSwingupPyBulletEnv-v0": "enjoy_TF_InvertedPendulumSwingupPyBulletEnv_v0_2017may.py",
     "InvertedDoublePendulumPyBulletEnv-v0": "enjoy_TF_InvertedDoublePendulumPyBulletEnv_v0_2017may.py",
+    "ReacherPyBulletEnv-v0": "enjoy_TF_ReacherPyBulletEnv_v0_2017may.py",
     "HopperPyBulletEnv-v0": "enjoy_TF_HopperPyBulletEnv_v0_2017may.py",
     "Walker2DPyBulletEnv-v0": "enjoy_TF_Walker2DPyBulletEnv_v0_2017may.py",
     "HalfCheetahPyBulletEnv-v0": "enjoy_TF_HalfCheetahPyBulletEnv_v0_2017may.py",

@@ -108,9 +108,17 @@ class FakeBulletClient:
                 ids.append(len(self.bodies) - 1)
             self.bodies.append({"kind": "misc", "base": b"rail", "name": b"rail"})
             ids.append(len(self.bodies) - 1)
-        self.bodies.append({"kind": "robot", "base": self.bm.links[0].name.encode(), "name": self.bm.name.encode()})
-        ids.append(len(self.bodies) - 1)
-        self.robot_id = ids[-1]
+        if os.path.basename(path) == "reacher.xml":
+            # six world-level geoms (ground, four sides, root) -> static bodies, loaded first
+            for nm in (b"ground", b"sideS", b"sideE", b"sideN", b"sideW", b"root"):
+                self.bodies.append({"kind": "misc", "base": nm, "name": nm})
+                ids.append(len(self.bodies) - 1)
+        # one pybullet multibody per top-level <body> (Reacher: arm, target); joint j of a body = link links[j]
+        for a, b in self.bm.multibody_links:
+            self.bodies.append({"kind": "robot", "base": self.bm.links[0].name.encode(), "name": self.bm.name.encode(),
+                                "links": list(range(a, b))})
+            ids.append(len(self.bodies) - 1)
+        self.robot_id = ids[-1] if len(self.bm.multibody_links) == 1 else ids[-len(self.bm.multibody_links)]
         return tuple(ids)
 
     def loadSDF(self, path):
@@ -125,19 +133,24 @@ class FakeBulletClient:
         # HumanoidFlagrunHarder's aggressive cube (gym_utils.py:9-16) is a simulated body of the oracle
         if os.path.basename(path) == "cube_small.urdf" and FakeBulletClient.current_spec.cube is not None:
             self.bodies[-1]["kind"] = "cube"
+            self.cube_id = len(self.bodies) - 1
             self.orc.set_cube(pos=list(basePosition), quat=[0, 0, 0, 1], omega=[0, 0, 0], vel=[0, 0, 0])
         return len(self.bodies) - 1
 
     # ---- structure queries
     def getNumJoints(self, body):
-        return len(self.bm.links) - 1 if self.bodies[body]["kind"] == "robot" else 0
+        return len(self.bodies[body]["links"]) if self.bodies[body]["kind"] == "robot" else 0
+
+    def _li(self, body, j):
+        """oracle link index of joint / link j of a robot body"""
+        return self.bodies[body]["links"][j]
 
     def getBodyInfo(self, body):
         b = self.bodies[body]
         return (b["base"], b["name"])
 
     def getJointInfo(self, body, j):
-        l = self.bm.links[j + 1]
+        l = self.bm.links[self._li(body, j)]
         jt = {mj.JT_REVOLUTE: JOINT_REVOLUTE, mj.JT_PRISMATIC: JOINT_PRISMATIC, mj.JT_FIXED: JOINT_FIXED}[l.jtype]
         return (j, l.joint_name.encode(), jt, -1, -1, 0, l.damping, 0.0, l.lower, l.upper, 0.0, 0.0, l.name.encode(),
                 tuple(l.axis), (0, 0, 0), (0, 0, 0, 1), l.parent - 1)
@@ -146,10 +159,10 @@ class FakeBulletClient:
     def setJointMotorControl2(self, bodyIndex=None, jointIndex=None, controlMode=None, *args, **kw):
         self._count("setJointMotorControl2")
         if controlMode == TORQUE_CONTROL:
-            self.tau[self.dof_of_link[jointIndex + 1]] += kw.get("force", 0.0)
+            self.tau[self.dof_of_link[self._li(bodyIndex, jointIndex)]] += kw.get("force", 0.0)
 
     def resetJointState(self, body, j, targetValue=0.0, targetVelocity=0.0):
-        self.orc.set_joint(self.dof_of_link[j + 1], targetValue, targetVelocity)
+        self.orc.set_joint(self.dof_of_link[self._li(body, j)], targetValue, targetVelocity)
 
     def resetBasePositionAndOrientation(self, body, pos, orn):
         if self.bodies[body]["kind"] == "misc":
@@ -172,7 +185,7 @@ class FakeBulletClient:
     # ---- state queries
     def getJointState(self, body, j):
         self._count("getJointState")
-        q, qd = self.orc.get_joint(self.dof_of_link[j + 1])
+        q, qd = self.orc.get_joint(self.dof_of_link[self._li(body, j)])
         return (q, qd, (0,) * 6, 0.0)
 
     def _link(self, idx):
@@ -193,7 +206,7 @@ class FakeBulletClient:
 
     def getLinkState(self, body, link, computeLinkVelocity=0):
         self._count("getLinkState")
-        s = self._link(link + 1)
+        s = self._link(self._li(body, link))
         base = (tuple(s[0:3]), tuple(s[3:7]), (0, 0, 0), (0, 0, 0, 1), tuple(s[0:3]), tuple(s[3:7]))
         if computeLinkVelocity:
             return base + (tuple(s[7:10]), (0.0, 0.0, 0.0))
@@ -210,7 +223,9 @@ class FakeBulletClient:
         out = []
         for a, b, d in zip(la, lb, dist):
             if bodyA == self.robot_id and a - 1 == linkIndexA:
-                if b < 0:
+                if b == -2:      # the cube (oracle.c LINK_CUBE)
+                    out.append((0, bodyA, getattr(self, "cube_id", -1), linkIndexA, -1, (0, 0, 0), (0, 0, 0), (0, 0, 1), d, 0.0))
+                elif b < 0:
                     out.append((0, bodyA, self.floor_id, linkIndexA, -1, (0, 0, 0), (0, 0, 0), (0, 0, 1), d, 0.0))
                 else:
                     out.append((0, bodyA, bodyA, linkIndexA, int(b) - 1, (0, 0, 0), (0, 0, 0), (0, 0, 1), d, 0.0))

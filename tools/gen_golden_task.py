@@ -33,6 +33,7 @@ CASES = {
     "InvertedPendulumPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedPendulumBulletEnv", 3, 40, 1.0),
     "InvertedPendulumSwingupPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedPendulumSwingupBulletEnv", 2, 40, 1.0),
     "InvertedDoublePendulumPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedDoublePendulumBulletEnv", 3, 60, 0.3),
+    "ReacherPyBulletEnv-v0": ("gym_manipulator_envs", "ReacherBulletEnv", 3, 60, 1.3),
     "HopperPyBulletEnv-v0": ("gym_locomotion_envs", "HopperBulletEnv", 4, 40, 1.3),
     "Walker2DPyBulletEnv-v0": ("gym_locomotion_envs", "Walker2DBulletEnv", 4, 40, 1.3),
     "HalfCheetahPyBulletEnv-v0": ("gym_locomotion_envs", "HalfCheetahBulletEnv", 4, 40, 1.3),

@@ -16,7 +16,7 @@ import os
 import sys
 import xml.etree.ElementTree as ET
 
-MODELS = ["inverted_pendulum", "inverted_double_pendulum", "hopper", "walker2d", "half_cheetah", "ant", "humanoid_symmetric"]
+MODELS = ["inverted_pendulum", "inverted_double_pendulum", "reacher", "hopper", "walker2d", "half_cheetah", "ant", "humanoid_symmetric"]
 
 KEEP = {
     "mujoco": ["model"],
