@@ -26,7 +26,8 @@ ENV_ID = "AntPyBulletEnv-v0"
 ALG = {
     "AntPyBulletEnv-v0": (461, 1.04e5), "HalfCheetahPyBulletEnv-v0": (373, 5.6e4), "HopperPyBulletEnv-v0": (229, 2.7e4),
     "Walker2DPyBulletEnv-v0": (325, 4.9e4), "HumanoidPyBulletEnv-v0": (849, 3.0e5),
-    "InvertedPendulumPyBulletEnv-v0": (109, 1.5e3),
+    "InvertedPendulumPyBulletEnv-v0": (109, 1.5e3), "HumanoidFlagrunHarderPyBulletEnv-v0": (849, 3.0e5),
+    "HumanoidFlagrunPyBulletEnv-v0": (849, 3.0e5),
 }
 
 
@@ -202,22 +203,28 @@ def run_ours(args):
     h_obs = torch.empty(E, D).pin_memory()
     h_rew = torch.empty(E).pin_memory()
     h_done = torch.empty(E, dtype=torch.uint8).pin_memory()
-    for i in range(5):
-        env.step_host(h_act[i % 8], h_obs, h_rew, h_done)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        env.step_host(h_act[i % 8], h_obs, h_rew, h_done)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    barrier()
+    def time_host_path(zero_copy):
+        env.set_zero_copy(zero_copy)
+        for i in range(5):
+            env.step_host(h_act[i % 8], h_obs, h_rew, h_done)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            env.step_host(h_act[i % 8], h_obs, h_rew, h_done)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        return dt, env.last_host_path()
+
+    t_staged, _ = time_host_path(False)           # H2D copy -> kernel -> D2H copies -> sync
+    t_e2e, host_path = time_host_path(True)       # default transport of pbg_step_host (zero-copy for pinned buffers)
 
     from pybullet_gym_b200 import sharding
 
     def maxr(x):
         return sharding.max_over_ranks(x, device=dev)
 
-    t_flushed, t_resident, t_e2e = maxr(t_flushed), maxr(t_resident), maxr(t_e2e)
+    t_flushed, t_resident, t_e2e, t_staged = maxr(t_flushed), maxr(t_resident), maxr(t_e2e), maxr(t_staged)
     stats = sharding.reduce_stats(env.stats(), device=dev)
     if rank == 0:
         peaks = {}
@@ -244,8 +251,8 @@ def run_ours(args):
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
             "value_l2_resident": world * E * K / t_resident,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": (1.56e6 if (args.env == ENV_ID and E == 4096) else None),
-                         "traffic_source": "dram__bytes_read+write per launch, ncu --set full, profiles/r01_ant_step_kernel_ncu.md",
+                         "traffic": (1.70e6 if (args.env == ENV_ID and E == 4096) else None),
+                         "traffic_source": "dram__bytes_read+write per launch, ncu --set full, profiles/r01b_ant_step_kernel_ncu.md",
                          "peak_source": peak_src,
                          "note": "latency/issue-bound FP32 small-matrix kernel: the HBM fraction is reported because the "
                                  "schema asks for it; the meaningful ceiling is fp32 below",
@@ -255,7 +262,9 @@ def run_ours(args):
                                   "alg_flops_per_env_step": alg_f, "alg_bytes_per_env_step": alg_b}},
             "e2e": {"value": world * E * Ke / t_e2e, "unit": UNIT, "h2d_bytes_per_step": E * nA * 4,
                     "d2h_bytes_per_step": E * (D + 1) * 4 + E, "steps": Ke,
-                    "path": "pbg_step_host: pinned host actions -> H2D -> step kernel -> D2H obs/reward/done -> sync"},
+                    "path": "pbg_step_host (%s): pinned host actions -> step kernel -> host obs/reward/done -> sync; "
+                            "zero-copy = the kernel reads / writes the mapped pinned buffers over PCIe itself" % host_path,
+                    "value_staged_copies": world * E * Ke / t_staged},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "episodes": {"finished": stats["episodes"], "mean_len": stats["length_sum"] / max(1, stats["episodes"]),

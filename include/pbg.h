@@ -159,6 +159,13 @@ int pbg_step(pbg_handle *h, const float *actions_dev, float *obs_dev, float *rew
  * steps, copies obs/reward/done D2H and synchronises.  Buffers should be pinned for full speed. */
 int pbg_step_host(pbg_handle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *done_host);
 
+/* pbg_step_host transport.  By default buffers that are pinned (cudaHostAlloc / cudaHostRegister; torch
+ * pin_memory()) are read and written by the step kernel directly through their UVA mapping ("zero-copy": no
+ * cudaMemcpy, one launch + one synchronise); pageable buffers, or enabled = 0, use staged H2D / D2H copies.
+ * pbg_last_host_path: 1 = zero-copy, 2 = staged copies, 0 = pbg_step_host not called yet. */
+int pbg_set_zero_copy(pbg_handle *h, int32_t enabled);
+int pbg_last_host_path(const pbg_handle *h);
+
 int pbg_set_auto_reset(pbg_handle *h, int32_t enabled);
 
 /* Canonical state access for parity tests (replaces getJointState / getBasePositionAndOrientation /

@@ -79,6 +79,8 @@ struct pbg_handle {
     unsigned long long seed = 0, env_offset = 0;
     int auto_reset = 1;
     int debug_env = 0;
+    int zero_copy = 1;          // pbg_step_host: let the kernel read / write mapped pinned host buffers directly
+    int last_host_path = 0;     // 1: zero-copy, 2: staged copies
     int64_t launches = 0;
     int64_t steps = 0;
     std::string err;
@@ -427,11 +429,41 @@ int pbg_step(pbg_handle *h, const float *actions_dev, float *obs_dev, float *rew
     return launch(h, MODE_STEP, b, 1, stream);
 }
 
+// device-visible alias of a pinned (cudaHostAlloc / cudaHostRegister, UVA-mapped) host buffer, or nullptr
+static void *mapped_alias(const void *p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+int pbg_set_zero_copy(pbg_handle *h, int32_t enabled) {
+    if (!h) return PBG_ERR_INVALID;
+    h->zero_copy = enabled ? 1 : 0;
+    return PBG_OK;
+}
+int pbg_last_host_path(const pbg_handle *h) { return h ? h->last_host_path : PBG_ERR_INVALID; }
+
 int pbg_step_host(pbg_handle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *done_host) {
     if (!h || !actions_host) return fail(h, PBG_ERR_INVALID, "pbg_step_host: actions_host is NULL");
     CUDA_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = h->hstream;
     const size_t E = h->E;
+    if (h->zero_copy) {
+        // Pinned host buffers are mapped into the device address space (UVA): the kernel reads the 32 B of actions per env
+        // over PCIe at its start and posts obs / reward / done straight into host memory at its end -- no copy
+        // engine round trips, one launch and one stream synchronisation per step.
+        void *da = mapped_alias(actions_host), *dobs = mapped_alias(obs_host), *drew = mapped_alias(reward_host),
+             *ddone = mapped_alias(done_host);
+        if (da && (dobs || !obs_host) && (drew || !reward_host) && (ddone || !done_host)) {
+            int rc = pbg_step(h, (const float *)da, (float *)dobs, (float *)drew, (uint8_t *)ddone, nullptr, nullptr, nullptr, s);
+            if (rc != PBG_OK) return rc;
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            h->last_host_path = 1;
+            return PBG_OK;
+        }
+    }
+    h->last_host_path = 2;
     CUDA_TRY(h, cudaMemcpyAsync(h->d_act, actions_host, E * h->k.nact * sizeof(float), cudaMemcpyHostToDevice, s));
     int rc = pbg_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, nullptr, nullptr, nullptr, s);
     if (rc != PBG_OK) return rc;

@@ -66,7 +66,8 @@ struct KCfg {
     static constexpr int sLIM = sCT + (MAXC > 0 ? MAXC : 1) * CTS;
     static constexpr int sCD = sLIM + 2 * (NLIM > 0 ? NLIM : 1);
     static constexpr int sMISC = sCD + (NSLOT > 0 ? NSLOT : 1);   // this step's feet flags
-    static constexpr int sU = (sMISC + 8 + 3) / 4 * 4;
+    static constexpr int sACTN = sMISC + 8;                        // this step's actions, read from global / mapped host memory once
+    static constexpr int sU = (sACTN + NACT + 3) / 4 * 4;
     static constexpr int sKIN = sU;
     static constexpr int sACC = sKIN + NB * KS;
     static constexpr int sSH = (sACC + NB * 17 + 3) / 4 * 4;
@@ -1236,6 +1237,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     // coalesced, vectorised state load
     for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
         reinterpret_cast<float4 *>(S)[i] = reinterpret_cast<const float4 *>(gs)[i];
+    // the actions may live in mapped pinned host memory (pbg_step_host zero-copy path): read them exactly once
+    const float *gact = B.actions ? B.actions + env * C::NACT : nullptr;
+    if (gl < C::NACT) e.sm[C::sACTN + gl] = gact ? gact[gl] : 0.f;
     __syncwarp();
     float *T = S + C::oT;
     const int mode = la.mode;
@@ -1281,7 +1285,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
         return;
     }
 
-    const float *act = B.actions ? B.actions + env * C::NACT : nullptr;
+    const float *act = gact ? e.sm + C::sACTN : nullptr;
     float *obs = B.obs ? B.obs + env * C::OBS : nullptr;
     // outputs are staged in shared memory, then written by consecutive lanes
     float *so = e.sm + C::sOUT;

@@ -138,6 +138,13 @@ class VectorEnv:
         if rc:
             _lib.check(rc, self._h)
 
+    def set_zero_copy(self, enabled: bool):
+        """pbg_step_host transport: kernel reads / writes pinned host buffers directly (default) or staged copies."""
+        _lib.check(self._L.pbg_set_zero_copy(self._h, int(enabled)), self._h)
+
+    def last_host_path(self) -> str:
+        return {0: "none", 1: "zero-copy", 2: "staged"}[self._L.pbg_last_host_path(self._h)]
+
     # ------------------------------------------------------------------ parity / diagnostics
     def get_state(self) -> torch.Tensor:
         s = torch.zeros(self.num_envs, self.state_dim, device=self.device)

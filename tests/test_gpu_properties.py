@@ -133,5 +133,19 @@ def test_step_host_round_trip():
     a = (torch.rand(256, 8) * 2 - 1).pin_memory()
     obs = torch.empty(256, 28).pin_memory(); rew = torch.empty(256).pin_memory(); done = torch.empty(256, dtype=torch.uint8).pin_memory()
     env.step_host(a, obs, rew, done)
+    assert env.last_host_path() == "zero-copy"            # pinned buffers: the kernel reads / writes them directly
     o2, r2, d2, _ = ref.step(a.cuda())
     assert torch.equal(obs, o2.cpu()) and torch.equal(rew, r2.cpu()) and torch.equal(done, d2.cpu())
+    # staged-copy transport (pageable buffers or zero-copy switched off) gives the same bytes
+    env.set_zero_copy(False)
+    a2 = (torch.rand(256, 8) * 2 - 1).pin_memory()
+    env.step_host(a2, obs, rew, done)
+    assert env.last_host_path() == "staged"
+    o3, r3, d3, _ = ref.step(a2.cuda())
+    assert torch.equal(obs, o3.cpu()) and torch.equal(rew, r3.cpu()) and torch.equal(done, d3.cpu())
+    env.set_zero_copy(True)
+    a3, obs_p, rew_p, done_p = torch.rand(256, 8) * 2 - 1, torch.empty(256, 28), torch.empty(256), torch.empty(256, dtype=torch.uint8)
+    env.step_host(a3, obs_p, rew_p, done_p)               # pageable buffers fall back to staged copies
+    assert env.last_host_path() == "staged"
+    o4, r4, d4, _ = ref.step(a3.cuda())
+    assert torch.equal(obs_p, o4.cpu()) and torch.equal(rew_p, r4.cpu()) and torch.equal(done_p, d4.cpu())
