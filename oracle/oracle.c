@@ -1044,12 +1044,19 @@ static double reacher_potential(const orc_env *e) { return -100.0 * v3norm(e->bo
 static void pendulum_calc_state(orc_env *e, double *obs) {
     /* rs/robot_pendula.py:27-51: slider = dof 0, hinge = dof 1 */
     double x = e->q[0], vx = e->qd[0], th = e->q[1], thd = e->qd[1];
-    if (e->m.kind == ORC_KIND_DOUBLE_PENDULUM) {
+    if (e->m.kind == ORC_KIND_DOUBLE_PENDULUM || e->m.kind == ORC_KIND_DOUBLE_PENDULUM_MJ) {
         /* InvertedDoublePendulum.calc_state (rs/robot_pendula.py:75-87): pole2 = last link, its COM is the
          * middle of the second pole (rs/gym_pendulum_envs.py:73-74) */
         fk(e);
         double ga = e->q[2], gad = e->qd[2];
         e->body_xyz[0] = e->c[e->m.nl - 1][0]; e->body_xyz[2] = e->c[e->m.nl - 1][2];
+        if (e->m.kind == ORC_KIND_DOUBLE_PENDULUM_MJ) {
+            /* pybulletgym/envs/mujoco/robot_pendula.py:73-88: [x, sin, sin, cos, cos, clip(qvel, +-10), qfrc_constraint = 0] */
+            double v[3] = {vx, thd, gad};
+            obs[0] = x; obs[1] = sin(th); obs[2] = sin(ga); obs[3] = cos(th); obs[4] = cos(ga);
+            for (int k = 0; k < 3; k++) { obs[5 + k] = v[k] < -10 ? -10 : (v[k] > 10 ? 10 : v[k]); obs[8 + k] = 0; }
+            return;
+        }
         obs[0] = x; obs[1] = vx; obs[2] = e->body_xyz[0]; obs[3] = cos(th); obs[4] = sin(th); obs[5] = thd;
         obs[6] = cos(ga); obs[7] = sin(ga); obs[8] = gad;
         return;
@@ -1088,10 +1095,12 @@ int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double
     } else if (!is_walker(m->kind)) {
         pendulum_calc_state(e, obs);
         double th = e->q[1];
-        if (m->kind == ORC_KIND_DOUBLE_PENDULUM) {
-            /* InvertedDoublePendulumBulletEnv._step (rs/gym_pendulum_envs.py:69-83) */
+        if (m->kind == ORC_KIND_DOUBLE_PENDULUM || m->kind == ORC_KIND_DOUBLE_PENDULUM_MJ) {
+            /* InvertedDoublePendulumBulletEnv._step (rs/gym_pendulum_envs.py:69-83); the MuJoCo-style variant
+             * (pybulletgym/envs/mujoco/gym_pendulum_envs.py:56-69) adds the velocity penalty */
             double px = e->body_xyz[0], py = e->body_xyz[2];
             t5[0] = 10.0; t5[1] = -(0.01 * px * px + (py + 0.3 - 2) * (py + 0.3 - 2)); t5[2] = -0.0;
+            if (m->kind == ORC_KIND_DOUBLE_PENDULUM_MJ) t5[2] = -(1e-3 * e->qd[1] * e->qd[1] + 5e-3 * e->qd[2] * e->qd[2]);
             done = py + 0.3 <= 1;
             *reward = t5[0] + t5[1] + t5[2];
         } else {
@@ -1146,7 +1155,7 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
         e->q[2] = noise[0]; e->q[3] = noise[1]; e->q[0] = noise[2]; e->q[1] = noise[3];
     } else {
         e->q[1] = noise[0] + (m->kind == ORC_KIND_PENDULUM_SWINGUP ? 3.1415 : 0.0);
-        if (m->kind == ORC_KIND_DOUBLE_PENDULUM) e->q[2] = noise[1];       /* rs/robot_pendula.py:66-68 */
+        if (m->kind == ORC_KIND_DOUBLE_PENDULUM || m->kind == ORC_KIND_DOUBLE_PENDULUM_MJ) e->q[2] = noise[1];       /* rs/robot_pendula.py:66-68 */
     }
     if (m->cube) {
         /* restoreState + resetBasePositionAndOrientation(cube, [-1.5,0,0.05], identity) (rs/robot_locomotors.py:240-243) */
@@ -1176,7 +1185,7 @@ void orc_reset_with(orc_env *e, const double *noise, int floor_in_parts, double 
 void orc_reset(orc_env *e, int floor_in_parts, double *obs) {
     double noise[MAXD];
     e->episode++;
-    int n = is_walker(e->m.kind) ? e->m.nact : (e->m.kind == ORC_KIND_DOUBLE_PENDULUM ? 2 : 1);
+    int n = is_walker(e->m.kind) ? e->m.nact : ((e->m.kind == ORC_KIND_DOUBLE_PENDULUM || e->m.kind == ORC_KIND_DOUBLE_PENDULUM_MJ) ? 2 : 1);
     for (int k = 0; k < n; k++) noise[k] = rng_uniform(e->seed, e->env_index, e->episode, (uint32_t)k, -0.1f, 0.1f);
     if (e->m.kind == ORC_KIND_REACHER)
         for (int k = 0; k < 4; k++) { float r = k < 2 ? 0.27f : 3.14f; noise[k] = rng_uniform(e->seed, e->env_index, e->episode, (uint32_t)k, -r, r); }

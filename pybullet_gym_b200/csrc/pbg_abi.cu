@@ -15,6 +15,7 @@ using namespace pbg;
 // 14 warps x 2 envs = 28 envs per CTA = one CTA per SM (7.2 KB shared memory per env): 148 CTAs hold 4144 envs.
 using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5, 4, 4>;
 using CfgDoublePendulum = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 9, 4, 4, 0, 2>;
+using CfgDoublePendulumMJ = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 11, 4, 4, 0, 2>;
 using CfgReacher = KCfg<4, 4, 0, 3, 0, 16, 0, 0, 0, 2, 9, 4, 4, 0, 4>;
 using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15, 14, 1>;
 using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1>;
@@ -54,6 +55,7 @@ static bool kernel_for_kind(int kind, KernelInfo *out) {
     switch (kind) {
     case PBG_KIND_PENDULUM: case PBG_KIND_PENDULUM_SWINGUP: *out = info_of<CfgPendulum>(); return true;
     case PBG_KIND_DOUBLE_PENDULUM: *out = info_of<CfgDoublePendulum>(); return true;
+    case PBG_KIND_DOUBLE_PENDULUM_MJ: *out = info_of<CfgDoublePendulumMJ>(); return true;
     case PBG_KIND_REACHER: *out = info_of<CfgReacher>(); return true;
     case PBG_KIND_HOPPER: *out = info_of<CfgHopper>(); return true;
     case PBG_KIND_WALKER2D: *out = info_of<CfgWalker>(); return true;

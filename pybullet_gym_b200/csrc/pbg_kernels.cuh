@@ -1079,7 +1079,7 @@ struct Env {
         const float xx = S[C::oQ], th = S[C::oQ + 1], vx = S[C::oU], thd = S[C::oU + 1];
         float s, c;
         sincosf(th, &s, &c);
-        if (m->kind == 9) {
+        if (m->kind == 9 || m->kind == 11) {
             // InvertedDoublePendulum (rs/robot_pendula.py:57-87, rs/gym_pendulum_envs.py:50-83): pole2's link COM is
             // the middle of the second pole; reward = 10 - 0.01 x^2 - (y + 0.3 - 2)^2, done when y + 0.3 <= 1
             fk(false);
@@ -1089,6 +1089,23 @@ struct Env {
             float s2, c2;
             sincosf(ga, &s2, &c2);
             const float dist = 0.01f * px * px + (py + 0.3f - 2.f) * (py + 0.3f - 2.f);
+            if (m->kind == 11) {
+                // MuJoCo-style variant (pybulletgym/envs/mujoco/robot_pendula.py:73-88, gym_pendulum_envs.py:56-69):
+                // [x, sin, sin, cos, cos, clip(qvel, +-10), qfrc_constraint = 0], velocity penalty in the reward
+                const float velp = 1e-3f * thd * thd + 5e-3f * gad * gad;
+                if (gl == 0 && pred) {
+                    if (obs_out) {
+                        obs_out[0] = xx; obs_out[1] = s; obs_out[2] = s2; obs_out[3] = c; obs_out[4] = c2;
+                        obs_out[5] = fminf(fmaxf(vx, -10.f), 10.f); obs_out[6] = fminf(fmaxf(thd, -10.f), 10.f);
+                        obs_out[7] = fminf(fmaxf(gad, -10.f), 10.f); obs_out[8] = 0.f; obs_out[9] = 0.f; obs_out[10] = 0.f;
+                    }
+                    if (!reset_pass) {
+                        if (rew_out) *rew_out = 10.f - dist - velp;
+                        if (terms_out) { terms_out[0] = 10.f; terms_out[1] = -dist; terms_out[2] = -velp; terms_out[3] = 0.f; terms_out[4] = 0.f; }
+                    }
+                }
+                return !reset_pass && py + 0.3f <= 1.f;
+            }
             if (gl == 0 && pred) {
                 if (obs_out) {
                     obs_out[0] = xx; obs_out[1] = vx; obs_out[2] = px; obs_out[3] = c; obs_out[4] = s; obs_out[5] = thd;
@@ -1151,7 +1168,7 @@ struct Env {
     // while only some of its env groups need it (no divergent __syncwarp / shuffles).
     __device__ bool task(const float *act, float *obs_out, float *rew_out, float *terms_out, bool reset_pass,
                          bool pred = true) {
-        if (m->kind <= 1 || m->kind == 9) return pendulum_task(obs_out, rew_out, terms_out, reset_pass, pred);
+        if (m->kind <= 1 || m->kind == 9 || m->kind == 11) return pendulum_task(obs_out, rew_out, terms_out, reset_pass, pred);
         if (m->kind == 10) return reacher_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
         return walker_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
     }
@@ -1184,7 +1201,7 @@ struct Env {
                 const float rr = m->kind == 10 ? (gl < 2 ? 0.27f : 3.14f) : 0.1f;
                 const float nz = noise ? noise[gl] : rng_uniform(la.seed, env, ep, 0u, (unsigned)gl, -rr, rr);
                 if (m->kind <= 1) { if (gl == 0) S[C::oQ + 1] = nz + (m->kind == 1 ? 3.1415f : 0.f); }
-                else if (m->kind == 9) S[C::oQ + 1 + gl] = nz;          // hinge, hinge2 (rs/robot_pendula.py:66-68)
+                else if (m->kind == 9 || m->kind == 11) S[C::oQ + 1 + gl] = nz;   // hinge, hinge2 (rs/robot_pendula.py:66-68)
                 else if (m->kind == 10) S[C::oQ + (gl ^ 2)] = nz;        // draws: target_x, target_y, joint0, joint1 -> dofs 2, 3, 0, 1
                 else S[C::oQ + m->act_joint[gl]] = nz;
             }

@@ -27,14 +27,16 @@ def make(id, **kwargs):
     if id not in registry:
         raise KeyError("No registered env with id: %s" % id)
     from .roboschool import envs as _envs
+    from .mujoco import envs as _mj_envs
     from .time_limit import TimeLimit
-    cls = _envs.ENTRY_POINTS[id]
+    cls = _envs.ENTRY_POINTS[id] if id in _envs.ENTRY_POINTS else _mj_envs.ENTRY_POINTS[id]
     env = cls(**kwargs)
     return TimeLimit(env, max_episode_steps=registry[id]["max_episode_steps"])
 
 
 for _s in SPECS.values():
-    register(_s.id, "pybullet_gym_b200.envs.roboschool.envs:" + _s.entry_point.split(":")[1], _s.max_episode_steps,
+    register(_s.id, "pybullet_gym_b200.envs.%s.envs:" % ("mujoco" if ".mujoco." in _s.entry_point else "roboschool")
+             + _s.entry_point.split(":")[1], _s.max_episode_steps,
              _s.reward_threshold)
 
 

@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 KIND_PENDULUM, KIND_PENDULUM_SWINGUP, KIND_HOPPER, KIND_WALKER2D, KIND_HALFCHEETAH, KIND_ANT, KIND_HUMANOID, \
-    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM, KIND_REACHER = range(11)
+    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM, KIND_REACHER, KIND_DOUBLE_PENDULUM_MJ = range(12)
 
 
 @dataclass(frozen=True)
@@ -100,7 +100,7 @@ class EnvSpec:
         """Reset draws per episode that the caller may inject (pbg_reset_with): one per actuated joint for the
         walkers (robot_locomotors.py:18-19), the hinge for the pendulum (robot_pendula.py:16), both hinges for the
         double pendulum (robot_pendula.py:66-68)."""
-        if self.kind == KIND_DOUBLE_PENDULUM:
+        if self.kind in (KIND_DOUBLE_PENDULUM, KIND_DOUBLE_PENDULUM_MJ):
             return 2
         if self.kind == KIND_REACHER:
             return 4            # target_x, target_y, joint0, joint1 (robot_manipulators.py:12-21)
@@ -118,8 +118,8 @@ class EnvSpec:
         if self.kind in (KIND_PENDULUM, KIND_PENDULUM_SWINGUP):
             # robot_pendula.py:25: only the slider is driven, 100 * clip(a)
             return [100.0 if n == "slider" else 0.0 for n in ordered_joint_names]
-        if self.kind == KIND_DOUBLE_PENDULUM:
-            # robot_pendula.py:73: 200 * clip(a) on the slider
+        if self.kind in (KIND_DOUBLE_PENDULUM, KIND_DOUBLE_PENDULUM_MJ):
+            # robot_pendula.py:73 (roboschool and mujoco variants alike): 200 * clip(a) on the slider
             return [200.0 if n == "slider" else 0.0 for n in ordered_joint_names]
         if self.kind == KIND_REACHER:
             # robot_manipulators.py:23-26: 0.05 * clip(a) on the two arm hinges
@@ -147,6 +147,10 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
     EnvSpec("InvertedDoublePendulumPyBulletEnv-v0", KIND_DOUBLE_PENDULUM, "inverted_double_pendulum.xml", "cart", 1, 9,
             1.0, scene=_PENDULUM_SCENE, reward_threshold=9100.0,
             entry_point=_RS + "gym_pendulum_envs:InvertedDoublePendulumBulletEnv"),
+    # MuJoCo-style variant (pybulletgym/envs/mujoco/): same physics, gym-mujoco observation / reward layout
+    EnvSpec("InvertedDoublePendulumMuJoCoEnv-v0", KIND_DOUBLE_PENDULUM_MJ, "inverted_double_pendulum.xml", "cart", 1, 11,
+            1.0, scene=_PENDULUM_SCENE, reward_threshold=9100.0,
+            entry_point="pybulletgym.envs.mujoco.gym_pendulum_envs:InvertedDoublePendulumMuJoCoEnv"),
     EnvSpec("ReacherPyBulletEnv-v0", KIND_REACHER, "reacher.xml", "body0", 2, 9, 1.0,
             scene=SceneSpec(gravity=0.0, timestep=0.0165, frame_skip=1), max_episode_steps=150, reward_threshold=18.0,
             aux_links=("fingertip", "target"), entry_point=_RS + "gym_manipulator_envs:ReacherBulletEnv"),
@@ -181,6 +185,6 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
 UNBACKED_IDS = (
     "PusherPyBulletEnv-v0",
     "ThrowerPyBulletEnv-v0", "StrikerPyBulletEnv-v0", "AtlasPyBulletEnv-v0",
-    "InvertedPendulumMuJoCoEnv-v0", "InvertedDoublePendulumMuJoCoEnv-v0", "Walker2DMuJoCoEnv-v0",
+    "InvertedPendulumMuJoCoEnv-v0", "Walker2DMuJoCoEnv-v0",
     "HalfCheetahMuJoCoEnv-v0", "AntMuJoCoEnv-v0", "HopperMuJoCoEnv-v0", "HumanoidMuJoCoEnv-v0",
 )

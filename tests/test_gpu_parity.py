@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 
 IDS = ["InvertedPendulumPyBulletEnv-v0", "InvertedDoublePendulumPyBulletEnv-v0", "ReacherPyBulletEnv-v0", "HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
        "AntPyBulletEnv-v0", "HumanoidPyBulletEnv-v0"]
-TASK_IDS = IDS + ["HumanoidFlagrunPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0"]
+TASK_IDS = IDS + ["HumanoidFlagrunPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0", "InvertedDoublePendulumMuJoCoEnv-v0"]
 E = 48
 
 

@@ -33,6 +33,7 @@ CASES = {
     "InvertedPendulumPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedPendulumBulletEnv", 3, 40, 1.0),
     "InvertedPendulumSwingupPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedPendulumSwingupBulletEnv", 2, 40, 1.0),
     "InvertedDoublePendulumPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedDoublePendulumBulletEnv", 3, 60, 0.3),
+    "InvertedDoublePendulumMuJoCoEnv-v0": ("mujoco.gym_pendulum_envs", "InvertedDoublePendulumMuJoCoEnv", 3, 60, 0.3),
     "ReacherPyBulletEnv-v0": ("gym_manipulator_envs", "ReacherBulletEnv", 3, 60, 1.3),
     "HopperPyBulletEnv-v0": ("gym_locomotion_envs", "HopperBulletEnv", 4, 40, 1.3),
     "Walker2DPyBulletEnv-v0": ("gym_locomotion_envs", "Walker2DBulletEnv", 4, 40, 1.3),
@@ -60,7 +61,7 @@ def main():
         spec = SPECS[env_id]
         fp.FakeBulletClient.current_spec = spec
         fp.FakeBulletClient.max_contacts = 0
-        m = importlib.import_module("pybulletgym.envs.roboschool." + mod)
+        m = importlib.import_module("pybulletgym.envs." + (mod if "." in mod else "roboschool." + mod))
         import io
         import contextlib
         with contextlib.redirect_stdout(io.StringIO()):     # the reference prints "WalkerBase::__init__"
@@ -110,7 +111,8 @@ def main():
                "episodes": eps}
         if held:
             out["held"] = True
-        path = os.path.join(OUT, "task_%s%s.json" % (env_id.split("PyBullet")[0], "Held" if held else ""))
+        stem = env_id.split("PyBullet")[0] if "PyBullet" in env_id else env_id.split("Env-")[0]
+        path = os.path.join(OUT, "task_%s%s.json" % (stem, "Held" if held else ""))
         with open(path, "w") as f:
             json.dump(out, f)
         nsteps = sum(len(e["steps"]) for e in eps)
