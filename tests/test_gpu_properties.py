@@ -149,3 +149,19 @@ def test_step_host_round_trip():
     assert env.last_host_path() == "staged"
     o4, r4, d4, _ = ref.step(a3.cuda())
     assert torch.equal(obs_p, o4.cpu()) and torch.equal(rew_p, r4.cpu()) and torch.equal(done_p, d4.cpu())
+
+
+@pytest.mark.parametrize("n", [1, 2, 27, 29, 57])
+def test_ragged_batch_sizes_match_the_big_batch(n):
+    """Batch sizes that leave warps / CTAs partly empty (1 env, odd counts, one more than a CTA's 28 envs) step
+    exactly like the first n envs of a large batch."""
+    big = _mk("AntPyBulletEnv-v0", 256, seed=11, auto_reset=True)
+    small = _mk("AntPyBulletEnv-v0", n, seed=11, auto_reset=True)
+    big.reset(); small.reset()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(25):
+        a = torch.rand(256, 8, device="cuda", generator=gen) * 2 - 1
+        ob, rb, db, _ = big.step(a)
+        os_, rs, ds, _ = small.step(a[:n].contiguous())
+        assert torch.equal(ob[:n], os_) and torch.equal(rb[:n], rs) and torch.equal(db[:n], ds)
+    assert small.stats()["steps"] == 25 * n
