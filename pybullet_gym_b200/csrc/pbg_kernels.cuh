@@ -424,6 +424,140 @@ struct Env {
         return g;
     }
 
+    // ---------------------------------------------------------------- constraint rows
+    // lane = row (slot s holds row s * LPE + lane): Jacobian J, Y = L^-1 J^T, right-hand side and bounds.
+    // NS = number of register slots built; for NS = 2 the two rows' chains are interleaved statement by statement.
+    template <int NS>
+    __device__ __forceinline__ void build_rows(const V3 xref, const float h, float (&rhs)[2], float (&dinv)[2], float (&lo)[2],
+                                               float (&hi)[2], float (&lmb)[2], float (&mu)[2], float (&Yr)[2][C::ND]) {
+        const float *S = st();
+        const float *u = uvec();
+        const float *lim = sm + C::sLIM;
+        const float *SH = sm + C::sSH;
+        const float *Lm = sm + C::sL, *inv = sm + C::sINV;
+        float *Ym = sm + C::sY, *lam = sm + C::sLAM;
+        const float *warm = S + C::oW;
+        const int nr = nl + 3 * nc;
+        float J[NS][C::ND], pen[NS];
+        int kind[NS], slot[NS];
+        V3 d[NS], pA[NS], pB[NS], pAx[NS], pBx[NS];
+        unsigned ma[NS], mb[NS];
+        int ldof[NS]; float ldir[NS];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            rhs[sl] = 0.f; dinv[sl] = 0.f; lo[sl] = 0.f; hi[sl] = 0.f; lmb[sl] = 0.f; mu[sl] = 0.f;
+#pragma unroll
+            for (int k = 0; k < C::ND; ++k) Yr[sl][k] = 0.f;
+        }
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) {
+            const int i = sl * C::LPE + gl;
+            pen[sl] = 0.f; kind[sl] = -1; slot[sl] = 0; ma[sl] = 0u; mb[sl] = 0u; ldof[sl] = -1; ldir[sl] = 0.f;
+            d[sl] = pA[sl] = pB[sl] = pAx[sl] = pBx[sl] = mk(0.f, 0.f, 0.f);
+            if (i < nl) {
+                kind[sl] = 0;
+                const int code = __float_as_int(lim[2 * i]);
+                ldof[sl] = code & 0xff;
+                ldir[sl] = (code >> 8) ? -1.f : 1.f;
+                pen[sl] = lim[2 * i + 1];
+            } else if (i < nr) {
+                const int ci = i - nl;
+                int c;
+                const float *ct;
+                if (ci < nc) { kind[sl] = 1; c = ci; ct = sm + C::sCT + c * C::CTS; d[sl] = ld3(ct + 10); }
+                else {
+                    kind[sl] = 2; c = (ci - nc) >> 1; ct = sm + C::sCT + c * C::CTS;
+                    const V3 n = ld3(ct + 10);
+                    V3 t1, t2;   // btPlaneSpace1
+                    if (fabsf(n.z) > 0.70710678f) {
+                        const float aa = n.y * n.y + n.z * n.z, k = rsqrtf(aa);
+                        t1 = mk(0.f, -n.z * k, n.y * k); t2 = mk(aa * k, -n.x * t1.z, n.x * t1.y);
+                    } else {
+                        const float aa = n.x * n.x + n.y * n.y, k = rsqrtf(aa);
+                        t1 = mk(-n.y * k, n.x * k, 0.f); t2 = mk(-n.z * t1.y, n.z * t1.x, aa * k);
+                    }
+                    d[sl] = ((ci - nc) & 1) ? t2 : t1;
+                }
+                const int ba = __float_as_int(ct[0]), bb = __float_as_int(ct[1]);
+                slot[sl] = __float_as_int(ct[2]);
+                pen[sl] = ct[13] + m->slop;
+                mu[sl] = ct[14];
+                pA[sl] = ld3(ct + 4); pB[sl] = ld3(ct + 7);
+                ma[sl] = m->anc[ba]; mb[sl] = bb >= 0 ? m->anc[bb] : 0u;
+                pAx[sl] = pA[sl]; pBx[sl] = pB[sl];     // the same points seen from the cube's centre
+                if (C::HASX) { const V3 rc = ld3(kin(C::NB - 1) + 9) - xref; pAx[sl] = pA[sl] - rc; pBx[sl] = pB[sl] - rc; }
+            }
+        }
+        // Jacobian entries, one S_k load for all slots
+#pragma unroll
+        for (int k = 0; k < C::ND; ++k) {
+            const V3 so = ld3(SH + k * 12), sv = ld3(SH + k * 12 + 3);
+            const bool xk = C::HASX && k >= C::XD0;
+#pragma unroll
+            for (int sl = 0; sl < NS; ++sl) {
+                float val = 0.f;
+                if ((ma[sl] >> k) & 1u) val += dot(d[sl], sv + cross(so, xk ? pAx[sl] : pA[sl]));
+                if (C::NPAIR > 0) { if ((mb[sl] >> k) & 1u) val -= dot(d[sl], sv + cross(so, xk ? pBx[sl] : pB[sl])); }
+                if (kind[sl] == 0) val = (k == ldof[sl]) ? ldir[sl] : 0.f;
+                J[sl][k] = val;
+            }
+        }
+        float rel[NS];
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) rel[sl] = 0.f;
+#pragma unroll
+        for (int k = 0; k < C::ND; ++k) {
+            const float uk = u[k];
+#pragma unroll
+            for (int sl = 0; sl < NS; ++sl) rel[sl] += J[sl][k] * uk;
+        }
+        // forward substitution Y = L^-1 J^T, one L load for all slots
+#pragma unroll
+        for (int k = 0; k < C::ND; ++k) {
+            float sacc[NS];
+#pragma unroll
+            for (int sl = 0; sl < NS; ++sl) sacc[sl] = J[sl][k];
+#pragma unroll
+            for (int mm = 0; mm < k; ++mm) {
+                const float lkm = Lm[k * C::LST + mm];
+#pragma unroll
+                for (int sl = 0; sl < NS; ++sl) sacc[sl] -= lkm * J[sl][mm];
+            }
+            const float ik = inv[k];
+#pragma unroll
+            for (int sl = 0; sl < NS; ++sl) J[sl][k] = sacc[sl] * ik;
+        }
+        const float ih = 1.f / h;
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) {
+            const int i = sl * C::LPE + gl;
+            float dd = 0.f;
+#pragma unroll
+            for (int k = 0; k < C::ND; ++k) { dd += J[sl][k] * J[sl][k]; Yr[sl][k] = J[sl][k]; }
+            const float di = dd > 1e-12f ? 1.f / dd : 0.f;
+            dinv[sl] = di;
+            if (kind[sl] == 0) {
+                float poserr = -pen[sl] * m->erp_limit * ih;
+                if (m->limit_split && !(pen[sl] > m->split_thr)) poserr = 0.f;
+                rhs[sl] = (poserr - rel[sl]) * di; lo[sl] = 0.f; hi[sl] = m->limit_max_imp;
+            } else if (kind[sl] == 1) {
+                float poserr = 0.f, velerr = -rel[sl];
+                if (pen[sl] > 0.f) velerr -= pen[sl] * ih; else poserr = -pen[sl] * m->erp_contact * ih;
+                rhs[sl] = (poserr + velerr) * di; lo[sl] = 0.f; hi[sl] = 1e10f;
+                lmb[sl] = warm[slot[sl]] * m->warm;
+            } else if (kind[sl] == 2) {
+                rhs[sl] = -rel[sl] * di;
+            } else {
+                dinv[sl] = 0.f;
+            }
+            if (i < C::MAXR) {
+#pragma unroll
+                for (int k = 0; k < C::ND; ++k) Ym[i * C::LST + k] = J[sl][k];
+                lam[i] = lmb[sl];
+            }
+        }
+    }
+
     // ---------------------------------------------------------------- dynamics of one substep
     __device__ void substep(bool last) {
         const float h = m->h;
@@ -618,99 +752,10 @@ struct Env {
         float *lam = sm + C::sLAM;
         float *warm = S + C::oW;
         float rhs[2], dinv[2], lo[2], hi[2], lmb[2], mu[2], Yr[2][C::ND];
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-            rhs[sl] = 0.f; dinv[sl] = 0.f; lo[sl] = 0.f; hi[sl] = 0.f; lmb[sl] = 0.f; mu[sl] = 0.f;
-#pragma unroll
-            for (int k = 0; k < C::ND; ++k) Yr[sl][k] = 0.f;
-            if (sl * C::LPE >= nrmax) continue;
-            const int i = sl * C::LPE + gl;
-            float J[C::ND];
-#pragma unroll
-            for (int k = 0; k < C::ND; ++k) J[k] = 0.f;
-            float pen = 0.f; int kind = -1;     // 0 limit, 1 normal, 2 friction
-            int slot = 0;
-            if (i < nl) {
-                kind = 0;
-                const int code = __float_as_int(lim[2 * i]);
-                const int d = code & 0xff;
-                const float dir = (code >> 8) ? -1.f : 1.f;
-                pen = lim[2 * i + 1];
-#pragma unroll
-                for (int k = 0; k < C::ND; ++k) J[k] = (k == d) ? dir : 0.f;
-            } else if (i < nr) {
-                const int ci = i - nl;
-                int c; V3 d;
-                const float *ct;
-                if (ci < nc) { kind = 1; c = ci; ct = sm + C::sCT + c * C::CTS; d = ld3(ct + 10); }
-                else {
-                    kind = 2; c = (ci - nc) >> 1; ct = sm + C::sCT + c * C::CTS;
-                    const V3 n = ld3(ct + 10);
-                    V3 t1, t2;   // btPlaneSpace1
-                    if (fabsf(n.z) > 0.70710678f) {
-                        const float aa = n.y * n.y + n.z * n.z, k = rsqrtf(aa);
-                        t1 = mk(0.f, -n.z * k, n.y * k); t2 = mk(aa * k, -n.x * t1.z, n.x * t1.y);
-                    } else {
-                        const float aa = n.x * n.x + n.y * n.y, k = rsqrtf(aa);
-                        t1 = mk(-n.y * k, n.x * k, 0.f); t2 = mk(-n.z * t1.y, n.z * t1.x, aa * k);
-                    }
-                    d = ((ci - nc) & 1) ? t2 : t1;
-                }
-                const int ba = __float_as_int(ct[0]), bb = __float_as_int(ct[1]);
-                slot = __float_as_int(ct[2]);
-                pen = ct[13] + m->slop;
-                mu[sl] = ct[14];
-                const V3 pA = ld3(ct + 4), pB = ld3(ct + 7);
-                const unsigned ma = m->anc[ba], mb = bb >= 0 ? m->anc[bb] : 0u;
-                V3 pAx = pA, pBx = pB;               // the same points seen from the cube's centre
-                if (C::HASX) { const V3 rc = ld3(kin(C::NB - 1) + 9) - xref; pAx = pA - rc; pBx = pB - rc; }
-#pragma unroll
-                for (int k = 0; k < C::ND; ++k) {
-                    const V3 so = ld3(SH + k * 12), sv = ld3(SH + k * 12 + 3);
-                    const bool xk = C::HASX && k >= C::XD0;
-                    float val = 0.f;
-                    if ((ma >> k) & 1u) val += dot(d, sv + cross(so, xk ? pAx : pA));
-                    if (C::NPAIR > 0) { if ((mb >> k) & 1u) val -= dot(d, sv + cross(so, xk ? pBx : pB)); }
-                    J[k] = val;
-                }
-            }
-            float rel = 0.f;
-#pragma unroll
-            for (int k = 0; k < C::ND; ++k) rel += J[k] * u[k];
-            // forward substitution Y = L^-1 J^T
-#pragma unroll
-            for (int k = 0; k < C::ND; ++k) {
-                float sacc = J[k];
-#pragma unroll
-                for (int mm = 0; mm < k; ++mm) sacc -= Lm[k * C::LST + mm] * J[mm];
-                J[k] = sacc * inv[k];
-            }
-            float dd = 0.f;
-#pragma unroll
-            for (int k = 0; k < C::ND; ++k) { dd += J[k] * J[k]; Yr[sl][k] = J[k]; }
-            const float di = dd > 1e-12f ? 1.f / dd : 0.f;
-            dinv[sl] = di;
-            const float ih = 1.f / h;
-            if (kind == 0) {
-                float poserr = -pen * m->erp_limit * ih;
-                if (m->limit_split && !(pen > m->split_thr)) poserr = 0.f;
-                rhs[sl] = (poserr - rel) * di; lo[sl] = 0.f; hi[sl] = m->limit_max_imp;
-            } else if (kind == 1) {
-                float poserr = 0.f, velerr = -rel;
-                if (pen > 0.f) velerr -= pen * ih; else poserr = -pen * m->erp_contact * ih;
-                rhs[sl] = (poserr + velerr) * di; lo[sl] = 0.f; hi[sl] = 1e10f;
-                lmb[sl] = warm[slot] * m->warm;
-            } else if (kind == 2) {
-                rhs[sl] = -rel * di;
-            } else {
-                dinv[sl] = 0.f;
-            }
-            if (i < C::MAXR) {
-#pragma unroll
-                for (int k = 0; k < C::ND; ++k) Ym[i * C::LST + k] = J[k];
-                lam[i] = lmb[sl];
-            }
-        }
+        // One register slot in the common case.  When a warp needs the second slot (an env with more than LPE
+        // rows) both slots are built in ONE pass with their dependent chains interleaved and the S / L loads shared.
+        if (nrmax <= C::LPE) build_rows<1>(xref, h, rhs, dinv, lo, hi, lmb, mu, Yr);
+        else build_rows<2>(xref, h, rhs, dinv, lo, hi, lmb, mu, Yr);
         __syncwarp();
 
         // --- Delassus matrix A = Y Y^T and warm-started residual r = A lambda0
