@@ -1041,6 +1041,16 @@ static void reacher_calc_state(orc_env *e, double *obs) {
 }
 static double reacher_potential(const orc_env *e) { return -100.0 * v3norm(e->body_xyz); }
 
+/* MuJoCo-style Hopper / Walker2D (pybulletgym/envs/mujoco/robot_locomotors.py:86-165): qpos[1:] ++ clip(qvel, +-10) over
+ * all dofs (root joints included), float32 storage */
+static int is_mjwalker(int kind) { return kind == ORC_KIND_HOPPER_MJ || kind == ORC_KIND_WALKER2D_MJ; }
+static void mjwalker_calc_state(orc_env *e, double *obs) {
+    int nd = e->nd, o = 0;
+    for (int k = 1; k < nd; k++) obs[o++] = (double)(float)e->q[k];
+    for (int k = 0; k < nd; k++) { float v = (float)e->qd[k]; v = v < -10.f ? -10.f : (v > 10.f ? 10.f : v); obs[o++] = v; }
+}
+static double mjwalker_body_x(orc_env *e) { fk(e); return e->c[e->m.torso_link][0]; }   /* robot_body.get_pose()[0] */
+
 static void pendulum_calc_state(orc_env *e, double *obs) {
     /* rs/robot_pendula.py:27-51: slider = dof 0, hinge = dof 1 */
     double x = e->q[0], vx = e->qd[0], th = e->q[1], thd = e->qd[1];
@@ -1082,7 +1092,24 @@ int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double
     const orc_model *m = &e->m;
     double t5[5] = {0, 0, 0, 0, 0};
     int done = 0;
-    if (m->kind == ORC_KIND_REACHER) {
+    if (is_mjwalker(m->kind)) {
+        /* HopperMuJoCoEnv._step / Walker2DMuJoCoEnv._step (pybulletgym/envs/mujoco/gym_locomotion_envs.py:121-206) */
+        double x = mjwalker_body_x(e);
+        t5[0] = (x - e->potential) / m->dt_scene;          /* calc_potential(): (pos_after - pos_before) / dt */
+        e->potential = x;
+        t5[1] = 1.0;
+        double ss = 0; for (int n = 0; n < m->nact; n++) ss += a[n] * a[n];
+        t5[2] = -1e-3 * ss;
+        mjwalker_calc_state(e, obs);
+        double height = obs[0], ang = obs[1];
+        int ok = 1;
+        for (int k = 0; k < m->obs_dim; k++) if (!isfinite(obs[k])) ok = 0;
+        for (int k = 2; k < m->obs_dim; k++) if (!(fabs(obs[k]) < 100)) ok = 0;
+        if (m->kind == ORC_KIND_HOPPER_MJ) ok = ok && height > -0.3 && fabs(ang) < 0.2;
+        else ok = ok && 1.0 > height && height > -0.2 && -1.0 < ang && ang < 1.0;
+        done = !ok;
+        *reward = t5[0] + t5[1] + t5[2];
+    } else if (m->kind == ORC_KIND_REACHER) {
         /* ReacherBulletEnv._step (rs/gym_manipulator_envs.py:15-32): never done */
         reacher_calc_state(e, obs);
         double pold = e->potential;
@@ -1150,6 +1177,8 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
     }
     if (is_walker(m->kind)) {
         for (int n = 0; n < m->nact; n++) e->q[e->dof_of_link[m->act_link[n]]] = noise[n];
+    } else if (is_mjwalker(m->kind)) {
+        for (int n = 0; n < e->nd; n++) e->q[n] = noise[n];       /* every ordered joint, root joints included */
     } else if (m->kind == ORC_KIND_REACHER) {
         /* rs/robot_manipulators.py:12-21: target_x, target_y, joint0, joint1 in this draw order */
         e->q[2] = noise[0]; e->q[3] = noise[1]; e->q[0] = noise[2]; e->q[1] = noise[3];
@@ -1171,6 +1200,7 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
     if (is_flagrun(m->kind)) flag_reposition(e);
     if (is_walker(m->kind)) { walker_calc_state(e, obs); e->potential = calc_potential(e); }
     else if (m->kind == ORC_KIND_REACHER) { reacher_calc_state(e, obs); e->potential = reacher_potential(e); }
+    else if (is_mjwalker(m->kind)) { mjwalker_calc_state(e, obs); e->potential = mjwalker_body_x(e); }
     else pendulum_calc_state(e, obs);
     /* quirk Q1: the env adds the floor to robot.parts right after this first calc_state
      * (rs/gym_locomotion_envs.py:30-31), so every later calc_state of the episode averages it in */
@@ -1187,6 +1217,8 @@ void orc_reset(orc_env *e, int floor_in_parts, double *obs) {
     e->episode++;
     int n = is_walker(e->m.kind) ? e->m.nact : ((e->m.kind == ORC_KIND_DOUBLE_PENDULUM || e->m.kind == ORC_KIND_DOUBLE_PENDULUM_MJ) ? 2 : 1);
     for (int k = 0; k < n; k++) noise[k] = rng_uniform(e->seed, e->env_index, e->episode, (uint32_t)k, -0.1f, 0.1f);
+    if (is_mjwalker(e->m.kind))
+        for (int k = 0; k < e->nd; k++) noise[k] = rng_uniform(e->seed, e->env_index, e->episode, (uint32_t)k, -0.1f, 0.1f);
     if (e->m.kind == ORC_KIND_REACHER)
         for (int k = 0; k < 4; k++) { float r = k < 2 ? 0.27f : 3.14f; noise[k] = rng_uniform(e->seed, e->env_index, e->episode, (uint32_t)k, -r, r); }
     reset_common(e, noise, floor_in_parts, obs);

@@ -18,6 +18,8 @@ using CfgDoublePendulum = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 9, 4, 4, 0, 2>;
 using CfgDoublePendulumMJ = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 11, 4, 4, 0, 2>;
 using CfgReacher = KCfg<4, 4, 0, 3, 0, 16, 0, 0, 0, 2, 9, 4, 4, 0, 4>;
 using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15, 14, 1>;
+using CfgHopperMJ = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 11, 14, 1, 0, 6>;
+using CfgWalkerMJ = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 17, 14, 1, 0, 9>;
 using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1>;
 using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1>;
 #ifndef PBG_ANT_WARPS
@@ -59,6 +61,8 @@ static bool kernel_for_kind(int kind, KernelInfo *out) {
     case PBG_KIND_REACHER: *out = info_of<CfgReacher>(); return true;
     case PBG_KIND_HOPPER: *out = info_of<CfgHopper>(); return true;
     case PBG_KIND_WALKER2D: *out = info_of<CfgWalker>(); return true;
+    case PBG_KIND_HOPPER_MJ: *out = info_of<CfgHopperMJ>(); return true;
+    case PBG_KIND_WALKER2D_MJ: *out = info_of<CfgWalkerMJ>(); return true;
     case PBG_KIND_HALFCHEETAH: *out = info_of<CfgCheetah>(); return true;
     case PBG_KIND_ANT: *out = info_of<CfgAnt>(); return true;
     case PBG_KIND_HUMANOID: case PBG_KIND_FLAGRUN: *out = info_of<CfgHumanoid>(); return true;

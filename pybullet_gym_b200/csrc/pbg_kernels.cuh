@@ -1174,6 +1174,45 @@ struct Env {
         return !reset_pass && m->kind == 0 && fabsf(th) > 0.2f;
     }
 
+    // MuJoCo-style Hopper / Walker2D (pybulletgym/envs/mujoco/robot_locomotors.py:86-165, gym_locomotion_envs.py:121-206):
+    // obs = qpos[1:] ++ clip(qvel, +-10) over all dofs (root joints included); reward = [dx / dt, 1, -1e-3 |a|^2].
+    __device__ bool mjwalker_task(const float *act, float *obs_out, float *rew_out, float *terms_out, bool reset_pass, bool pred) {
+        float *S = st();
+        float *T = S + C::oT;
+        fk(false);
+        const float *kt = kin(m->torso_body);
+        const float x = kt[9] + mulR(kt, ld3(m->torso_off)).x;       // robot_body.get_pose()[0]: torso link COM
+        const float q = gl < C::NJ ? S[C::oQ + gl] : 0.f;
+        const float qd = gl < C::NJ ? fminf(fmaxf(S[C::oU + gl], -10.f), 10.f) : 0.f;
+        const float aval = (act && gl < C::NACT) ? act[gl] : 0.f;
+        const float ss = gsum(aval * aval);
+        // done = not (finite and |state[2:]| < 100 and height / angle window)
+        bool bad = gl < C::NJ && (!(isfinite(q) && isfinite(qd)) || (gl >= 3 && !(fabsf(q) < 100.f)));   // qvel is clipped to 10
+        const bool anybad = gballot(bad) != 0u;
+        const float height = S[C::oQ + 1], ang = S[C::oQ + 2];
+        bool ok = !anybad;
+        if (m->kind == 12) ok = ok && height > -0.3f && fabsf(ang) < 0.2f;
+        else ok = ok && 1.0f > height && height > -0.2f && -1.0f < ang && ang < 1.0f;
+        if (pred) {
+            if (obs_out && gl < C::NJ) {
+                if (gl >= 1) obs_out[gl - 1] = q;
+                obs_out[C::NJ - 1 + gl] = qd;
+            }
+            if (gl == 0) {
+                if (!reset_pass) {
+                    const float pot = (float)(((double)x - (double)T[T_POT_LO]) / m->dt_scene);
+                    const float pc = -1e-3f * ss;
+                    if (rew_out) *rew_out = pot + 1.0f + pc;
+                    if (terms_out) { terms_out[0] = pot; terms_out[1] = 1.0f; terms_out[2] = pc; terms_out[3] = 0.f; terms_out[4] = 0.f; }
+                    if (anybad) T[T_HAVEZ] = 2.f;
+                }
+                T[T_POT_LO] = x;
+            }
+        }
+        __syncwarp();
+        return !reset_pass && !ok;
+    }
+
     // Reacher (rs/robot_manipulators.py:28-50, rs/gym_manipulator_envs.py:15-32): dofs joint0, joint1, target_x, target_y.
     // Never done; reward = potential change + electricity + stuck-joint cost.
     __device__ bool reacher_task(const float *act, float *obs_out, float *rew_out, float *terms_out, bool reset_pass, bool pred) {
@@ -1215,6 +1254,7 @@ struct Env {
                          bool pred = true) {
         if (m->kind <= 1 || m->kind == 9 || m->kind == 11) return pendulum_task(obs_out, rew_out, terms_out, reset_pass, pred);
         if (m->kind == 10) return reacher_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
+        if (m->kind == 12 || m->kind == 13) return mjwalker_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
         return walker_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
     }
 
@@ -1248,6 +1288,7 @@ struct Env {
                 if (m->kind <= 1) { if (gl == 0) S[C::oQ + 1] = nz + (m->kind == 1 ? 3.1415f : 0.f); }
                 else if (m->kind == 9 || m->kind == 11) S[C::oQ + 1 + gl] = nz;   // hinge, hinge2 (rs/robot_pendula.py:66-68)
                 else if (m->kind == 10) S[C::oQ + (gl ^ 2)] = nz;        // draws: target_x, target_y, joint0, joint1 -> dofs 2, 3, 0, 1
+                else if (m->kind == 12 || m->kind == 13) S[C::oQ + gl] = nz;   // every ordered joint incl. the root joints
                 else S[C::oQ + m->act_joint[gl]] = nz;
             }
             if (gl == 0) {

@@ -1,8 +1,11 @@
 """MuJoCo-style env shells (pybulletgym/envs/mujoco/): same robots and physics, gym-mujoco observation layouts.
 
-Backed so far: InvertedDoublePendulumMuJoCoEnv-v0 (mujoco/gym_pendulum_envs.py:40-75, mujoco/robot_pendula.py:55-91).
+Backed so far: InvertedDoublePendulumMuJoCoEnv-v0 (mujoco/gym_pendulum_envs.py:40-75, mujoco/robot_pendula.py:55-91),
+HopperMuJoCoEnv-v0 and Walker2DMuJoCoEnv-v0 (mujoco/gym_locomotion_envs.py:121-206, mujoco/robot_locomotors.py:86-165).
 The reference's InvertedPendulumMuJoCoEnv raises on its first reset (mujoco/robot_pendula.py:16 reads an undefined
-``self.swingup``); the five MuJoCo-style walkers are SURVEY.md section 8f N2 work.
+``self.swingup``); HalfCheetahMuJoCoEnv switches spinning / rolling friction and restitution on for every link
+(mujoco/robot_locomotors.py:209-210), which the CUDA contact rows do not model yet; Ant / Humanoid MuJoCo-style
+observations (111 / 376 entries, mostly zero padding) are SURVEY.md section 8f N2 work as well.
 """
 from __future__ import annotations
 
@@ -53,4 +56,70 @@ class InvertedDoublePendulumMuJoCoEnv(BaseBulletEnv):
         return state, sum(self.rewards), d, {}
 
 
-ENTRY_POINTS = {"InvertedDoublePendulumMuJoCoEnv-v0": InvertedDoublePendulumMuJoCoEnv}
+class _MJWalker(R.MJCFBasedRobot):
+    """Hopper / Walker2D of pybulletgym/envs/mujoco/robot_locomotors.py:86-165 (add_ignored_joints=True: the three root
+    joints are part of ordered_joints with power_coef 0)."""
+
+    def __init__(self, env_id):
+        R.MJCFBasedRobot.__init__(self, env_id)
+        b = self.bullet
+        dof_of = {li: k for k, li in enumerate(b.dof_links())}
+        self.ordered_joints = [R.Joint(self, b.links[i].joint_name, i, dof_of[i]) for i in b.dof_links()]
+        self.jdict = {j.joint_name: j for j in self.ordered_joints}
+        for j in self.ordered_joints:
+            j.power_coef = 0.0 if j.joint_name.startswith("ignore") else float(self.spec.power_coef.get(j.joint_name, 100.0))
+        self.power = self.spec.power
+        self.foot_list = list(self.spec.foot_list)
+        self.pos_after = 0
+
+
+class WalkerBaseMuJoCoEnv(BaseBulletEnv):
+    def __init__(self, robot, **kw):
+        BaseBulletEnv.__init__(self, robot, **kw)
+        self.walk_target_x, self.walk_target_y = 1e3, 0
+        self.stateId = -1
+
+    def create_single_player_scene(self, bullet_client):
+        from ..roboschool.scenes import StadiumScene
+        self.stadium_scene = StadiumScene(self.robot.spec.scene)
+        return self.stadium_scene
+
+    def _draw_reset_noise(self):
+        # mujoco/robot_locomotors.py:16-19: one draw per ordered joint, root joints included
+        return [self.np_random.uniform(low=-0.1, high=0.1) for _ in self.robot.ordered_joints]
+
+    def _finish_reset(self, obs):
+        self.robot._invalidate()
+        self.robot.pos_after = float(self.robot.robot_body.get_pose()[0])
+        self.stateId = 0
+        return obs
+
+    def _step(self, a):
+        a = np.asarray(a, dtype=np.float32)
+        assert np.isfinite(a).all()
+        obs, rew, done, info = self._backend.step(torch.from_numpy(a.reshape(1, -1)))
+        state = obs[0].cpu().numpy()
+        self.robot._invalidate()
+        self.robot.pos_after = float(self.robot.robot_body.get_pose()[0])
+        terms = info["reward_terms"][0].cpu().numpy()
+        self.rewards = [float(terms[0]), float(terms[1]), float(terms[2])]     # potential, alive_bonus, power_cost
+        d = bool(done[0])
+        self.HUD(state, a, d)
+        self.reward += sum(self.rewards)
+        return state, sum(self.rewards), d, {}
+
+
+class HopperMuJoCoEnv(WalkerBaseMuJoCoEnv):
+    def __init__(self, **kw):
+        self.robot = _MJWalker("HopperMuJoCoEnv-v0")
+        WalkerBaseMuJoCoEnv.__init__(self, self.robot, **kw)
+
+
+class Walker2DMuJoCoEnv(WalkerBaseMuJoCoEnv):
+    def __init__(self, **kw):
+        self.robot = _MJWalker("Walker2DMuJoCoEnv-v0")
+        WalkerBaseMuJoCoEnv.__init__(self, self.robot, **kw)
+
+
+ENTRY_POINTS = {"InvertedDoublePendulumMuJoCoEnv-v0": InvertedDoublePendulumMuJoCoEnv,
+                "HopperMuJoCoEnv-v0": HopperMuJoCoEnv, "Walker2DMuJoCoEnv-v0": Walker2DMuJoCoEnv}

@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 KIND_PENDULUM, KIND_PENDULUM_SWINGUP, KIND_HOPPER, KIND_WALKER2D, KIND_HALFCHEETAH, KIND_ANT, KIND_HUMANOID, \
-    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM, KIND_REACHER, KIND_DOUBLE_PENDULUM_MJ = range(12)
+    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM, KIND_REACHER, KIND_DOUBLE_PENDULUM_MJ, KIND_HOPPER_MJ, KIND_WALKER2D_MJ = range(14)
 
 
 @dataclass(frozen=True)
@@ -104,6 +104,10 @@ class EnvSpec:
             return 2
         if self.kind == KIND_REACHER:
             return 4            # target_x, target_y, joint0, joint1 (robot_manipulators.py:12-21)
+        if self.kind in (KIND_HOPPER_MJ, KIND_WALKER2D_MJ):
+            # add_ignored_joints=True puts the three root joints into ordered_joints, and WalkerBase.robot_specific_reset
+            # draws for every ordered joint (mujoco/robot_bases.py:85-90, mujoco/robot_locomotors.py:16-19)
+            return self.action_dim + 3
         return self.action_dim
 
     @property
@@ -151,6 +155,11 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
     EnvSpec("InvertedDoublePendulumMuJoCoEnv-v0", KIND_DOUBLE_PENDULUM_MJ, "inverted_double_pendulum.xml", "cart", 1, 11,
             1.0, scene=_PENDULUM_SCENE, reward_threshold=9100.0,
             entry_point="pybulletgym.envs.mujoco.gym_pendulum_envs:InvertedDoublePendulumMuJoCoEnv"),
+    EnvSpec("HopperMuJoCoEnv-v0", KIND_HOPPER_MJ, "hopper.xml", "torso", 3, 11, 0.75, foot_list=("foot",),
+            reward_threshold=2500.0, entry_point="pybulletgym.envs.mujoco.gym_locomotion_envs:HopperMuJoCoEnv"),
+    EnvSpec("Walker2DMuJoCoEnv-v0", KIND_WALKER2D_MJ, "walker2d.xml", "torso", 6, 17, 0.40,
+            power_coef={"foot_joint": 30.0, "foot_left_joint": 30.0}, foot_list=("foot", "foot_left"),
+            reward_threshold=2500.0, entry_point="pybulletgym.envs.mujoco.gym_locomotion_envs:Walker2DMuJoCoEnv"),
     EnvSpec("ReacherPyBulletEnv-v0", KIND_REACHER, "reacher.xml", "body0", 2, 9, 1.0,
             scene=SceneSpec(gravity=0.0, timestep=0.0165, frame_skip=1), max_episode_steps=150, reward_threshold=18.0,
             aux_links=("fingertip", "target"), entry_point=_RS + "gym_manipulator_envs:ReacherBulletEnv"),
@@ -185,6 +194,5 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
 UNBACKED_IDS = (
     "PusherPyBulletEnv-v0",
     "ThrowerPyBulletEnv-v0", "StrikerPyBulletEnv-v0", "AtlasPyBulletEnv-v0",
-    "InvertedPendulumMuJoCoEnv-v0", "Walker2DMuJoCoEnv-v0",
-    "HalfCheetahMuJoCoEnv-v0", "AntMuJoCoEnv-v0", "HopperMuJoCoEnv-v0", "HumanoidMuJoCoEnv-v0",
+    "InvertedPendulumMuJoCoEnv-v0", "HalfCheetahMuJoCoEnv-v0", "AntMuJoCoEnv-v0", "HumanoidMuJoCoEnv-v0",
 )

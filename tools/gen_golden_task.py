@@ -34,6 +34,8 @@ CASES = {
     "InvertedPendulumSwingupPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedPendulumSwingupBulletEnv", 2, 40, 1.0),
     "InvertedDoublePendulumPyBulletEnv-v0": ("gym_pendulum_envs", "InvertedDoublePendulumBulletEnv", 3, 60, 0.3),
     "InvertedDoublePendulumMuJoCoEnv-v0": ("mujoco.gym_pendulum_envs", "InvertedDoublePendulumMuJoCoEnv", 3, 60, 0.3),
+    "HopperMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "HopperMuJoCoEnv", 6, 40, 0.2),
+    "Walker2DMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "Walker2DMuJoCoEnv", 4, 40, 1.3),
     "ReacherPyBulletEnv-v0": ("gym_manipulator_envs", "ReacherBulletEnv", 3, 60, 1.3),
     "HopperPyBulletEnv-v0": ("gym_locomotion_envs", "HopperBulletEnv", 4, 40, 1.3),
     "Walker2DPyBulletEnv-v0": ("gym_locomotion_envs", "Walker2DBulletEnv", 4, 40, 1.3),
@@ -95,7 +97,7 @@ def main():
                       "done": bool(done), "rewards": [float(r) for r in env.rewards]}
                 if t < 40 or held:
                     st["state"] = env._p.orc.get_state().tolist()
-                if hasattr(env.robot, "feet_contact"):
+                if hasattr(env.robot, "feet_contact") and hasattr(env.robot, "joints_at_limit"):
                     st["feet_contact"] = [float(f) for f in env.robot.feet_contact]
                     st["joints_at_limit"] = int(env.robot.joints_at_limit)
                     st["body_xyz"] = [float(v) for v in env.robot.body_xyz]
