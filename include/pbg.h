@@ -40,7 +40,8 @@ enum {
     PBG_KIND_HALFCHEETAH = 4, PBG_KIND_ANT = 5, PBG_KIND_HUMANOID = 6, PBG_KIND_FLAGRUN = 7,
     PBG_KIND_FLAGRUN_HARDER = 8, PBG_KIND_DOUBLE_PENDULUM = 9, PBG_KIND_REACHER = 10,
     PBG_KIND_DOUBLE_PENDULUM_MJ = 11,  /* pybulletgym/envs/mujoco/gym_pendulum_envs.py:40-75 */
-    PBG_KIND_HOPPER_MJ = 12, PBG_KIND_WALKER2D_MJ = 13   /* pybulletgym/envs/mujoco/gym_locomotion_envs.py:121-206 */
+    PBG_KIND_HOPPER_MJ = 12, PBG_KIND_WALKER2D_MJ = 13,  /* pybulletgym/envs/mujoco/gym_locomotion_envs.py:121-206 */
+    PBG_KIND_ANT_MJ = 14, PBG_KIND_HUMANOID_MJ = 15      /* pybulletgym/envs/mujoco/gym_locomotion_envs.py:246-260 */
 };
 
 enum { PBG_JT_FIXED = 0, PBG_JT_REVOLUTE = 1, PBG_JT_PRISMATIC = 2, PBG_JT_FREE = 3 };

@@ -914,7 +914,10 @@ static void mat_to_quat(m3 m, double q[4]) {
     }
 }
 
-static int is_walker(int kind) { return kind >= ORC_KIND_HOPPER && kind <= ORC_KIND_FLAGRUN_HARDER; }
+/* WalkerBase robots; the MuJoCo-style Ant / Humanoid (pybulletgym/envs/mujoco/robot_locomotors.py:222-319) run the same
+ * WalkerBase.calc_state and only re-pack the observation */
+static int is_mjfloat(int kind) { return kind == ORC_KIND_ANT_MJ || kind == ORC_KIND_HUMANOID_MJ; }
+static int is_walker(int kind) { return (kind >= ORC_KIND_HOPPER && kind <= ORC_KIND_FLAGRUN_HARDER) || is_mjfloat(kind); }
 static double potential_leak(const orc_env *e);
 
 static double alive_bonus(orc_env *e, double z, double pitch) {
@@ -922,7 +925,7 @@ static double alive_bonus(orc_env *e, double z, double pitch) {
     case ORC_KIND_HOPPER: case ORC_KIND_WALKER2D: return (z > 0.8 && fabs(pitch) < 1.0) ? 1 : -1;
     case ORC_KIND_HALFCHEETAH:
         return (fabs(pitch) < 1.0 && !e->feet_contact[1] && !e->feet_contact[2] && !e->feet_contact[4] && !e->feet_contact[5]) ? 1 : -1;
-    case ORC_KIND_ANT: return z > 0.26 ? 1 : -1;
+    case ORC_KIND_ANT: case ORC_KIND_ANT_MJ: return z > 0.26 ? 1 : -1;
     case ORC_KIND_FLAGRUN_HARDER:
         /* rs/robot_locomotors.py:250-273: every 30 frames after frame 100 the cube is thrown at the spot the
          * robot will be at when it arrives */
@@ -1051,6 +1054,23 @@ static void mjwalker_calc_state(orc_env *e, double *obs) {
 }
 static double mjwalker_body_x(orc_env *e) { fk(e); return e->c[e->m.torso_link][0]; }   /* robot_body.get_pose()[0] */
 
+/* observation of a WalkerBase robot.  MuJoCo-style Ant / Humanoid (pybulletgym/envs/mujoco/robot_locomotors.py:222-319): run
+ * WalkerBase.calc_state for its side effects, then qpos[2:] ++ qvel ++ zero padding (cinert, cvel, qfrc_actuator, cfrc_ext
+ * are "TODO: FIND" zeros in the reference); float64 throughout */
+static void walker_obs(orc_env *e, double *obs) {
+    const orc_model *m = &e->m;
+    if (!is_mjfloat(m->kind)) { walker_calc_state(e, obs); return; }
+    double tmp[64]; walker_calc_state(e, tmp);
+    int o = 0, nA = m->nact;
+    obs[o++] = e->bpos[2];
+    for (int k = 0; k < 4; k++) obs[o++] = e->bquat[k];
+    for (int n = 0; n < nA; n++) obs[o++] = e->q[e->dof_of_link[m->act_link[n]]];
+    for (int k = 0; k < 3; k++) obs[o++] = e->bvel[k];
+    for (int k = 0; k < 3; k++) obs[o++] = e->bomega[k];
+    for (int n = 0; n < nA; n++) obs[o++] = e->qd[e->dof_of_link[m->act_link[n]]];
+    while (o < m->obs_dim) obs[o++] = 0.0;
+}
+
 static void pendulum_calc_state(orc_env *e, double *obs) {
     /* rs/robot_pendula.py:27-51: slider = dof 0, hinge = dof 1 */
     double x = e->q[0], vx = e->qd[0], th = e->q[1], thd = e->qd[1];
@@ -1136,9 +1156,10 @@ int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double
         *reward = t5[0];
         }
     } else {
-        walker_calc_state(e, obs);
         double zz;
-        if (m->initial_z >= 0) zz = (double)((float)obs[0] + (float)e->initial_z);   /* np.float32 + python float */
+        walker_obs(e, obs);
+        if (is_mjfloat(m->kind)) zz = obs[0] + e->initial_z;   /* WalkerBaseMuJoCoEnv._step: state[0] = torso z stands in for z - initial_z */
+        else if (m->initial_z >= 0) zz = (double)((float)obs[0] + (float)e->initial_z);   /* np.float32 + python float */
         else zz = obs[0] + e->initial_z;                                            /* np.float32 + np.float64 */
         double alive = alive_bonus(e, zz, e->body_rpy[1]);
         done = alive < 0;
@@ -1152,6 +1173,7 @@ int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double
         double elec = m->elec_cost * (se / m->nact) + m->stall_cost * (ss / m->nact);
         double lim = m->limit_cost * e->joints_at_limit;
         t5[0] = alive; t5[1] = progress; t5[2] = elec; t5[3] = lim; t5[4] = 0.0;
+        if (is_mjfloat(m->kind)) { t5[2] = lim; t5[3] = 0.0; }     /* [alive, progress, joints_at_limit_cost, feet_collision_cost] */
         *reward = t5[0] + t5[1] + t5[2] + t5[3] + t5[4];
     }
     if (terms) memcpy(terms, t5, sizeof(t5));
@@ -1198,7 +1220,7 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
     if (m->initial_z >= 0) { e->initial_z = m->initial_z; e->have_initial_z = 1; } else e->have_initial_z = 0;
     e->flag_count = 0; e->flag_timeout = 0; e->frame = 0; e->on_ground = 0; e->crawl_has = 0; e->crawl_start = 0; e->crawl_ign = 0; e->attacks = 0;
     if (is_flagrun(m->kind)) flag_reposition(e);
-    if (is_walker(m->kind)) { walker_calc_state(e, obs); e->potential = calc_potential(e); }
+    if (is_walker(m->kind)) { walker_obs(e, obs); e->potential = calc_potential(e); }
     else if (m->kind == ORC_KIND_REACHER) { reacher_calc_state(e, obs); e->potential = reacher_potential(e); }
     else if (is_mjwalker(m->kind)) { mjwalker_calc_state(e, obs); e->potential = mjwalker_body_x(e); }
     else pendulum_calc_state(e, obs);
@@ -1295,7 +1317,7 @@ void orc_mass_matrix_inv(orc_env *e, double *Minv) {
 }
 
 long orc_rollout(orc_env *e, long steps, uint64_t action_seed, double *ret_sum, long *episodes) {
-    double obs[64], act[MAXD], rew, rs = 0; long eps = 0;
+    double obs[512], act[MAXD], rew, rs = 0; long eps = 0;
     orc_reset(e, 1, obs);
     for (long t = 0; t < steps; t++) {
         for (int n = 0; n < e->m.nact; n++)

@@ -27,6 +27,8 @@ using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1>;
 #define PBG_ANT_BLOCKS 1
 #endif
 using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28, PBG_ANT_WARPS, PBG_ANT_BLOCKS>;
+using CfgAntMJ = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 111, PBG_ANT_WARPS, PBG_ANT_BLOCKS>;
+using CfgHumanoidMJ = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 376, 7, 1>;
 using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1>;
 // HumanoidFlagrunHarder: the humanoid + the cube (one more free body, 8 corner candidates, 17 geom-vs-cube pairs)
 using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17>;
@@ -65,6 +67,8 @@ static bool kernel_for_kind(int kind, KernelInfo *out) {
     case PBG_KIND_WALKER2D_MJ: *out = info_of<CfgWalkerMJ>(); return true;
     case PBG_KIND_HALFCHEETAH: *out = info_of<CfgCheetah>(); return true;
     case PBG_KIND_ANT: *out = info_of<CfgAnt>(); return true;
+    case PBG_KIND_ANT_MJ: *out = info_of<CfgAntMJ>(); return true;
+    case PBG_KIND_HUMANOID_MJ: *out = info_of<CfgHumanoidMJ>(); return true;
     case PBG_KIND_HUMANOID: case PBG_KIND_FLAGRUN: *out = info_of<CfgHumanoid>(); return true;
     case PBG_KIND_FLAGRUN_HARDER: *out = info_of<CfgHarder>(); return true;
     default: return false;

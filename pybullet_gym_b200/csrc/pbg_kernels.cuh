@@ -33,6 +33,9 @@ struct KCfg {
     static constexpr int ND = XD0 + 6 * HASX;
     static constexpr int MAXC = MAXC_, LPE = LPE_, NCAND = NCAND_ + 8 * HASX, NPAIR = NPAIR_ + XP_, NSLOT = NCAND + NPAIR;
     static constexpr int NFEET = NFEET_, NACT = NACT_, OBS = OBS_;
+    // observations wider than the 64-float staging area are MuJoCo-style layouts whose tail is zero padding
+    // (pybulletgym/envs/mujoco/robot_locomotors.py:222-319): only the first OBSNZ entries are staged
+    static constexpr int OBSNZ = OBS_ <= 64 ? OBS_ : 11 + 2 * NJ_;
     static constexpr int MAXR = NLIM + 3 * MAXC;
     static constexpr int MAXRP = MAXR > 0 ? MAXR : 1;
     static constexpr int NDP = (ND + 3) / 4 * 4;
@@ -1027,7 +1030,17 @@ struct Env {
         // observation, clipped to +-5
         auto clip5 = [](float q) { return fminf(fmaxf(q, -5.f), 5.f); };
         const float o0 = clip5(z - initz);
-        if (obs_out && pred) {
+        const bool mjf = kind == 14 || kind == 15;
+        if (mjf && obs_out && pred) {
+            // MuJoCo-style Ant / Humanoid: [z, quat xyzw, q] ++ [base v, base omega, qdot] (unclipped), zeros after that
+            if (gl == 0) { obs_out[0] = S[2]; obs_out[1] = S[3]; obs_out[2] = S[4]; obs_out[3] = S[5]; obs_out[4] = S[6]; }
+            if (gl < 3) { obs_out[5 + C::NJ + gl] = S[C::oU + 3 + gl]; obs_out[8 + C::NJ + gl] = S[C::oU + gl]; }
+            if (gl < C::NACT) {
+                const int j = m->act_joint[gl];
+                obs_out[5 + gl] = S[C::oQ + j]; obs_out[11 + C::NJ + gl] = S[C::oU + 6 * C::FLOATING + j];
+            }
+        }
+        if (!mjf && obs_out && pred) {
             if (gl == 0) {
                 obs_out[0] = o0; obs_out[1] = clip5(sa); obs_out[2] = clip5(ca); obs_out[3] = clip5(0.3f * vx);
                 obs_out[4] = clip5(0.3f * vy); obs_out[5] = clip5(0.3f * vz); obs_out[6] = clip5(roll); obs_out[7] = clip5(pitch);
@@ -1074,12 +1087,13 @@ struct Env {
         const double pot_new = harder ? harder_potential(dist) : -dist / m->dt_scene;
         {
             // alive uses state[0] + initial_z after the float32 round trip (rs/gym_locomotion_envs.py:61)
-            const float zz = (m->initial_z >= 0.f) ? (o0 + initz) : (float)((double)o0 + (double)initz);
+            // (MuJoCo-style variants pass state[0] = torso z itself: mujoco/gym_locomotion_envs.py:60)
+            const float zz = mjf ? (S[2] + initz) : ((m->initial_z >= 0.f) ? (o0 + initz) : (float)((double)o0 + (double)initz));
             const float *fc = S + C::oF;
             float alive;
             if (kind == 2 || kind == 3) alive = (zz > 0.8f && fabsf(pitch) < 1.0f) ? 1.f : -1.f;
             else if (kind == 4) alive = (fabsf(pitch) < 1.0f && fc[1] == 0.f && fc[2] == 0.f && fc[4] == 0.f && fc[5] == 0.f) ? 1.f : -1.f;
-            else if (kind == 5) alive = zz > 0.26f ? 1.f : -1.f;
+            else if (kind == 5 || kind == 14) alive = zz > 0.26f ? 1.f : -1.f;
             else if (kind == 8) alive = h_alive;
             else alive = zz > 0.78f ? 2.f : -1.f;
             done = alive < 0.f;
@@ -1093,7 +1107,13 @@ struct Env {
             const float progress = (float)(pot_new - pot_old);
             const float elec = m->elec_cost * (se / (float)C::NACT) + m->stall_cost * (ss / (float)C::NACT);
             const float limc = m->limit_cost * (float)nlim;
-            if (gl == 0 && pred && !reset_pass) {
+            if (gl == 0 && pred && !reset_pass && mjf) {
+                // WalkerBaseMuJoCoEnv._step: [alive, progress, joints_at_limit_cost, feet_collision_cost]
+                if (rew_out) *rew_out = alive + progress + limc;
+                if (terms_out) { terms_out[0] = alive; terms_out[1] = progress; terms_out[2] = limc; terms_out[3] = 0.f; terms_out[4] = 0.f; }
+                if (anybad) T[T_HAVEZ] = 2.f;
+            }
+            if (gl == 0 && pred && !reset_pass && !mjf) {
                 if (rew_out) *rew_out = alive + progress + elec + limc;
                 if (terms_out) { terms_out[0] = alive; terms_out[1] = progress; terms_out[2] = elec; terms_out[3] = limc; terms_out[4] = 0.f; }
                 if (anybad) T[T_HAVEZ] = 2.f;      // marks a non-finite termination for the statistics
@@ -1480,13 +1500,13 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
                 if (T[T_HAVEZ] == 2.f) atomicAdd(&B.stats[4], 1ull);
             }
             if (la.auto_reset && valid && B.final_obs)
-                for (int i = gl; i < C::OBS; i += C::LPE) B.final_obs[env * C::OBS + i] = so_obs[i];
+                for (int i = gl; i < C::OBS; i += C::LPE) B.final_obs[env * C::OBS + i] = i < C::OBSNZ ? so_obs[i] : 0.f;
         }
         want_reset = mode == MODE_STEP && finished && la.auto_reset;
     }
     __syncwarp();
     if (valid) {
-        if (obs) for (int i = gl; i < C::OBS; i += C::LPE) obs[i] = so_obs[i];
+        if (obs) for (int i = gl; i < C::OBS; i += C::LPE) obs[i] = i < C::OBSNZ ? so_obs[i] : 0.f;
         if (store_state)
             for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
                 reinterpret_cast<float4 *>(gs)[i] = reinterpret_cast<const float4 *>(S)[i];

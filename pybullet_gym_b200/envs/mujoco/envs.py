@@ -4,8 +4,9 @@ Backed so far: InvertedDoublePendulumMuJoCoEnv-v0 (mujoco/gym_pendulum_envs.py:4
 HopperMuJoCoEnv-v0 and Walker2DMuJoCoEnv-v0 (mujoco/gym_locomotion_envs.py:121-206, mujoco/robot_locomotors.py:86-165).
 The reference's InvertedPendulumMuJoCoEnv raises on its first reset (mujoco/robot_pendula.py:16 reads an undefined
 ``self.swingup``); HalfCheetahMuJoCoEnv switches spinning / rolling friction and restitution on for every link
-(mujoco/robot_locomotors.py:209-210), which the CUDA contact rows do not model yet; Ant / Humanoid MuJoCo-style
-observations (111 / 376 entries, mostly zero padding) are SURVEY.md section 8f N2 work as well.
+(mujoco/robot_locomotors.py:209-210), which the CUDA contact rows do not model yet.  AntMuJoCoEnv-v0 and
+HumanoidMuJoCoEnv-v0 (mujoco/gym_locomotion_envs.py:246-260, mujoco/robot_locomotors.py:222-319) re-pack the WalkerBase state
+as qpos[2:] ++ qvel ++ zero padding (111 / 376 entries).
 """
 from __future__ import annotations
 
@@ -14,6 +15,7 @@ import torch
 
 from ..roboschool import robots as R
 from ..roboschool.envs import BaseBulletEnv
+from ..roboschool.envs import WalkerBaseBulletEnv as _RsWalkerEnv
 from ..roboschool.scenes import SingleRobotEmptyScene
 
 
@@ -121,5 +123,43 @@ class Walker2DMuJoCoEnv(WalkerBaseMuJoCoEnv):
         WalkerBaseMuJoCoEnv.__init__(self, self.robot, **kw)
 
 
+class Ant(R.WalkerBase):
+    def __init__(self):
+        R.WalkerBase.__init__(self, "AntMuJoCoEnv-v0")
+
+    def alive_bonus(self, z, pitch):
+        return +1 if z > 0.26 else -1
+
+
+class _FloatingMuJoCoEnv(_RsWalkerEnv):
+    """AntMuJoCoEnv / HumanoidMuJoCoEnv (mujoco/gym_locomotion_envs.py:246-260): WalkerBaseMuJoCoEnv._step with the
+    robot's MuJoCo-style observation; rewards = [alive, progress, joints_at_limit_cost, feet_collision_cost]."""
+
+    def _finish_reset(self, obs):
+        return _RsWalkerEnv._finish_reset(self, obs).astype(np.float64)
+
+    def _step(self, a):
+        state, rew, done, info = _RsWalkerEnv._step(self, a)
+        self.reward -= sum(self.rewards)
+        self.rewards = self.rewards[:4]
+        self.reward += sum(self.rewards)
+        return state.astype(np.float64), rew, done, info
+
+
+class AntMuJoCoEnv(_FloatingMuJoCoEnv):
+    def __init__(self, **kw):
+        self.robot = Ant()
+        _RsWalkerEnv.__init__(self, self.robot, **kw)
+
+
+class HumanoidMuJoCoEnv(_FloatingMuJoCoEnv):
+    def __init__(self, **kw):
+        self.robot = R.Humanoid("HumanoidMuJoCoEnv-v0")
+        _RsWalkerEnv.__init__(self, self.robot, **kw)
+        self.electricity_cost = 4.25 * _RsWalkerEnv.electricity_cost        # set but unused (mujoco/gym_locomotion_envs.py:257-260)
+        self.stall_torque_cost = 4.25 * _RsWalkerEnv.stall_torque_cost
+
+
 ENTRY_POINTS = {"InvertedDoublePendulumMuJoCoEnv-v0": InvertedDoublePendulumMuJoCoEnv,
-                "HopperMuJoCoEnv-v0": HopperMuJoCoEnv, "Walker2DMuJoCoEnv-v0": Walker2DMuJoCoEnv}
+                "HopperMuJoCoEnv-v0": HopperMuJoCoEnv, "Walker2DMuJoCoEnv-v0": Walker2DMuJoCoEnv,
+                "AntMuJoCoEnv-v0": AntMuJoCoEnv, "HumanoidMuJoCoEnv-v0": HumanoidMuJoCoEnv}

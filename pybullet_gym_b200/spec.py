@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 KIND_PENDULUM, KIND_PENDULUM_SWINGUP, KIND_HOPPER, KIND_WALKER2D, KIND_HALFCHEETAH, KIND_ANT, KIND_HUMANOID, \
-    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM, KIND_REACHER, KIND_DOUBLE_PENDULUM_MJ, KIND_HOPPER_MJ, KIND_WALKER2D_MJ = range(14)
+    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM, KIND_REACHER, KIND_DOUBLE_PENDULUM_MJ, KIND_HOPPER_MJ, KIND_WALKER2D_MJ, KIND_ANT_MJ, KIND_HUMANOID_MJ = range(16)
 
 
 @dataclass(frozen=True)
@@ -160,6 +160,12 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
     EnvSpec("Walker2DMuJoCoEnv-v0", KIND_WALKER2D_MJ, "walker2d.xml", "torso", 6, 17, 0.40,
             power_coef={"foot_joint": 30.0, "foot_left_joint": 30.0}, foot_list=("foot", "foot_left"),
             reward_threshold=2500.0, entry_point="pybulletgym.envs.mujoco.gym_locomotion_envs:Walker2DMuJoCoEnv"),
+    EnvSpec("AntMuJoCoEnv-v0", KIND_ANT_MJ, "ant.xml", "torso", 8, 111, 2.5,
+            foot_list=("front_left_foot", "front_right_foot", "left_back_foot", "right_back_foot"),
+            reward_threshold=2500.0, entry_point="pybulletgym.envs.mujoco.gym_locomotion_envs:AntMuJoCoEnv"),
+    EnvSpec("HumanoidMuJoCoEnv-v0", KIND_HUMANOID_MJ, "humanoid_symmetric.xml", "torso", 17, 376, 0.41,
+            power_coef=_HUMANOID_POWER, foot_list=("right_foot", "left_foot"), initial_z=0.8,
+            entry_point="pybulletgym.envs.mujoco.gym_locomotion_envs:HumanoidMuJoCoEnv"),
     EnvSpec("ReacherPyBulletEnv-v0", KIND_REACHER, "reacher.xml", "body0", 2, 9, 1.0,
             scene=SceneSpec(gravity=0.0, timestep=0.0165, frame_skip=1), max_episode_steps=150, reward_threshold=18.0,
             aux_links=("fingertip", "target"), entry_point=_RS + "gym_manipulator_envs:ReacherBulletEnv"),
@@ -194,5 +200,5 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
 UNBACKED_IDS = (
     "PusherPyBulletEnv-v0",
     "ThrowerPyBulletEnv-v0", "StrikerPyBulletEnv-v0", "AtlasPyBulletEnv-v0",
-    "InvertedPendulumMuJoCoEnv-v0", "HalfCheetahMuJoCoEnv-v0", "AntMuJoCoEnv-v0", "HumanoidMuJoCoEnv-v0",
+    "InvertedPendulumMuJoCoEnv-v0", "HalfCheetahMuJoCoEnv-v0",
 )

@@ -201,6 +201,10 @@ class FakeBulletClient:
         if b["kind"] == "cube":
             p, q, _, _ = self.orc.get_cube()
             return tuple(p), tuple(q)
+        if self.bm.floating:
+            # the multibody's own (integrated, sign-continuous) base quaternion, as pybullet reports it
+            st = self.orc.get_state()
+            return tuple(st[0:3]), tuple(st[3:7])
         s = self._link(0)
         return tuple(s[0:3]), tuple(s[3:7])
 
@@ -215,7 +219,8 @@ class FakeBulletClient:
     def getBaseVelocity(self, body):
         self._count("getBaseVelocity")
         s = self._link(0)
-        return tuple(s[7:10]), (0.0, 0.0, 0.0)
+        ang = tuple(self.orc.get_state()[7:10]) if self.bm.floating else (0.0, 0.0, 0.0)    # base angular velocity
+        return tuple(s[7:10]), ang
 
     def getContactPoints(self, bodyA=-1, bodyB=-1, linkIndexA=-2, linkIndexB=-2):
         self._count("getContactPoints")

@@ -36,6 +36,8 @@ CASES = {
     "InvertedDoublePendulumMuJoCoEnv-v0": ("mujoco.gym_pendulum_envs", "InvertedDoublePendulumMuJoCoEnv", 3, 60, 0.3),
     "HopperMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "HopperMuJoCoEnv", 6, 40, 0.2),
     "Walker2DMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "Walker2DMuJoCoEnv", 4, 40, 1.3),
+    "AntMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "AntMuJoCoEnv", 3, 40, 1.3),
+    "HumanoidMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "HumanoidMuJoCoEnv", 3, 40, 1.3),
     "ReacherPyBulletEnv-v0": ("gym_manipulator_envs", "ReacherBulletEnv", 3, 60, 1.3),
     "HopperPyBulletEnv-v0": ("gym_locomotion_envs", "HopperBulletEnv", 4, 40, 1.3),
     "Walker2DPyBulletEnv-v0": ("gym_locomotion_envs", "Walker2DBulletEnv", 4, 40, 1.3),
