@@ -158,6 +158,18 @@ int pbg_reset_with(pbg_handle *h, const float *joint_noise_dev, int32_t floor_in
 int pbg_step(pbg_handle *h, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
              float *reward_terms_dev, float *final_obs_dev, uint8_t *truncated_dev, void *stream);
 
+/* Fused policy rollouts (the reference's counterpart is the numpy MLP loop of
+ * pybulletgym/examples/roboschool-weights/enjoy_TF_*.py: obs -> relu(W1) -> relu(W2) -> W3 -> env.step).
+ * pbg_set_policy copies a two-hidden-layer ReLU policy (host pointers, row-major [in, out]: w1[obs_dim, h1], w2[h1, h2],
+ * w3[h2, action_dim]) to the device.  pbg_rollout_policy then advances every env by `nsteps` env steps in ONE kernel launch:
+ * observation -> MLP -> action -> step, state resident in shared memory, auto-reset as in pbg_step.  obs_dev is in/out: the
+ * observation of the current state on entry (what pbg_reset / pbg_step returned), the last one on return;
+ * reward_sum_dev[num_envs] (optional) receives the sum of the nsteps rewards, done_any_dev[num_envs] (optional) whether an
+ * episode ended during the rollout. */
+int pbg_set_policy(pbg_handle *h, int32_t h1, int32_t h2, const float *w1, const float *b1, const float *w2, const float *b2,
+                   const float *w3, const float *b3);
+int pbg_rollout_policy(pbg_handle *h, int32_t nsteps, float *obs_dev, float *reward_sum_dev, uint8_t *done_any_dev, void *stream);
+
 /* Host-buffer variant (the reference-facing call: numpy in, numpy out).  Copies actions H2D,
  * steps, copies obs/reward/done D2H and synchronises.  Buffers should be pinned for full speed. */
 int pbg_step_host(pbg_handle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *done_host);

@@ -119,6 +119,8 @@ def lib():
     L.pbg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.pbg_step_host.argtypes = [vp, vp, vp, vp, vp]
     L.pbg_set_auto_reset.argtypes = [vp, C.c_int32]
+    L.pbg_set_policy.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.pbg_rollout_policy.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
     L.pbg_set_zero_copy.argtypes = [vp, C.c_int32]
     L.pbg_last_host_path.argtypes = [vp]
     L.pbg_get_state.argtypes = [vp, vp, vp]
@@ -137,7 +139,7 @@ def lib():
 
 EXPORTS = ["pbg_version", "pbg_create", "pbg_destroy", "pbg_last_error", "pbg_num_envs", "pbg_obs_dim",
            "pbg_action_dim", "pbg_state_dim", "pbg_noise_dim", "pbg_reset", "pbg_reset_with", "pbg_step", "pbg_step_host",
-           "pbg_set_auto_reset", "pbg_set_zero_copy", "pbg_last_host_path", "pbg_get_state", "pbg_set_state", "pbg_physics_step", "pbg_physics_step_counts",
+           "pbg_set_auto_reset", "pbg_set_zero_copy", "pbg_last_host_path", "pbg_set_policy", "pbg_rollout_policy", "pbg_get_state", "pbg_set_state", "pbg_physics_step", "pbg_physics_step_counts",
            "pbg_max_contacts", "pbg_measure_fp32_peak", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count"]
 
 

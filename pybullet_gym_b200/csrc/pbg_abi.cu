@@ -34,7 +34,7 @@ using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1>;
 using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17>;
 
 struct KernelInfo {
-    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet, nnoise;
+    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet, nnoise, ysz;
     size_t smem;
     void (*launch)(const DevModel *, const StepBuffers &, const LaunchArgs &, cudaStream_t);
     cudaError_t (*prepare)();
@@ -43,16 +43,19 @@ struct KernelInfo {
 template <class C>
 static void launch_cfg(const DevModel *m, const StepBuffers &b, const LaunchArgs &la, cudaStream_t s) {
     const int blocks = (la.E + C::EPB - 1) / C::EPB;
-    env_kernel<C><<<blocks, C::THREADS, C::SMEM_BYTES, s>>>(m, b, la);
+    if (la.mode == MODE_POLICY) env_kernel<C, true><<<blocks, C::THREADS, C::SMEM_BYTES, s>>>(m, b, la);
+    else env_kernel<C, false><<<blocks, C::THREADS, C::SMEM_BYTES, s>>>(m, b, la);
 }
 template <class C>
 static cudaError_t prepare_cfg() {
-    return cudaFuncSetAttribute(env_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(env_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(env_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
 }
 template <class C>
 static KernelInfo info_of() {
     return KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
 }
 
 static bool kernel_for_kind(int kind, KernelInfo *out) {
@@ -89,6 +92,8 @@ struct pbg_handle {
     unsigned long long seed = 0, env_offset = 0;
     int auto_reset = 1;
     int debug_env = 0;
+    float *policy_buf = nullptr;   // fused-policy weights (pbg_set_policy)
+    PolicyDev policy{};
     int zero_copy = 1;          // pbg_step_host: let the kernel read / write mapped pinned host buffers directly
     int last_host_path = 0;     // 1: zero-copy, 2: staged copies
     int64_t launches = 0;
@@ -383,7 +388,7 @@ int pbg_destroy(pbg_handle *h) {
     if (!h) return PBG_OK;
     cudaSetDevice(h->device);
     cudaFree(h->dmodel); cudaFree(h->state); cudaFree(h->stats);
-    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
+    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->policy_buf);
     if (h->hstream) cudaStreamDestroy(h->hstream);
     delete h;
     return PBG_OK;
@@ -403,7 +408,8 @@ static int launch(pbg_handle *h, int mode, StepBuffers &b, int floor_in_parts, v
     b.stats = h->stats;
     LaunchArgs la;
     la.E = h->E; la.mode = mode; la.auto_reset = h->auto_reset; la.floor_in_parts = floor_in_parts;
-    la.seed = h->seed; la.env_offset = h->env_offset; la.debug_env = h->debug_env;
+    la.seed = h->seed; la.env_offset = h->env_offset; la.debug_env = h->debug_env; la.nsteps = 1;
+    if (mode >= 100) { la.nsteps = mode - 100; la.mode = mode = MODE_POLICY; b.policy = h->policy; }
     h->k.launch(h->dmodel, b, la, (cudaStream_t)stream);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
@@ -482,6 +488,37 @@ int pbg_step_host(pbg_handle *h, const float *actions_host, float *obs_host, flo
     if (done_host) CUDA_TRY(h, cudaMemcpyAsync(done_host, h->d_done, E, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     return PBG_OK;
+}
+
+int pbg_set_policy(pbg_handle *h, int32_t h1, int32_t h2, const float *w1, const float *b1, const float *w2, const float *b2,
+                   const float *w3, const float *b3) {
+    if (!h || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || h1 <= 0 || h2 <= 0) return fail(h, PBG_ERR_INVALID, "pbg_set_policy: bad arguments");
+    // the hidden activations live in the env's kinematics / Delassus scratch (dead between two steps)
+    if (h1 + h2 > h->k.ysz) return fail(h, PBG_ERR_UNSUPPORTED, "pbg_set_policy: hidden layers do not fit this env kind's shared-memory scratch");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t D = h->k.obs, A = h->k.nact;
+    const size_t n = D * h1 + h1 + size_t(h1) * h2 + h2 + size_t(h2) * A + A;
+    cudaFree(h->policy_buf); h->policy_buf = nullptr;
+    CUDA_TRY(h, cudaMalloc(&h->policy_buf, n * sizeof(float)));
+    float *p = h->policy_buf;
+    const float *src[6] = {w1, b1, w2, b2, w3, b3};
+    const size_t cnt[6] = {D * h1, size_t(h1), size_t(h1) * h2, size_t(h2), size_t(h2) * A, A};
+    const float *dst[6];
+    for (int i = 0; i < 6; ++i) {
+        CUDA_TRY(h, cudaMemcpy(p, src[i], cnt[i] * sizeof(float), cudaMemcpyHostToDevice));
+        dst[i] = p; p += cnt[i];
+    }
+    h->policy = PolicyDev{dst[0], dst[1], dst[2], dst[3], dst[4], dst[5], h1, h2};
+    return PBG_OK;
+}
+
+int pbg_rollout_policy(pbg_handle *h, int32_t nsteps, float *obs_dev, float *reward_sum_dev, uint8_t *done_any_dev, void *stream) {
+    if (!h || !obs_dev || nsteps <= 0 || nsteps > 100000) return fail(h, PBG_ERR_INVALID, "pbg_rollout_policy: bad arguments");
+    if (!h->policy_buf) return fail(h, PBG_ERR_INVALID, "pbg_rollout_policy: no policy set (pbg_set_policy)");
+    StepBuffers b{};
+    b.obs = obs_dev; b.reward = reward_sum_dev; b.done = done_any_dev;
+    h->steps += int64_t(h->E) * nsteps;
+    return launch(h, 100 + nsteps, b, 1, stream);
 }
 
 int pbg_get_state(pbg_handle *h, float *state_dev, void *stream) {

@@ -80,6 +80,7 @@ struct KCfg {
     static constexpr int sA = sU;
     static constexpr int ENV_FLOATS = (sU + (G1 > MAXRP * MAXRP + 2 * LPE ? G1 : MAXRP * MAXRP + 2 * LPE) + 3) / 4 * 4;
     static constexpr size_t SMEM_BYTES = size_t(ENV_FLOATS) * EPB * sizeof(float);
+    static constexpr int HIDCAP = ENV_FLOATS - sU;             // room for the fused policy's hidden activations
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1268,6 +1269,30 @@ struct Env {
         return false;
     }
 
+    // Fused policy inference: the observation staged in shared memory goes through the MLP, lane = output
+    // unit, weights streamed from global memory (every env group of the grid reads the same addresses: L1 / L2 hits).
+    __device__ void policy_actions(const PolicyDev &P, const float *obs_s, float *hid, float *act_out) {
+        float *h1v = hid, *h2v = hid + P.h1;
+        for (int o = gl; o < P.h1; o += C::LPE) {
+            float acc = __ldg(P.b1 + o);
+            for (int d = 0; d < C::OBS; ++d) acc = fmaf(d < C::OBSNZ ? obs_s[d] : 0.f, __ldg(P.w1 + d * P.h1 + o), acc);
+            h1v[o] = fmaxf(acc, 0.f);
+        }
+        __syncwarp();
+        for (int o = gl; o < P.h2; o += C::LPE) {
+            float acc = __ldg(P.b2 + o);
+            for (int d = 0; d < P.h1; ++d) acc = fmaf(h1v[d], __ldg(P.w2 + d * P.h2 + o), acc);
+            h2v[o] = fmaxf(acc, 0.f);
+        }
+        __syncwarp();
+        for (int o = gl; o < C::NACT; o += C::LPE) {
+            float acc = __ldg(P.b3 + o);
+            for (int d = 0; d < P.h2; ++d) acc = fmaf(h2v[d], __ldg(P.w3 + d * C::NACT + o), acc);
+            act_out[o] = acc;            // raw policy output: the torque clips it, the electricity cost does not (quirk Q3)
+        }
+        __syncwarp();
+    }
+
     // `pred` guards every persistent write, so that a whole warp can run the task / reset code
     // while only some of its env groups need it (no divergent __syncwarp / shuffles).
     __device__ bool task(const float *act, float *obs_out, float *rew_out, float *terms_out, bool reset_pass,
@@ -1336,7 +1361,9 @@ struct Env {
 };
 
 // ---------------------------------------------------------------------------------------------
-template <class C>
+// POLICY = true is the multi-step fused-policy instantiation (MODE_POLICY only); keeping it a separate kernel leaves the
+// single-step kernel's register allocation untouched.
+template <class C, bool POLICY = false>
 __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const DevModel *__restrict__ model, StepBuffers B, LaunchArgs la) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1414,7 +1441,24 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     float *so = e.sm + C::sOUT;
     float *so_obs = so, *so_rew = so + 64, *so_terms = so + 65;
 
-    if (mode == MODE_STEP || mode == MODE_PHYSICS) {
+    // MODE_POLICY: `nsteps` env steps in this one launch, actions from the fused MLP on the staged observation;
+    // the state stays in shared memory in between.  Everything else is exactly MODE_STEP.
+    const bool policy_mode = POLICY;
+    const int mode_eff = policy_mode ? (int)MODE_STEP : mode;
+    const int nsteps = policy_mode ? la.nsteps : 1;
+    float ret_acc = 0.f;
+    bool any_done = false;
+    bool store_state = mode_eff == MODE_STEP || mode == MODE_OBSERVE;
+    if (policy_mode) {
+        for (int i = gl; i < C::OBSNZ; i += C::LPE) so_obs[i] = obs[i];      // the observation the caller holds for this state
+        act = e.sm + C::sACTN;
+        __syncwarp();
+    }
+  for (int step = 0; step < nsteps; ++step) {
+    const bool last_step = step == nsteps - 1;
+    // hidden activations go to the kinematics / Delassus scratch, which is dead between the task phase and the next sub-step
+    if (policy_mode) e.policy_actions(B.policy, so_obs, e.sm + C::sU, e.sm + C::sACTN);
+    if (mode_eff == MODE_STEP || mode == MODE_PHYSICS) {
         // apply_action: tau = power * power_coef * clip(a, -1, 1) (rs/robot_locomotors.py:26-29),
         // plus the joint damping torque, both held for all substeps
         float tq = 0.f;
@@ -1455,7 +1499,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     if (mode == MODE_OBSERVE) e.nc = 0;
     const bool reset_mode = mode == MODE_RESET;
     const bool mask_on = reset_mode && (!B.mask || B.mask[env]);
-    bool store_state = mode == MODE_STEP || mode == MODE_OBSERVE;
     bool want_reset = mask_on;
     for (int pass = reset_mode ? 1 : 0; pass < 2; ++pass) {
         bool rp = false, pred = true;
@@ -1470,11 +1513,11 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
         }
         const bool done = e.task(act, so_obs, so_rew, so_terms, rp, pred);
         if (pass == 1) break;
-        if (mode == MODE_STEP && C::MAXC > 0 && gl < C::NFEET) S[C::oF + gl] = e.sm[C::sMISC + gl];
+        if (mode_eff == MODE_STEP && C::MAXC > 0 && gl < C::NFEET) S[C::oF + gl] = e.sm[C::sMISC + gl];
         if (mode == MODE_OBSERVE && C::MAXC > 0 && gl < C::NFEET) S[C::oF + gl] = S[C::oP + gl];
         __syncwarp();
         bool trunc = false;
-        if (mode == MODE_STEP) {
+        if (mode_eff == MODE_STEP) {
             if (gl == 0) {
                 T[T_STEPS] = __int_as_float(__float_as_int(T[T_STEPS]) + 1);
                 T[T_RETURN] += so_rew[0];
@@ -1483,7 +1526,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
             trunc = !done && __float_as_int(T[T_STEPS]) >= model->max_steps;
         }
         const bool finished = done || trunc;
-        if (valid && gl == 0) {
+        if (policy_mode) { ret_acc += so_rew[0]; any_done = any_done || finished; }
+        if (valid && gl == 0 && !policy_mode) {
             if (B.reward) B.reward[env] = so_rew[0];
             if (B.done) B.done[env] = (done || (trunc && la.auto_reset)) ? 1 : 0;
             if (B.truncated) B.truncated[env] = trunc ? 1 : 0;
@@ -1491,7 +1535,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
         }
         if (valid && B.terms) { if (gl < 5) B.terms[env * 5 + gl] = so_terms[gl]; }
         if (valid && B.feet_out) { if (gl < C::NFEET) B.feet_out[env * C::NFEET + gl] = S[C::oF + gl]; }
-        if (mode == MODE_STEP && finished) {
+        if (mode_eff == MODE_STEP && finished) {
             if (valid && gl == 0 && B.stats) {
                 atomicAdd(&B.stats[0], 1ull);
                 atomicAdd(&B.stats[1], (unsigned long long)__float_as_int(T[T_STEPS]));
@@ -1502,9 +1546,15 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
             if (la.auto_reset && valid && B.final_obs)
                 for (int i = gl; i < C::OBS; i += C::LPE) B.final_obs[env * C::OBS + i] = i < C::OBSNZ ? so_obs[i] : 0.f;
         }
-        want_reset = mode == MODE_STEP && finished && la.auto_reset;
+        want_reset = mode_eff == MODE_STEP && finished && la.auto_reset;
     }
     __syncwarp();
+    (void)last_step;
+  }
+    if (policy_mode && valid && gl == 0) {
+        if (B.reward) B.reward[env] = ret_acc;            // sum of the rewards of the nsteps steps
+        if (B.done) B.done[env] = any_done ? 1 : 0;       // an episode ended (and restarted) during the rollout
+    }
     if (valid) {
         if (obs) for (int i = gl; i < C::OBS; i += C::LPE) obs[i] = i < C::OBSNZ ? so_obs[i] : 0.f;
         if (store_state)

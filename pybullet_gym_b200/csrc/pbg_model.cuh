@@ -59,6 +59,14 @@ enum {
     T_CRAWL_IGN_HI = 18, T_ATTACKS = 19
 };
 
+// Two-hidden-layer ReLU policy (the shape of the reference's pretrained agents,
+// /root/reference/pybulletgym/examples/roboschool-weights/enjoy_TF_*.py): a = W3^T relu(W2^T relu(W1^T obs + b1) + b2) + b3,
+// weights row-major [in, out] in device memory
+struct PolicyDev {
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    int h1, h2;
+};
+
 struct StepBuffers {
     float *state;             // [E, SSTRIDE]
     const float *actions;     // [E, nact]
@@ -75,9 +83,10 @@ struct StepBuffers {
     unsigned long long *stats;  // [8] device episode statistics
     float *canon;             // [E, state_dim] for get/set state
     float *debug;             // development: constraint-row dump of env `debug_env`
+    PolicyDev policy;         // MODE_POLICY
 };
 
-enum { MODE_STEP = 0, MODE_PHYSICS = 1, MODE_OBSERVE = 2, MODE_RESET = 3, MODE_GET = 4, MODE_SET = 5 };
+enum { MODE_STEP = 0, MODE_PHYSICS = 1, MODE_OBSERVE = 2, MODE_RESET = 3, MODE_GET = 4, MODE_SET = 5, MODE_POLICY = 6 };
 
 struct LaunchArgs {
     int E;
@@ -86,6 +95,7 @@ struct LaunchArgs {
     int floor_in_parts;
     unsigned long long seed, env_offset;
     int debug_env;
+    int nsteps;               // MODE_POLICY: env steps per launch
 };
 
 }  // namespace pbg

@@ -138,6 +138,27 @@ class VectorEnv:
         if rc:
             _lib.check(rc, self._h)
 
+    # ------------------------------------------------------------------ fused policy rollouts
+    def set_policy(self, w1, b1, w2, b2, w3, b3):
+        """Two-hidden-layer ReLU policy, weights [in, out] (numpy / torch, any device); evaluated inside the step kernel."""
+        import numpy as np
+        arrs = [np.ascontiguousarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, dtype=np.float32)
+                for a in (w1, b1, w2, b2, w3, b3)]
+        h1, h2 = arrs[0].shape[1], arrs[2].shape[1]
+        assert arrs[0].shape == (self.obs_dim, h1) and arrs[2].shape == (h1, h2) and arrs[4].shape == (h2, self.action_dim)
+        assert arrs[1].shape == (h1,) and arrs[3].shape == (h2,) and arrs[5].shape == (self.action_dim,)
+        with torch.cuda.device(self.device):
+            rc = self._L.pbg_set_policy(self._h, h1, h2, *[C.c_void_p(a.ctypes.data) for a in arrs])
+        _lib.check(rc, self._h)
+
+    def rollout_policy(self, steps: int):
+        """`steps` env steps in one launch with the policy set by set_policy(), starting from self.obs (the observation
+        reset() / step() returned last).  Returns (obs, reward_sum[E], done_any[E])."""
+        with torch.cuda.device(self.device):
+            rc = self._L.pbg_rollout_policy(self._h, int(steps), _ptr(self.obs), _ptr(self.reward), _ptr(self.done), self._stream())
+        _lib.check(rc, self._h)
+        return self.obs, self.reward, self.done
+
     def set_zero_copy(self, enabled: bool):
         """pbg_step_host transport: kernel reads / writes pinned host buffers directly (default) or staged copies."""
         _lib.check(self._L.pbg_set_zero_copy(self._h, int(enabled)), self._h)

@@ -85,3 +85,53 @@ def test_policies_on_the_cuda_path(name, floor):
         score += alive * r; frames += alive
         alive = alive * (1 - d.float())
     assert frames.median().item() == 1000 and score.median().item() >= floor, (score.median().item(), frames.median().item())
+
+
+@pytest.mark.gpu
+def test_fused_policy_rollout_matches_stepwise_policy():
+    """pbg_rollout_policy: K env steps in one launch with the MLP evaluated inside the kernel
+    == K single-step launches of the same fused kernel (bitwise), and one fused step == torch MLP + pbg_step (fp32 tolerance)."""
+    torch = pytest.importorskip("torch")
+    from pybullet_gym_b200.vector_env import VectorEnv
+    w = dict(np.load(os.path.join(GOLD, "policy_Ant.npz")))
+    args = [w[k] for k in ("dense1_w", "dense1_b", "dense2_w", "dense2_b", "final_w", "final_b")]
+    n = 128
+    envs = [VectorEnv("AntPyBulletEnv-v0", n, device="cuda:0", seed=9, auto_reset=True) for _ in range(3)]
+    for e in envs:
+        e.set_policy(*args)
+        e.reset()
+    a, b, c = envs
+    # one fused step against torch MLP + step
+    wt = {k: torch.tensor(v, device="cuda") for k, v in w.items()}
+    ob = c.obs.clone()
+    x = torch.relu(ob @ wt["dense1_w"] + wt["dense1_b"]); x = torch.relu(x @ wt["dense2_w"] + wt["dense2_b"])
+    oc, rc, dc, _ = c.step((x @ wt["final_w"] + wt["final_b"]).contiguous())
+    oa, ra, da = a.rollout_policy(1)
+    assert (oa - oc).abs().max().item() < 2e-3 and (ra - rc).abs().max().item() < 2e-2
+    b.rollout_policy(1)
+    # 40 more steps: one launch vs 40 launches
+    oa, ra, da = a.rollout_policy(40)
+    tot = torch.zeros(n, device="cuda"); anyd = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    for t in range(40):
+        ob_, rb, db = b.rollout_policy(1)
+        tot += rb; anyd |= db
+    assert torch.equal(oa, ob_) and torch.equal(da, anyd)
+    assert (ra - tot).abs().max().item() < 1e-3            # same rewards, summed in a different order
+    assert a.stats()["steps"] == 41 * n
+
+
+@pytest.mark.gpu
+def test_hopper_policy_whole_episode_in_one_launch():
+    torch = pytest.importorskip("torch")
+    from pybullet_gym_b200.vector_env import VectorEnv
+    w = dict(np.load(os.path.join(GOLD, "policy_Hopper.npz")))
+    n = 256
+    env = VectorEnv("HopperPyBulletEnv-v0", n, device="cuda:0", seed=3, auto_reset=True)
+    env.set_policy(*[w[k] for k in ("dense1_w", "dense1_b", "dense2_w", "dense2_b", "final_w", "final_b")])
+    env.reset()
+    obs, ret, done = env.rollout_policy(1000)
+    torch.cuda.synchronize()
+    # most hoppers run the full 1000 steps (then TimeLimit restarts them); reward_threshold is 2500
+    assert ret.median().item() > 1500.0, ret.median().item()
+    st = env.stats()
+    assert st["steps"] == 1000 * n and st["episodes"] >= n // 2
