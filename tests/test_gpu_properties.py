@@ -165,3 +165,30 @@ def test_ragged_batch_sizes_match_the_big_batch(n):
         os_, rs, ds, _ = small.step(a[:n].contiguous())
         assert torch.equal(ob[:n], os_) and torch.equal(rb[:n], rs) and torch.equal(db[:n], ds)
     assert small.stats()["steps"] == 25 * n
+
+
+def test_nonfinite_action_ends_only_that_env():
+    """SURVEY 8b error contract: a NaN in one env ends that env's episode (rs/gym_locomotion_envs.py:63-65), is counted in
+    pbg_episode_stats.nonfinite, the env restarts clean, and its neighbours (same warp, same CTA) are untouched."""
+    n = 64
+    env = _mk("AntPyBulletEnv-v0", n, seed=2, auto_reset=True)
+    ref = _mk("AntPyBulletEnv-v0", n, seed=2, auto_reset=True)
+    env.reset(); ref.reset()
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    for t in range(6):
+        a = torch.rand(n, 8, device="cuda", generator=gen) * 2 - 1
+        b = a.clone()
+        if t == 3:
+            b[5, 2] = float("nan")
+        ob, rb, db, _ = env.step(b)
+        orf, rr, dr, _ = ref.step(a)
+        others = torch.ones(n, dtype=torch.bool, device="cuda"); others[5] = False
+        if t < 3:
+            assert torch.equal(ob, orf)
+        else:
+            assert torch.equal(ob[others], orf[others]) and torch.equal(rb[others], rr[others])
+        if t == 3:
+            assert db[5].item() == 1 and torch.isfinite(ob[5]).all()       # ended, and the returned obs is the fresh episode's
+        assert torch.isfinite(ob).all()
+    st = env.stats()
+    assert st["nonfinite"] == 1 and st["episodes"] >= 1
