@@ -723,7 +723,7 @@ struct Env {
             g = backsolve(g, Lm, inv);
             if (gl < C::ND) {
                 const float mv = m->maxvel;
-                u[gl] = fminf(fmaxf(u[gl] + h * g, -mv), mv);
+                { const float un = u[gl] + h * g; u[gl] = un > mv ? mv : (un < -mv ? -mv : un); }   // btClamp: a NaN stays a NaN
             }
         }
         __syncwarp();
@@ -899,7 +899,7 @@ struct Env {
         __syncwarp();
         if (gl < C::ND) {
             const float mv = m->maxvel;
-            u[gl] = fminf(fmaxf(u[gl] + g, -mv), mv);
+            { const float un = u[gl] + g; u[gl] = un > mv ? mv : (un < -mv ? -mv : un); }
         }
         __syncwarp();
         // --- semi-implicit Euler (btMultiBody::stepPositionsMultiDof)
@@ -1466,7 +1466,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
             const int j = gl - 6 * C::FLOATING;
             tq = -model->jdamp[j] * S[C::oU + gl];
             const int ai = model->jact[j];
-            if (ai >= 0) tq += model->jtorque[j] * fminf(fmaxf(act[ai], -1.f), 1.f);
+            // a non-finite action (the reference asserts on it, rs/robot_locomotors.py:27) must not be laundered into a
+            // finite torque by fminf / fmaxf: it poisons this env's state, which ends its episode as a non-finite observation
+            if (ai >= 0) { const float av = act[ai]; tq += model->jtorque[j] * (isfinite(av) ? fminf(fmaxf(av, -1.f), 1.f) : CUDART_NAN_F); }
         }
         e.tau = tq;
         const int nsub = model->nsub;
@@ -1520,7 +1522,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
         if (mode_eff == MODE_STEP) {
             if (gl == 0) {
                 T[T_STEPS] = __int_as_float(__float_as_int(T[T_STEPS]) + 1);
-                T[T_RETURN] += so_rew[0];
+                T[T_RETURN] += isfinite(so_rew[0]) ? so_rew[0] : 0.f;     // keep the episode statistics finite
             }
             __syncwarp();
             trunc = !done && __float_as_int(T[T_STEPS]) >= model->max_steps;
