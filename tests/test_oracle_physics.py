@@ -124,3 +124,94 @@ def test_random_rollouts_stay_finite(env_id, oracle_lib):
     assert n == 1500 and np.isfinite(ret)
     if SPECS[env_id].kind in (2, 3):     # hopper / walker fall quickly under random actions
         assert eps > 20
+
+
+def test_airborne_centre_of_mass_is_ballistic(oracle_lib):
+    """Internal joint torques cannot move the centre of mass: an airborne Ant keeps its horizontal COM fixed and its vertical
+    COM on the discrete ballistic curve -- exactly when nothing moves internally, and to the integrator's O(h * qdot^2)
+    momentum error under moderate random actions (link damping and joint limits off: a limit row that throws an ankle to
+    25 rad/s inside one sub-step makes that error visible, in Bullet's semi-implicit scheme as well)."""
+    rules = mj.ImporterRules(link_damping=0.0)
+    mass = None
+
+    def run(scale):
+        nonlocal mass
+        bm = mj.parse_mjcf("ant.xml", rules)
+        for l in bm.links:
+            l.lower, l.upper = 0.0, -1.0
+        env = oracle_lib.OracleEnv("AntPyBulletEnv-v0", bm=bm)
+        env.reset(noise=np.zeros(8))
+        s = env.get_state(); s[2] = 50.0; env.set_state(s)
+        mass = np.array([l.mass for l in bm.links])
+
+        def com():
+            ls = env.link_state()
+            return (mass[:, None] * ls[:, 0:3]).sum(0) / mass.sum(), (mass[:, None] * ls[:, 7:10]).sum(0) / mass.sum()
+
+        c0, _ = com()
+        rng = np.random.default_rng(2)
+        h, n, w = 0.0165 / 4, 0, np.zeros(4)
+        for t in range(40):
+            env.physics_step(scale * rng.uniform(-1, 1, 8))
+            n += 4
+            c, v = com()
+            assert env.num_contacts() == 0
+            w = np.maximum(w, [np.abs(c[:2] - c0[:2]).max(), np.abs(v[:2]).max(), abs(v[2] + 9.8 * h * n),    # v_n = -g h n
+                               abs(c[2] - (c0[2] - 9.8 * h * h * n * (n + 1) / 2))])                       # z_n = z_0 - g h^2 n (n+1) / 2
+        return w
+
+    w0 = run(0.0)
+    assert w0.max() < 1e-12, w0
+    w1 = run(0.1)                     # joint speeds up to ~3 rad/s
+    assert w1[0] < 1e-4 and w1[1] < 1e-3 and w1[2] < 1e-3 and w1[3] < 2e-4, w1
+
+
+def test_static_contact_force_equals_weight(oracle_lib):
+    """An Ant resting on its feet: the contact normal impulses average m g h per sub-step (5 PGS sweeps with a 0.1 warm start
+    leave a small jitter, so single sub-steps scatter by ~10 % around it)."""
+    import dataclasses
+    spec = SPECS["AntPyBulletEnv-v0"]
+    spec1 = dataclasses.replace(spec, scene=dataclasses.replace(spec.scene, frame_skip=1))
+    env = oracle_lib.OracleEnv(spec1)
+    env.reset(noise=np.zeros(8))
+    s0 = env.get_state()
+    s0[13 + 1], s0[13 + 3], s0[13 + 5], s0[13 + 7] = 1.0, -1.0, -1.0, 1.0
+    env.set_state(s0)
+    for _ in range(2400):
+        env.physics_step(np.zeros(8))
+    weight = sum(l.mass for l in env.model.bm.links) * 9.8 * (0.0165 / 4)
+    tot = []
+    for _ in range(400):
+        env.physics_step(np.zeros(8))
+        nl, nc, rows = env.rows()
+        assert nc >= 3
+        tot.append(rows[nl:nl + nc, 2].sum())
+    assert abs(np.mean(tot) - weight) < 0.01 * weight, (np.mean(tot), weight)
+    assert np.abs(env.get_state()[7:13]).max() < 0.05
+
+
+def test_sliding_box_decelerates_at_mu_g(oracle_lib):
+    """Coulomb friction on the cube of HumanoidFlagrunHarder (mu = 1.0 x 0.8): sliding along x on the floor it decelerates
+    uniformly with an effective coefficient between mu and 1.3 mu, then sticks.  Not exactly mu: friction shifts the load to the
+    two leading corners, and a friction row whose normal impulse has dropped to 0 is *skipped*, not reset
+    (btMultiBodyConstraintSolver::solveSingleIteration, `if (totalImpulse > 0)`), so the unloaded corners keep the friction
+    impulse they picked up in the first sweeps -- the sequential-impulse artifact is part of the restated algorithm."""
+    env = oracle_lib.OracleEnv("HumanoidFlagrunHarderPyBulletEnv-v0", bm=mj.parse_mjcf("humanoid_symmetric.xml", mj.ImporterRules(link_damping=0.0)))
+    env.reset(noise=np.zeros(17))
+    x0, v0, mu_g = 30.0, 3.0, 0.8 * 9.8
+    env.set_cube(pos=[x0, 5.0, 0.025], quat=[0, 0, 0, 1], omega=[0, 0, 0], vel=[v0, 0, 0])
+    h = 0.0165 / 4
+    vs = []
+    for t in range(40):
+        env.physics_step(np.zeros(17))
+        p, q, w, v = env.get_cube()
+        vs.append(v[0])
+    vs = np.array(vs)
+    sliding = vs > 0.2
+    dec = -np.diff(vs[sliding]) / (4 * h)              # deceleration while sliding
+    assert sliding.sum() > 10 and dec.min() > 0.99 * mu_g and dec.max() < 1.3 * mu_g, (dec, mu_g)
+    assert np.abs(dec - dec.mean()).max() < 0.02 * dec.mean()        # uniform
+    assert abs(vs[-1]) < 1e-3                          # stuck
+    dist = p[0] - x0
+    assert v0 * v0 / (2 * 1.3 * mu_g) - 0.03 < dist < v0 * v0 / (2 * mu_g) + 0.03
+    assert abs(p[2] - 0.025) < 1e-3 and abs(p[1] - 5.0) < 5e-3
