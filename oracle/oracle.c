@@ -828,6 +828,22 @@ static void solve_rows(orc_env *e, int packed) {
     for (int it = 0; it < e->m.niter; it++) {
         for (int j = 0; j < nlim; j++) { int idx = (it & 1) ? j : nlim - 1 - j; row *r = &e->rows[idx]; RESOLVE(r); }
         for (int j = 0; j < nnrm; j++) { row *r = &e->rows[nrm0 + j]; RESOLVE(r); }
+        if (e->m.friction_cone && !e->m.torsional) {
+            for (int j = fr0; j + 1 < nr; j += 2) {
+                row *ra = &e->rows[j], *rb = &e->rows[j + 1];
+                double lim = ra->mu * e->rows[ra->fric_of].lambda;
+                double ja = 0, jb = 0;
+                for (int k = 0; k < nu; k++) { ja += ra->J[k] * dv[k]; jb += rb->J[k] * dv[k]; }
+                double sa = ra->lambda + (ra->rhs - ja * ra->dinv), sb = rb->lambda + (rb->rhs - jb * rb->dinv);
+                if (sa * sa + sb * sb >= lim * lim) {
+                    double nn = sqrt(sa * sa + sb * sb), sc = nn > 0 ? (lim > 0 ? lim : 0) / nn : 0;
+                    sa *= sc; sb *= sc;
+                }
+                double da = sa - ra->lambda, db = sb - rb->lambda;
+                ra->lambda = sa; rb->lambda = sb;
+                for (int k = 0; k < nu; k++) dv[k] += ra->U[k] * da + rb->U[k] * db;
+            }
+        } else
         for (int j = fr0; j < nr; j++) {
             row *r = &e->rows[j];
             double tot = e->rows[r->fric_of].lambda;

@@ -72,6 +72,10 @@ typedef struct {
     int32_t cube;
     double cube_half, cube_mass, cube_inertia, cube_friction, cube_threshold;
     double cube_pos0[3];
+    /* friction_cone = 1: the two friction rows of a contact are solved as a pair and projected onto the circle
+     * mu * lambda_n, also when lambda_n = 0 (btMultiBodyConstraintSolver::resolveConeFrictionConstraintRows, Bullet >= 2.88);
+     * 0: independent rows with box bounds, skipped while lambda_n = 0 (the older path; the CUDA kernel's).  Oracle-only probe. */
+    int32_t friction_cone;
     /* links whose COM the task layer reads besides torso_link (Reacher: fingertip, target); -1: unused */
     int32_t aux_link[2];
 } orc_model;

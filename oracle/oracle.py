@@ -54,6 +54,7 @@ class OrcModel(C.Structure):
         ("cube", C.c_int32),
         ("cube_half", C.c_double), ("cube_mass", C.c_double), ("cube_inertia", C.c_double),
         ("cube_friction", C.c_double), ("cube_threshold", C.c_double), ("cube_pos0", C.c_double * 3),
+        ("friction_cone", C.c_int32),
         ("aux_link", C.c_int32 * 2),
     ]
 
