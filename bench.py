@@ -93,8 +93,11 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "%s, random actions, auto-reset, CPU restatement of the reference path on host cores"
-                                   % args.env},
+            "config": {"workload": "%s, %d envs/GPU, U(-1,1) actions, auto-reset, frame_skip 4 x 5 PGS iterations" % (args.env, args.envs),
+                       "envs_per_gpu": args.envs,
+                       "reference_arm": "same env / action distribution / auto-reset, stepped by the CPU restatement of the reference "
+                                        "path (oracle/, double precision) as one independent env per host thread -- pybullet itself "
+                                        "is not installable in this image; each step is a bounded sample of ~1 s of CPU work"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d env steps per thread per step x %d threads" % (per_step, cores)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
