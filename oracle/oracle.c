@@ -64,7 +64,9 @@ static void qmul(double o[4], const double a[4], const double b[4]) {
     o[0] = x; o[1] = y; o[2] = z; o[3] = w;
 }
 static void axis_angle_m(m3 m, const v3 ax, double ang) {
-    double q[4], s = sin(0.5 * ang);
+    /* btQuaternion(axis, angle) divides by the axis length: a non-unit joint axis rotates by `ang` all the
+     * same, while the motion subspace S keeps the raw axis */
+    double q[4], s = sin(0.5 * ang) / sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
     q[0] = ax[0] * s; q[1] = ax[1] * s; q[2] = ax[2] * s; q[3] = cos(0.5 * ang);
     q2m(m, q);
 }

@@ -152,7 +152,13 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
         for (int i = 0; i < 3; ++i) {
             d->anchor_p[b][i] = (float)pm->anchor_p[3 * b + i];
             d->com_off[b][i] = (float)pm->com_off[3 * b + i];
-            d->axis[b][i] = (float)pm->axis[3 * b + i];
+        }
+        {
+            // Bullet keeps a non-unit MJCF joint axis as written: rotation about its direction, motion subspace with its length
+            const double *ax = pm->axis + 3 * b;
+            const double len = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+            d->axis_len[b] = len > 0 ? (float)len : 1.f;
+            for (int i = 0; i < 3; ++i) d->axis[b][i] = len > 0 ? (float)(ax[i] / len) : 0.f;
         }
         d->mass[b] = (float)pm->mass[b];
         for (int i = 0; i < 6; ++i) d->inertia[b][i] = (float)pm->inertia[6 * b + i];

@@ -155,7 +155,7 @@ struct Env {
     int grp;            // group within the warp
     // lane-as-body constants
     int bparent, bjtype, bdepth, bdof;
-    float Q0[9], anchor_p[3], com_off[3], axis[3], bmass, Ib[6];
+    float Q0[9], anchor_p[3], com_off[3], axis[3], alen, bmass, Ib[6];
     // lane-as-body kinematics of the current pass
     float R[9];
     V3 x, w, v, al, a;
@@ -193,7 +193,7 @@ struct Env {
         for (int i = 0; i < 9; ++i) Q0[i] = m->q0m[b][i];
 #pragma unroll
         for (int i = 0; i < 3; ++i) { anchor_p[i] = m->anchor_p[b][i]; com_off[i] = m->com_off[b][i]; axis[i] = m->axis[b][i]; }
-        bmass = m->mass[b];
+        bmass = m->mass[b]; alen = m->axis_len[b];
 #pragma unroll
         for (int i = 0; i < 6; ++i) Ib[i] = m->inertia[b][i];
         const int k = gl < C::ND ? gl : 0;
@@ -237,7 +237,7 @@ struct Env {
                     const float q = S[C::oQ + bdof - 6 * C::FLOATING], qd = S[C::oU + bdof];
                     A = xp + mulR(Rp, ld3(anchor_p));
                     const V3 ax = ld3(axis);
-                    zw = mulR(Rq, ax);
+                    zw = alen * mulR(Rq, ax);       // motion subspace: the MJCF axis as written (Bullet does not normalise it)
                     const V3 rpA = A - xp;
                     if (bjtype == 1) {
                         float s, c;

@@ -24,6 +24,7 @@ struct DevModel {
     unsigned down[MJ + 6];      // per dof: dofs whose body this dof moves (descendants or self)
     unsigned anc[MB];           // per body: dofs that move the body
     float q0m[MB][9], anchor_p[MB][3], com_off[MB][3], axis[MB][3], mass[MB], inertia[MB][6];
+    float axis_len[MB];         // axis[] holds the unit direction (rotation), axis_len the length of the MJCF vector (motion subspace)
     float part_cnt[MB], part_sum[MB][3];      // robot.parts entries folded into the body: count, sum of offsets
     int ds_begin[MB + 1];                     // per-link damping entries, grouped by body
     float ds_off[MSUB][3], ds_mass[MSUB], ds_inertia[MSUB][3];

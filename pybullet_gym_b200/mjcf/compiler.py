@@ -38,7 +38,12 @@ class ImporterRules:
     """[EXT] Bullet MJCF-importer behaviours, each switchable."""
     density: float = 1000.0                 # C1.5 / C6-2: geom `density`, `settotalmass` ignored
     joint_damping_from_mjcf: bool = False   # C1.6 / C6-1: MJCF joint damping is not imported
-    normalize_joint_axes: bool = True       # C1.13 / C6-10
+    # C1.13 / C6-10: Bullet hands the MJCF axis vector to btMultiBody::setupRevolute as written.  The joint angle still
+    # rotates about the *direction* of the axis (btQuaternion(axis, angle) divides by its length), but the motion subspace
+    # -- velocities, Jacobians, the joint-space inertia -- carries the raw vector.  Non-unit axes: the Ant's ankles
+    # (-1,1,0) / (1,1,0), the Humanoid's shoulders (2,1,1) and elbows (0,-1,1).  Evidence for "raw": the reference's pretrained
+    # Ant policy scores ~2250 (reward_threshold 2500) with raw axes and ~800 with normalised ones (DESIGN.md 5a).
+    normalize_joint_axes: bool = False
     aabb_box_inertia: bool = True           # C1.9 / C6-4: inertia = box inertia of the link AABB
     inertial_frame_last_fromto: bool = True  # C1.8: COM = midpoint of the last fromto geom
     honour_axisangle: bool = True           # C6-7

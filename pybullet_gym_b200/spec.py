@@ -39,7 +39,10 @@ class SceneSpec:
     warmstarting_factor: float = 0.1
     max_coordinate_velocity: float = 100.0
     limit_max_impulse: float = 100.0
-    limit_split_impulse: bool = False   # see DESIGN.md "limit rows"
+    # btMultiBodyJointLimitConstraint with solverInfo.m_splitImpulse (default on): a limit violated by more than 0.04 rad gets
+    # its position error routed to m_rhsPenetration, which the multibody solver never applies -- the row only stops the
+    # joint from moving further out.  The pretrained Ant policy prefers this variant (2250 vs 2020).
+    limit_split_impulse: bool = True
     split_impulse_threshold: float = -0.04
     torsional_friction: bool = False     # spinning / rolling friction rows (C1.11, C6-9)
 

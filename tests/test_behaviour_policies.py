@@ -5,9 +5,10 @@ tests/golden/policy_*.npz hold the inline MLP weights of
 The scripts assert nothing; gym's registered reward_threshold is the only known-answer value the reference
 holds (pybulletgym/envs/__init__.py:8,22,77).  What we can require of a restated physics:
   * contact-free envs reach their threshold (InvertedPendulum 950, Swingup 800)
-  * Hopper, the one contact env whose policy transfers to our contact model, runs full episodes
-The other walkers' policies do not transfer to the restated contact/limit model (DESIGN.md section 5a);
-their scores are printed, not asserted -- the gap is recorded, not hidden.
+  * Hopper and Ant -- the two contact envs the reference's README calls "similar to the reference implementation" whose
+    policies transfer -- run full episodes at 85-90 % of their thresholds
+Walker2D / HalfCheetah (README: *not* similar) and the Humanoid do not transfer; their scores are
+printed, not asserted -- the gap is recorded, not hidden.
 """
 import glob
 import os
@@ -59,8 +60,16 @@ def test_hopper_policy_runs_full_episodes(oracle_lib):
     assert all(n == 1000 for _, n in res) and min(s for s, _ in res) > 1500.0, res     # reward_threshold is 2500
 
 
+def test_ant_policy_walks(oracle_lib):
+    """reward_threshold 2500.  The Ant is the sharpest probe of the restated importer rules: ~2250 with Bullet's raw
+    (non-unit) ankle axes + split-impulse limit rows, ~800 with normalised axes, ~790 with the inertial frames at the body
+    origins, ~690 at half the motor power."""
+    res = rollout(oracle_lib, "Ant", episodes=3)
+    assert all(n == 1000 for _, n in res) and min(s for s, _ in res) > 1800.0, res
+
+
 def test_report_other_policies(oracle_lib, capsys):
-    rows = {n: rollout(oracle_lib, n, episodes=2) for n in ("Walker2D", "HalfCheetah", "Ant", "Humanoid")}
+    rows = {n: rollout(oracle_lib, n, episodes=2) for n in ("Walker2D", "HalfCheetah", "Humanoid")}
     with capsys.disabled():
         for n, r in rows.items():
             print("\n  [report only] %-12s (score, frames): %s" % (n, [(round(s), k) for s, k in r]), end="")
@@ -69,7 +78,7 @@ def test_report_other_policies(oracle_lib, capsys):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,floor", [("InvertedPendulum", 950.0), ("InvertedPendulumSwingup", 800.0),
-                                        ("InvertedDoublePendulum", 9100.0), ("Hopper", 1500.0)])
+                                        ("InvertedDoublePendulum", 9100.0), ("Hopper", 1500.0), ("Ant", 1800.0)])
 def test_policies_on_the_cuda_path(name, floor):
     torch = pytest.importorskip("torch")
     from pybullet_gym_b200.vector_env import VectorEnv
