@@ -1108,16 +1108,22 @@ struct Env {
             const float progress = (float)(pot_new - pot_old);
             const float elec = m->elec_cost * (se / (float)C::NACT) + m->stall_cost * (ss / (float)C::NACT);
             const float limc = m->limit_cost * (float)nlim;
+            // A non-finite state (a rare fp32 blow-up under saturated random torques: ~3 per 10^6 Humanoid env steps, or a
+            // non-finite action) ends the episode like the reference's "~INF~" branch; its reward is reported as 0 rather
+            // than NaN so that one bad env cannot poison a learner's batch statistics.
+            if (gl == 0 && pred && !reset_pass && anybad) {
+                if (rew_out) *rew_out = 0.f;
+                if (terms_out) { terms_out[0] = terms_out[1] = terms_out[2] = terms_out[3] = terms_out[4] = 0.f; }
+                T[T_HAVEZ] = 2.f;
+            } else
             if (gl == 0 && pred && !reset_pass && mjf) {
                 // WalkerBaseMuJoCoEnv._step: [alive, progress, joints_at_limit_cost, feet_collision_cost]
                 if (rew_out) *rew_out = alive + progress + limc;
                 if (terms_out) { terms_out[0] = alive; terms_out[1] = progress; terms_out[2] = limc; terms_out[3] = 0.f; terms_out[4] = 0.f; }
-                if (anybad) T[T_HAVEZ] = 2.f;
             }
-            if (gl == 0 && pred && !reset_pass && !mjf) {
+            if (gl == 0 && pred && !reset_pass && !mjf && !anybad) {
                 if (rew_out) *rew_out = alive + progress + elec + limc;
                 if (terms_out) { terms_out[0] = alive; terms_out[1] = progress; terms_out[2] = elec; terms_out[3] = limc; terms_out[4] = 0.f; }
-                if (anybad) T[T_HAVEZ] = 2.f;      // marks a non-finite termination for the statistics
             }
         }
         __syncwarp();
@@ -1221,10 +1227,11 @@ struct Env {
             }
             if (gl == 0) {
                 if (!reset_pass) {
-                    const float pot = (float)(((double)x - (double)T[T_POT_LO]) / m->dt_scene);
-                    const float pc = -1e-3f * ss;
-                    if (rew_out) *rew_out = pot + 1.0f + pc;
-                    if (terms_out) { terms_out[0] = pot; terms_out[1] = 1.0f; terms_out[2] = pc; terms_out[3] = 0.f; terms_out[4] = 0.f; }
+                    const float pot = anybad ? 0.f : (float)(((double)x - (double)T[T_POT_LO]) / m->dt_scene);
+                    const float pc = anybad ? 0.f : -1e-3f * ss;
+                    const float al = anybad ? 0.f : 1.0f;        // a non-finite state ends the episode with reward 0
+                    if (rew_out) *rew_out = pot + al + pc;
+                    if (terms_out) { terms_out[0] = pot; terms_out[1] = al; terms_out[2] = pc; terms_out[3] = 0.f; terms_out[4] = 0.f; }
                     if (anybad) T[T_HAVEZ] = 2.f;
                 }
                 T[T_POT_LO] = x;
