@@ -36,10 +36,17 @@ def main():
         arrs = {}
         for m in re.finditer(r"^(weights_\w+)\s*=\s*np\.array\(\[(.*?)\]\)\s*$", txt, re.S | re.M):
             arrs[m.group(1)] = np.array(eval("[" + m.group(2) + "]", {"__builtins__": {}}), dtype=np.float32)
+        # the only observation pre-processing any demo applies: `ob[0] += -1.4 + 0.8` in SmallReactivePolicy.act of the Humanoid
+        # and HumanoidFlagrun demos (enjoy_TF_HumanoidPyBulletEnv_v0_2017may.py:27) -- the policies were trained with
+        # initial_z = 1.4, the env reports z - 0.8
+        shift = np.zeros(arrs["weights_dense1_w"].shape[0], dtype=np.float32)
+        m = re.search(r"ob\[0\]\s*\+=\s*(-?[\d.]+)\s*\+\s*(-?[\d.]+)", txt)
+        if m:
+            shift[0] = float(m.group(1)) + float(m.group(2))
         keys = ["weights_dense1_w", "weights_dense1_b", "weights_dense2_w", "weights_dense2_b", "weights_final_w", "weights_final_b"]
         assert all(k in arrs for k in keys), (fn, list(arrs))
         path = os.path.join(OUT, "policy_%s.npz" % env_id.split("PyBullet")[0])
-        np.savez_compressed(path, **{k[8:]: arrs[k] for k in keys})
+        np.savez_compressed(path, obs_shift=shift, **{k[8:]: arrs[k] for k in keys})
         print(env_id, [arrs[k].shape for k in keys[::2]], "->", os.path.basename(path), os.path.getsize(path) // 1024, "KB")
 
 
