@@ -139,11 +139,16 @@ class VectorEnv:
             _lib.check(rc, self._h)
 
     # ------------------------------------------------------------------ fused policy rollouts
-    def set_policy(self, w1, b1, w2, b2, w3, b3):
-        """Two-hidden-layer ReLU policy, weights [in, out] (numpy / torch, any device); evaluated inside the step kernel."""
+    def set_policy(self, w1, b1, w2, b2, w3, b3, obs_shift=None):
+        """Two-hidden-layer ReLU policy, weights [in, out] (numpy / torch, any device); evaluated inside the step kernel.
+        obs_shift: optional constant added to the observation first (the reference's Humanoid demos do `ob[0] += -0.6`);
+        it is folded into the first bias."""
         import numpy as np
         arrs = [np.ascontiguousarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, dtype=np.float32)
                 for a in (w1, b1, w2, b2, w3, b3)]
+        if obs_shift is not None:
+            sh = np.asarray(obs_shift.detach().cpu().numpy() if isinstance(obs_shift, torch.Tensor) else obs_shift, dtype=np.float64)
+            arrs[1] = (arrs[1].astype(np.float64) + sh @ arrs[0].astype(np.float64)).astype(np.float32)
         h1, h2 = arrs[0].shape[1], arrs[2].shape[1]
         assert arrs[0].shape == (self.obs_dim, h1) and arrs[2].shape == (h1, h2) and arrs[4].shape == (h2, self.action_dim)
         assert arrs[1].shape == (h1,) and arrs[3].shape == (h2,) and arrs[5].shape == (self.action_dim,)

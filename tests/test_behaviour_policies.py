@@ -153,3 +153,19 @@ def test_hopper_policy_whole_episode_in_one_launch():
     assert ret.median().item() > 1500.0, ret.median().item()
     st = env.stats()
     assert st["steps"] == 1000 * n and st["episodes"] >= n // 2
+
+
+@pytest.mark.gpu
+def test_humanoid_policy_fused_rollout():
+    """The Humanoid policy (with its demo's observation offset folded into the first bias) evaluated inside the step kernel:
+    500 steps in one launch, most humanoids are still walking."""
+    torch = pytest.importorskip("torch")
+    from pybullet_gym_b200.vector_env import VectorEnv
+    w = dict(np.load(os.path.join(GOLD, "policy_Humanoid.npz")))
+    n = 256
+    env = VectorEnv("HumanoidPyBulletEnv-v0", n, device="cuda:0", seed=3, auto_reset=True)
+    env.set_policy(*[w[k] for k in ("dense1_w", "dense1_b", "dense2_w", "dense2_b", "final_w", "final_b")], obs_shift=w["obs_shift"])
+    env.reset()
+    obs, ret, done = env.rollout_policy(500)
+    assert ret.median().item() > 1200.0, ret.median().item()         # ~3.4 per step while walking
+    assert (done == 0).float().mean().item() > 0.5                    # more than half never fell
