@@ -1,8 +1,11 @@
 import numpy as np, glob, os, dataclasses, sys, itertools
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from oracle.oracle import OracleEnv
 from pybullet_gym_b200.spec import SPECS
 from pybullet_gym_b200.mjcf import compiler as mj
 def act(w, ob):
+    ob=ob+w["obs_shift"]      # the Humanoid demos' `ob[0] += -1.4 + 0.8` (tools/extract_policy_weights.py)
     x=np.maximum(ob@w["dense1_w"]+w["dense1_b"],0); x=np.maximum(x@w["dense2_w"]+w["dense2_b"],0); return x@w["final_w"]+w["final_b"]
 def run(name, rules=None, scene_kw=None, eps=2, T=1000):
     eid=name+"PyBulletEnv-v0"; w=np.load("tests/golden/policy_%s.npz"%name)
