@@ -184,6 +184,10 @@ class ModelTables:
         for name, arr in k.items():
             setattr(m, name, arr.ctypes.data_as(_pd if arr.dtype == np.float64 else _pi))
         sc = spec.scene
+        if sc.torsional_friction:
+            # spinning / rolling friction rows exist in the CPU oracle only (a probe for pin C6-9); refusing is better than
+            # silently stepping a different contact model on the GPU
+            raise NotImplementedError("SceneSpec.torsional_friction is an oracle-only probe; the CUDA path has no torsional rows")
         m.gravity, m.timestep, m.frame_skip, m.num_solver_iterations = sc.gravity, sc.timestep, sc.frame_skip, sc.num_solver_iterations
         m.contact_erp, m.erp, m.linear_slop, m.warmstarting_factor = sc.contact_erp, sc.erp, sc.linear_slop, sc.warmstarting_factor
         m.link_damping, m.max_coordinate_velocity = rm.link_damping, sc.max_coordinate_velocity
