@@ -185,7 +185,10 @@ class FakeBulletClient:
     # ---- state queries
     def getJointState(self, body, j):
         self._count("getJointState")
-        q, qd = self.orc.get_joint(self.dof_of_link[self._li(body, j)])
+        li = self._li(body, j)
+        if li not in self.dof_of_link:         # fixed joint (jointfix_*): pybullet reports zeros
+            return (0.0, 0.0, (0,) * 6, 0.0)
+        q, qd = self.orc.get_joint(self.dof_of_link[li])
         return (q, qd, (0,) * 6, 0.0)
 
     def _link(self, idx):
@@ -222,10 +225,25 @@ class FakeBulletClient:
         ang = tuple(self.orc.get_state()[7:10]) if self.bm.floating else (0.0, 0.0, 0.0)    # base angular velocity
         return tuple(s[7:10]), ang
 
+    def getDynamicsInfo(self, body, link):
+        """(mass, lateral_friction, local_inertia_diagonal, local_inertial_pos, local_inertial_orn, restitution, rolling_friction,
+        spinning_friction, contact_damping, contact_stiffness, body_type, collision_margin) of the Bullet-shaped link list"""
+        l = self.bm.links[0 if link < 0 else self._li(body, link)]
+        fr = l.geoms[0].friction if l.geoms else 0.5
+        return (l.mass, fr, tuple(l.inertia), tuple(l.com), (0.0, 0.0, 0.0, 1.0), 0.0, 0.0, 0.0, -1.0, -1.0, 2, 0.0)
+
+    def getPhysicsEngineParameters(self):
+        return dict(self.engine)
+
     def getContactPoints(self, bodyA=-1, bodyB=-1, linkIndexA=-2, linkIndexB=-2):
         self._count("getContactPoints")
         la, lb, dist = self.orc.contacts()
         out = []
+        if linkIndexA == -2:      # every contact point of the body (tools/pin_pybullet.py)
+            for a, b_, d in zip(la, lb, dist):
+                out.append((0, bodyA, self.floor_id if b_ == -1 else bodyA, int(a) - 1, int(b_) - 1 if b_ >= 0 else -1,
+                            (0, 0, 0), (0, 0, 0), (0, 0, 1), d, 0.0))
+            return tuple(out)
         for a, b, d in zip(la, lb, dist):
             if bodyA == self.robot_id and a - 1 == linkIndexA:
                 if b == -2:      # the cube (oracle.c LINK_CUBE)
