@@ -68,6 +68,7 @@ def main():
     ap.add_argument("--gamma", type=float, default=0.99)
     ap.add_argument("--lam", type=float, default=0.95)
     ap.add_argument("--clip", type=float, default=0.2)
+    ap.add_argument("--ent", type=float, default=0.0, help="entropy bonus coefficient")
     ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args()
     torch.manual_seed(a.seed)
@@ -117,7 +118,7 @@ def main():
                 ratio = (lp - flp[mb]).exp()
                 pl = -torch.min(ratio * fadv[mb], ratio.clamp(1 - a.clip, 1 + a.clip) * fadv[mb]).mean()
                 vl = 0.5 * (net.v(fo[mb]).squeeze(-1) - fret[mb]).pow(2).mean()
-                loss = pl + 0.5 * vl - 0.0 * d.entropy().sum(-1).mean()
+                loss = pl + 0.5 * vl - a.ent * d.entropy().sum(-1).mean()
                 opt.zero_grad(set_to_none=True)
                 loss.backward()
                 nn.utils.clip_grad_norm_(net.parameters(), 0.5)
