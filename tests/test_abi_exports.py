@@ -60,3 +60,31 @@ def test_unbacked_ids_raise():
     assert "AntPyBulletEnv-v0" in registry and registry["AntPyBulletEnv-v0"]["max_episode_steps"] == 1000
     with pytest.raises(NotImplementedError):
         make("PusherPyBulletEnv-v0")
+
+
+def test_argument_errors_need_no_device():
+    """include/pbg.h error contract: bad arguments are rejected with PBG_ERR_INVALID / PBG_ERR_UNSUPPORTED before any CUDA
+    call, NULL handles are errors and never dereferenced."""
+    from pybullet_gym_b200 import _lib
+    from pybullet_gym_b200.spec import SPECS
+    L = _lib.lib()
+    t = _lib.ModelTables(SPECS["HopperPyBulletEnv-v0"])
+    h = ctypes.c_void_p()
+    assert L.pbg_create(None, 8, 0, 0, 0, ctypes.byref(h)) == -1
+    assert L.pbg_create(ctypes.byref(t.c), 8, 0, 0, 0, None) == -1
+    for n in (0, -5):
+        assert L.pbg_create(ctypes.byref(t.c), n, 0, 0, 0, ctypes.byref(h)) == -1
+        assert b"bad arguments" in L.pbg_last_error(None)
+    kind = t.c.kind
+    t.c.kind = 99
+    assert L.pbg_create(ctypes.byref(t.c), 8, 0, 0, 0, ctypes.byref(h)) == -3            # PBG_ERR_UNSUPPORTED
+    t.c.kind = kind
+    for f in (L.pbg_num_envs, L.pbg_obs_dim, L.pbg_action_dim, L.pbg_state_dim, L.pbg_noise_dim, L.pbg_last_host_path):
+        assert f(None) == -1
+    null = ctypes.c_void_p()
+    assert L.pbg_step(None, null, null, null, null, null, null, null, null) == -1
+    assert L.pbg_step_host(None, null, null, null, null) == -1
+    assert L.pbg_reset(None, null, 0, null, null) == -1
+    assert L.pbg_rollout_policy(None, 4, null, null, null, null) == -1
+    assert L.pbg_stats(None, None, 0, null) == -1
+    L.pbg_destroy(None)                                                                   # a no-op, not a crash

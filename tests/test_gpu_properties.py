@@ -192,3 +192,35 @@ def test_nonfinite_action_ends_only_that_env():
         assert torch.isfinite(ob).all()
     st = env.stats()
     assert st["nonfinite"] == 1 and st["episodes"] >= 1
+
+
+def test_error_contract_on_a_live_handle():
+    """Bad calls on a live handle return an error (raised as PbgError / ValueError by the host mirror) and leave the handle
+    usable: the next good step is bit-identical to an undisturbed twin's."""
+    import ctypes
+    from pybullet_gym_b200 import _lib
+    env = _mk("HopperPyBulletEnv-v0", 64, seed=3)
+    twin = _mk("HopperPyBulletEnv-v0", 64, seed=3)
+    env.reset(); twin.reset()
+    L, h = env._L, env._h
+    null = ctypes.c_void_p()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(64, 4, device="cuda"))                     # wrong action width
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(63, 3, device="cuda"))                     # wrong batch
+    with pytest.raises(ValueError):
+        env.reset(joint_noise=torch.zeros(64, 2, device="cuda"))
+    assert L.pbg_step(h, null, null, null, null, null, null, null, null) == -1 and b"actions_dev" in L.pbg_last_error(h)
+    assert L.pbg_step_host(h, null, null, null, null) == -1
+    with pytest.raises(_lib.PbgError, match="no policy set"):
+        env.rollout_policy(4)
+    big = np.zeros((15, 4096), np.float32)
+    with pytest.raises(_lib.PbgError, match="do not fit"):
+        env.set_policy(big, np.zeros(4096, np.float32), np.zeros((4096, 64), np.float32), np.zeros(64, np.float32),
+                       np.zeros((64, 3), np.float32), np.zeros(3, np.float32))
+    with pytest.raises(_lib.PbgError):
+        env.rollout_policy(0)
+    a = torch.rand(64, 3, device="cuda") * 2 - 1
+    o1, r1, d1, _ = env.step(a)
+    o2, r2, d2, _ = twin.step(a)
+    assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
