@@ -188,6 +188,16 @@ int pbg_set_auto_reset(pbg_handle *h, int32_t enabled);
  * rs/robot_bases.py:233-275,323-356).  float[num_envs, pbg_state_dim]. */
 int pbg_get_state(pbg_handle *h, float *state_dev, void *stream);
 int pbg_set_state(pbg_handle *h, const float *state_dev, void *stream);
+/* Whole-handle snapshot: every env's physics state, warm-start impulses, task bookkeeping (potential, episode step and
+ * episode counters that drive the reset RNG, targets, cube) and the episode statistics -- what pybullet's saveState /
+ * restoreState (rs/gym_pendulum_envs.py:20-27) plus a pickle of the env object would hold.  pbg_restore into the same
+ * handle, or another handle created with the same model, num_envs, seed and env_offset, resumes bit-identically.
+ * `buf` may be device or (pinned or pageable) host memory of pbg_snapshot_bytes(h) bytes; the copy is ordered on `stream`
+ * (pageable host memory makes it synchronous).  The blob is opaque and only valid for this library version. */
+int64_t pbg_snapshot_bytes(const pbg_handle *h);
+int pbg_snapshot(pbg_handle *h, void *buf, void *stream);
+int pbg_restore(pbg_handle *h, const void *buf, void *stream);
+
 /* Physics only (apply_action + stepSimulation), no task bookkeeping; for single-step parity tests. */
 int pbg_physics_step(pbg_handle *h, const float *actions_dev, void *stream);
 /* calc_state + reward of the current state without physics (uses the given actions for the

@@ -133,6 +133,10 @@ def lib():
     L.pbg_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     L.pbg_launch_count.argtypes = [vp]
     L.pbg_launch_count.restype = C.c_int64
+    L.pbg_snapshot_bytes.argtypes = [vp]
+    L.pbg_snapshot_bytes.restype = C.c_int64
+    L.pbg_snapshot.argtypes = [vp, vp, vp]
+    L.pbg_restore.argtypes = [vp, vp, vp]
     _lib = L
     return L
 
@@ -140,7 +144,8 @@ def lib():
 EXPORTS = ["pbg_version", "pbg_create", "pbg_destroy", "pbg_last_error", "pbg_num_envs", "pbg_obs_dim",
            "pbg_action_dim", "pbg_state_dim", "pbg_noise_dim", "pbg_reset", "pbg_reset_with", "pbg_step", "pbg_step_host",
            "pbg_set_auto_reset", "pbg_set_zero_copy", "pbg_last_host_path", "pbg_set_policy", "pbg_rollout_policy", "pbg_get_state", "pbg_set_state", "pbg_physics_step", "pbg_physics_step_counts",
-           "pbg_max_contacts", "pbg_measure_fp32_peak", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count"]
+           "pbg_max_contacts", "pbg_measure_fp32_peak", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count",
+           "pbg_snapshot_bytes", "pbg_snapshot", "pbg_restore"]
 
 
 def _d(a):

@@ -81,6 +81,7 @@ static bool kernel_for_kind(int kind, KernelInfo *out) {
 struct pbg_handle {
     int device = 0;
     int E = 0;
+    int kind = 0;
     KernelInfo k{};
     DevModel *dmodel = nullptr;
     float *state = nullptr;
@@ -361,7 +362,7 @@ int pbg_create(const pbg_model *model, int32_t num_envs, int32_t device, uint64_
     std::string e = build_dev_model(model, k, &hm);
     if (!e.empty()) return fail(nullptr, PBG_ERR_INVALID, "pbg_create: " + e);
     pbg_handle *h = new pbg_handle();
-    h->device = device; h->E = num_envs; h->k = k; h->seed = seed; h->env_offset = env_offset;
+    h->device = device; h->E = num_envs; h->kind = model->kind; h->k = k; h->seed = seed; h->env_offset = env_offset;
 #define CREATE_TRY(expr)                                                                  \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \
@@ -539,6 +540,49 @@ int pbg_set_state(pbg_handle *h, const float *state_dev, void *stream) {
     StepBuffers b{};
     b.canon = const_cast<float *>(state_dev);
     return launch(h, MODE_SET, b, 1, stream);
+}
+
+static const uint32_t SNAP_MAGIC = 0x50424753u;   // "PBGS"
+struct SnapHeader { uint32_t magic, version; int32_t kind, E, sstride, pad; unsigned long long seed, env_offset; int64_t steps; };
+
+int64_t pbg_snapshot_bytes(const pbg_handle *h) {
+    if (!h) return PBG_ERR_INVALID;
+    return int64_t(sizeof(SnapHeader)) + int64_t(h->E) * h->k.sstride * sizeof(float) + 8 * sizeof(unsigned long long);
+}
+
+int pbg_snapshot(pbg_handle *h, void *buf, void *stream) {
+    if (!h || !buf) return fail(h, PBG_ERR_INVALID, "pbg_snapshot: NULL buffer");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SnapHeader hd{SNAP_MAGIC, (uint32_t)pbg_version(), h->kind, h->E, h->k.sstride, 0, h->seed, h->env_offset, h->steps};
+    const size_t sb = size_t(h->E) * h->k.sstride * sizeof(float);
+    char *p = static_cast<char *>(buf);
+    CUDA_TRY(h, cudaMemcpyAsync(p, &hd, sizeof hd, cudaMemcpyDefault, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));       // hd lives on this stack frame
+    CUDA_TRY(h, cudaMemcpyAsync(p + sizeof hd, h->state, sb, cudaMemcpyDefault, st));
+    CUDA_TRY(h, cudaMemcpyAsync(p + sizeof hd + sb, h->stats, 8 * sizeof(unsigned long long), cudaMemcpyDefault, st));
+    return PBG_OK;
+}
+
+int pbg_restore(pbg_handle *h, const void *buf, void *stream) {
+    if (!h || !buf) return fail(h, PBG_ERR_INVALID, "pbg_restore: NULL buffer");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SnapHeader hd{};
+    const char *p = static_cast<const char *>(buf);
+    CUDA_TRY(h, cudaMemcpyAsync(&hd, p, sizeof hd, cudaMemcpyDefault, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    if (hd.magic != SNAP_MAGIC || hd.version != (uint32_t)pbg_version())
+        return fail(h, PBG_ERR_INVALID, "pbg_restore: not a snapshot of this library version");
+    if (hd.kind != h->kind || hd.E != h->E || hd.sstride != h->k.sstride)
+        return fail(h, PBG_ERR_INVALID, "pbg_restore: snapshot of a different env kind or batch size");
+    if (hd.seed != h->seed || hd.env_offset != h->env_offset)
+        return fail(h, PBG_ERR_INVALID, "pbg_restore: snapshot of a handle with another seed / env_offset (its reset RNG streams differ)");
+    const size_t sb = size_t(h->E) * h->k.sstride * sizeof(float);
+    CUDA_TRY(h, cudaMemcpyAsync(h->state, p + sizeof hd, sb, cudaMemcpyDefault, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h->stats, p + sizeof hd + sb, 8 * sizeof(unsigned long long), cudaMemcpyDefault, st));
+    h->steps = hd.steps;
+    return PBG_OK;
 }
 
 int pbg_physics_step(pbg_handle *h, const float *actions_dev, void *stream) {

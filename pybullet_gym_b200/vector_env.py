@@ -184,6 +184,27 @@ class VectorEnv:
         with torch.cuda.device(self.device):
             _lib.check(self._L.pbg_set_state(self._h, _ptr(s), self._stream()), self._h)
 
+    def snapshot(self, pinned_host: bool = False) -> torch.Tensor:
+        """Opaque uint8 blob with the whole handle state (pbg_snapshot): physics, warm start, task bookkeeping, reset-RNG
+        counters, episode statistics.  On the device by default, in pinned host memory on request."""
+        n = int(self._L.pbg_snapshot_bytes(self._h))
+        buf = (torch.empty(n, dtype=torch.uint8).pin_memory() if pinned_host
+               else torch.empty(n, dtype=torch.uint8, device=self.device))
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pbg_snapshot(self._h, _ptr(buf), self._stream()), self._h)
+            if pinned_host:
+                torch.cuda.current_stream(self.device).synchronize()
+        return buf
+
+    def restore(self, blob: torch.Tensor, first_reset_done: bool = True):
+        """Resume bit-identically from snapshot(); the blob may come from another VectorEnv of the same env id, batch size,
+        seed and env_offset.  The observation / reward buffers are not part of it: call observe() or step()."""
+        if blob.dtype != torch.uint8 or not blob.is_contiguous() or blob.numel() != int(self._L.pbg_snapshot_bytes(self._h)):
+            raise ValueError("not a snapshot of this env (size %d expected)" % int(self._L.pbg_snapshot_bytes(self._h)))
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pbg_restore(self._h, _ptr(blob), self._stream()), self._h)
+        self._first_reset_done = bool(first_reset_done)    # host-side quirk flag Q1 (floor in robot.parts), not in the blob
+
     def physics_step(self, actions: torch.Tensor, want_contacts: bool = False):
         a = self._act(actions)
         with torch.cuda.device(self.device):

@@ -86,5 +86,6 @@ def test_argument_errors_need_no_device():
     assert L.pbg_step_host(None, null, null, null, null) == -1
     assert L.pbg_reset(None, null, 0, null, null) == -1
     assert L.pbg_rollout_policy(None, 4, null, null, null, null) == -1
-    assert L.pbg_stats(None, None, 0, null) == -1
+    assert L.pbg_stats(None, None, 0) == -1
+    assert L.pbg_snapshot_bytes(None) == -1 and L.pbg_snapshot(None, null, null) == -1 and L.pbg_restore(None, null, null) == -1
     L.pbg_destroy(None)                                                                   # a no-op, not a crash

@@ -224,3 +224,36 @@ def test_error_contract_on_a_live_handle():
     o1, r1, d1, _ = env.step(a)
     o2, r2, d2, _ = twin.step(a)
     assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+
+
+@pytest.mark.parametrize("env_id", ["AntPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0", "InvertedPendulumPyBulletEnv-v0"])
+def test_snapshot_restore_resumes_bit_identically(env_id):
+    """pbg_snapshot / pbg_restore (the reference's saveState / restoreState, rs/gym_pendulum_envs.py:20-27): the continuation
+    after a restore -- auto-resets and their RNG draws, targets, the thrown cube included -- repeats the original bit for bit, in
+    the same handle and in a fresh one, from a device blob and from a pinned-host blob; a wrong blob is refused."""
+    from pybullet_gym_b200 import _lib
+    n = 256
+    env = _mk(env_id, n, seed=13, auto_reset=True)
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    acts = [torch.rand(n, env.action_dim, device="cuda", generator=gen) * 2 - 1 for _ in range(90)]
+    for a in acts[:30]:
+        env.step(a)
+    blob_d, blob_h = env.snapshot(), env.snapshot(pinned_host=True)
+    stats0 = env.stats()
+    first = [tuple(x.clone() for x in env.step(a)[:3]) for a in acts[30:]]
+    assert sum(int(d.sum()) for _, _, d in first) > 0 or env_id.startswith("Ant")      # resets happen inside the window
+    stats1 = env.stats()
+    fresh = _mk(env_id, n, seed=13, auto_reset=True)
+    for target, blob in ((env, blob_d), (fresh, blob_h)):
+        target.restore(blob)
+        assert target.stats() == stats0
+        for a, (o, r, d) in zip(acts[30:], first):
+            o2, r2, d2, _ = target.step(a)
+            assert torch.equal(o, o2) and torch.equal(r, r2) and torch.equal(d, d2)
+        assert target.stats() == stats1
+    other = _mk(env_id, n, seed=14)
+    with pytest.raises(_lib.PbgError, match="seed"):
+        other.restore(blob_d)
+    with pytest.raises(ValueError):
+        _mk(env_id, n // 2, seed=13).restore(blob_d)
