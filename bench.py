@@ -271,7 +271,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "episodes": {"finished": stats["episodes"], "mean_len": stats["length_sum"] / max(1, stats["episodes"]),
-                         "mean_return": stats["return_sum"] / max(1, stats["episodes"])},
+                         "mean_return": stats["return_sum"] / max(1, stats["episodes"]),
+                         "resets_per_env_step": stats["episodes"] / max(1, stats["steps"])},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.env, args.cpu_seconds)
