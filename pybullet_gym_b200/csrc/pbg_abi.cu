@@ -98,7 +98,6 @@ struct pbg_handle {
     int zero_copy = 1;          // pbg_step_host: let the kernel read / write mapped pinned host buffers directly
     int last_host_path = 0;     // 1: zero-copy, 2: staged copies
     int64_t launches = 0;
-    int64_t steps = 0;
     std::string err;
 };
 
@@ -448,7 +447,6 @@ int pbg_step(pbg_handle *h, const float *actions_dev, float *obs_dev, float *rew
     StepBuffers b{};
     b.actions = actions_dev; b.obs = obs_dev; b.reward = reward_dev; b.done = done_dev; b.terms = reward_terms_dev;
     b.final_obs = final_obs_dev; b.truncated = truncated_dev;
-    h->steps += h->E;
     return launch(h, MODE_STEP, b, 1, stream);
 }
 
@@ -524,7 +522,6 @@ int pbg_rollout_policy(pbg_handle *h, int32_t nsteps, float *obs_dev, float *rew
     if (!h->policy_buf) return fail(h, PBG_ERR_INVALID, "pbg_rollout_policy: no policy set (pbg_set_policy)");
     StepBuffers b{};
     b.obs = obs_dev; b.reward = reward_sum_dev; b.done = done_any_dev;
-    h->steps += int64_t(h->E) * nsteps;
     return launch(h, 100 + nsteps, b, 1, stream);
 }
 
@@ -543,7 +540,7 @@ int pbg_set_state(pbg_handle *h, const float *state_dev, void *stream) {
 }
 
 static const uint32_t SNAP_MAGIC = 0x50424753u;   // "PBGS"
-struct SnapHeader { uint32_t magic, version; int32_t kind, E, sstride, pad; unsigned long long seed, env_offset; int64_t steps; };
+struct SnapHeader { uint32_t magic, version; int32_t kind, E, sstride, pad; unsigned long long seed, env_offset; };
 
 int64_t pbg_snapshot_bytes(const pbg_handle *h) {
     if (!h) return PBG_ERR_INVALID;
@@ -554,7 +551,7 @@ int pbg_snapshot(pbg_handle *h, void *buf, void *stream) {
     if (!h || !buf) return fail(h, PBG_ERR_INVALID, "pbg_snapshot: NULL buffer");
     CUDA_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    SnapHeader hd{SNAP_MAGIC, (uint32_t)pbg_version(), h->kind, h->E, h->k.sstride, 0, h->seed, h->env_offset, h->steps};
+    SnapHeader hd{SNAP_MAGIC, (uint32_t)pbg_version(), h->kind, h->E, h->k.sstride, 0, h->seed, h->env_offset};
     const size_t sb = size_t(h->E) * h->k.sstride * sizeof(float);
     char *p = static_cast<char *>(buf);
     CUDA_TRY(h, cudaMemcpyAsync(p, &hd, sizeof hd, cudaMemcpyDefault, st));
@@ -581,7 +578,6 @@ int pbg_restore(pbg_handle *h, const void *buf, void *stream) {
     const size_t sb = size_t(h->E) * h->k.sstride * sizeof(float);
     CUDA_TRY(h, cudaMemcpyAsync(h->state, p + sizeof hd, sb, cudaMemcpyDefault, st));
     CUDA_TRY(h, cudaMemcpyAsync(h->stats, p + sizeof hd + sb, 8 * sizeof(unsigned long long), cudaMemcpyDefault, st));
-    h->steps = hd.steps;
     return PBG_OK;
 }
 
@@ -690,8 +686,8 @@ int pbg_stats(pbg_handle *h, pbg_episode_stats *out, int32_t reset) {
     memcpy(&out->return_sum, &raw[2], sizeof(double));
     out->truncated = (int64_t)raw[3];
     out->nonfinite = (int64_t)raw[4];
-    out->steps = h->steps;
-    if (reset) { CUDA_TRY(h, cudaMemset(h->stats, 0, sizeof raw)); h->steps = 0; }
+    out->steps = (int64_t)raw[5];
+    if (reset) CUDA_TRY(h, cudaMemset(h->stats, 0, sizeof raw));
     return PBG_OK;
 }
 

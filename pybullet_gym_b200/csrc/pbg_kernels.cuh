@@ -1560,6 +1560,11 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     __syncwarp();
     (void)last_step;
   }
+    if (threadIdx.x == 0 && B.stats && mode_eff == MODE_STEP) {
+        // env steps taken, counted on the device so that CUDA-graph replays of pbg_step count too
+        const long long nv = (long long)la.E - (long long)blockIdx.x * C::EPB;
+        if (nv > 0) atomicAdd(&B.stats[5], (unsigned long long)(nv < C::EPB ? nv : C::EPB) * (unsigned long long)nsteps);
+    }
     if (policy_mode && valid && gl == 0) {
         if (B.reward) B.reward[env] = ret_acc;            // sum of the rewards of the nsteps steps
         if (B.done) B.done[env] = any_done ? 1 : 0;       // an episode ended (and restarted) during the rollout

@@ -286,3 +286,36 @@ def test_state_invariants_and_get_set_idempotence(env_id, n):
     assert same.float().mean().item() > 0.999
     err = (o1[same] - o2[same]).abs().flatten()
     assert err.median().item() < 1e-3 and torch.quantile(err[:1000000].float(), 0.99).item() < 5e-2
+
+
+@pytest.mark.parametrize("env_id", ["InvertedPendulumPyBulletEnv-v0", "AntPyBulletEnv-v0"])
+def test_steps_capture_into_a_cuda_graph(env_id):
+    """pbg_step enqueues exactly one kernel on the caller's stream (no allocation, no synchronisation), so a block of steps can
+    be captured into a CUDA graph -- what makes the launch-bound pendulum envs fast (tools/graph_probe.py).  The replay is
+    bit-identical to eager stepping and the device-side statistics (env steps, episodes) keep counting."""
+    n, K = 512, 24
+    eager = _mk(env_id, n, seed=1, auto_reset=True)
+    graphed = _mk(env_id, n, seed=1, auto_reset=True)
+    eager.reset(); graphed.reset()
+    acts = torch.rand(K, n, eager.action_dim, device="cuda") * 2 - 1
+    log_o = torch.empty(K, n, eager.obs_dim, device="cuda"); log_r = torch.empty(K, n, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        snap = graphed.snapshot()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for k in range(K):
+                o, r, d = graphed.step_fast(acts[k])
+                log_o[k].copy_(o); log_r[k].copy_(r)
+        graphed.restore(snap)
+        graphed.stats(reset=True)
+        for rep in range(2):
+            g.replay()
+            torch.cuda.synchronize()
+            for k in range(K):
+                o, r, d = eager.step_fast(acts[k])
+                assert torch.equal(o, log_o[k]) and torch.equal(r, log_r[k]), (rep, k)
+    st_g, st_e = graphed.stats(), eager.stats()
+    assert st_g["steps"] == 2 * K * n
+    assert st_g["episodes"] == st_e["episodes"] and st_g["length_sum"] == st_e["length_sum"]
