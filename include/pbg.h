@@ -14,6 +14,10 @@
  *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are asynchronous and
  *     ordered by the stream, except the *_host entry points, which synchronise before returning.
  *   - a handle is bound to one device and is not thread-safe.  Multi-GPU = one handle per device.
+ *     Every call makes the handle's device the calling thread's current CUDA device (cudaSetDevice) and leaves it so.
+ *   - the stream-ordered entry points (pbg_reset*, pbg_step, pbg_physics_step*, pbg_observe, pbg_rollout_policy,
+ *     pbg_get_state / pbg_set_state, pbg_get_feet_contact) enqueue kernels only -- no allocation, no synchronisation, all
+ *     counters on the device -- and may be recorded into a CUDA graph (cudaStreamBeginCapture) and replayed.
  */
 #ifndef PBG_H
 #define PBG_H
