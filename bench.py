@@ -254,8 +254,8 @@ def run_ours(args):
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
             "value_l2_resident": world * E * K / t_resident,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": (1.71e6 if (args.env == ENV_ID and E == 4096) else None),
-                         "traffic_source": "dram__bytes_read+write per launch, ncu --set full, profiles/r01b_ant_step_kernel_ncu.md",
+                         "traffic": (1.72e6 if (args.env == ENV_ID and E == 4096) else None),
+                         "traffic_source": "dram__bytes_read+write per launch, ncu --set full, profiles/r01c_ant_step_kernel_ncu.md",
                          "peak_source": peak_src,
                          "note": "latency/issue-bound FP32 small-matrix kernel: the HBM fraction is reported because the "
                                  "schema asks for it; the meaningful ceiling is fp32 below",

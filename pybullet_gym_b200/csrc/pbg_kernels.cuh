@@ -78,7 +78,10 @@ struct KCfg {
     static constexpr int sCOL = (sF + NDP + 3) / 4 * 4;
     static constexpr int G1 = sCOL + 2 * (NDP + 4) - sU;
     static constexpr int sA = sU;
-    static constexpr int ENV_FLOATS = (sU + (G1 > MAXRP * MAXRP + 2 * LPE ? G1 : MAXRP * MAXRP + 2 * LPE) + 3) / 4 * 4;
+    static constexpr int ENV_FLOATS_RAW = (sU + (G1 > MAXRP * MAXRP + 2 * LPE ? G1 : MAXRP * MAXRP + 2 * LPE) + 3) / 4 * 4;
+    // two envs per warp: place the second env's block 16 banks away from the first one's (stride = 16 mod 32), so that the two
+    // half-warps never collide, neither on env-uniform (broadcast) nor on lane-indexed shared-memory accesses
+    static constexpr int ENV_FLOATS = LPE == 16 ? ENV_FLOATS_RAW + ((48 - ENV_FLOATS_RAW % 32) % 32) : ENV_FLOATS_RAW;
     static constexpr size_t SMEM_BYTES = size_t(ENV_FLOATS) * EPB * sizeof(float);
     static constexpr int HIDCAP = ENV_FLOATS - sU;             // room for the fused policy's hidden activations
 };
