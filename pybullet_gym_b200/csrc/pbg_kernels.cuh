@@ -323,6 +323,13 @@ struct Env {
                     const V3 xb = ld3(kb + 9);
                     const V3 a0 = mulRt(kb, p1 - xb), dd = mulRt(kb, q1 - xb) - a0;
                     const float hh = m->p_b0[pi][0];
+                    // cheap exact reject: the box lies inside the sphere of radius sqrt(3) hh around its centre, so the
+                    // segment-box distance is at least (segment-centre distance) - sqrt(3) hh.  While the cube is away from
+                    // the robot (most of an episode) no lane of the warp enters the bisection.
+                    const float dd2 = dot(dd, dd);
+                    const V3 xc = a0 + (dd2 > 0.f ? __saturatef(-dot(a0, dd) / dd2) : 0.f) * dd;
+                    const bool near = sqrtf(dot(xc, xc)) - 1.7320509f * hh - m->p_ra[pi] < m->p_thr[pi] + 1e-3f;
+                    if (near) {
                     float lo_t = 0.f, hi_t = 1.f;
                     for (int it = 0; it < 32; ++it) {
                         const float t = 0.5f * (lo_t + hi_t);
@@ -340,6 +347,7 @@ struct Env {
                     act[p] = dist[p] < m->p_thr[pi] && len > 1e-9f;
                     const V3 n = (1.f / fmaxf(len, 1e-20f)) * d;
                     nn[p] = n; pa[p] = xb + mulR(kb, xx) - ra * n; pb[p] = xb + mulR(kb, cc);
+                    }
                 } else {
                 const V3 p2 = ld3(kb + 9) + mulR(kb, ld3(m->p_b0[pi])), q2 = ld3(kb + 9) + mulR(kb, ld3(m->p_b1[pi]));
                 const V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
