@@ -856,6 +856,7 @@ struct Env {
                 const int t0end = C::LPE;
                 for (int it = 0; it < niter; ++it) {
                     // rows 0 .. LPE-1 live in register slot 0
+#pragma unroll 2
                     for (int t = 0; t < t0end; ++t) {
                         int i = t;
                         if (t < nl) i = (it & 1) ? t : nl - 1 - t;
@@ -871,6 +872,7 @@ struct Env {
                         if (i == myn1) { ln[1] += dl; hi_e[1] = mu[1] * ln[1]; lo_e[1] = -hi_e[1]; }
                     }
                     // rows LPE .. 2 LPE-1 live in register slot 1 (never limit rows: nl <= NLIM <= LPE)
+#pragma unroll 2
                     for (int t = C::LPE; t < nrmax; ++t) {
                         const float d = fmaf(-r[1], dinv[1], rhs[1]);
                         float cd = fminf(fmaxf(lmb[1] + d, lo_e[1]), hi_e[1]) - lmb[1];
