@@ -15,6 +15,12 @@
  *     ordered by the stream, except the *_host entry points, which synchronise before returning.
  *   - a handle is bound to one device and is not thread-safe.  Multi-GPU = one handle per device.
  *     Every call makes the handle's device the calling thread's current CUDA device (cudaSetDevice) and leaves it so.
+ *   - a handle remembers the stream of its last stream-ordered call; a call on a different stream (and the *_host / pbg_stats
+ *     entry points, which use a private stream / block) first waits for the work enqueued on that previous stream, so e.g.
+ *     pbg_reset on one stream followed by pbg_step_host needs no synchronisation by the caller.  I/O buffers the CALLER writes
+ *     on yet another stream are the caller's to order.
+ *   - stepping (pbg_step*, pbg_physics_step*, pbg_observe, pbg_rollout_policy) before the first pbg_reset* / pbg_set_state /
+ *     pbg_restore returns PBG_ERR_INVALID.
  *   - the stream-ordered entry points (pbg_reset*, pbg_step, pbg_physics_step*, pbg_observe, pbg_rollout_policy,
  *     pbg_get_state / pbg_set_state, pbg_get_feet_contact) enqueue kernels only -- no allocation, no synchronisation, all
  *     counters on the device -- and may be recorded into a CUDA graph (cudaStreamBeginCapture) and replayed.
@@ -28,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PBG_VERSION 100
+#define PBG_VERSION 101
 
 typedef enum {
     PBG_OK = 0,
@@ -123,6 +129,9 @@ typedef struct pbg_episode_stats {
     int64_t truncated;            /* of which ended by max_episode_steps */
     int64_t nonfinite;            /* episodes ended by a non-finite observation (rs/gym_locomotion_envs.py:63-65) */
     int64_t steps;                /* env steps taken */
+    int64_t contact_overflow;     /* env steps in which a sub-step had more contact candidates under their breaking threshold
+                                     than the kernel's solver budget (pbg_max_contacts); the deepest were kept.  The feet flags
+                                     are not affected by the budget. */
 } pbg_episode_stats;
 
 int pbg_version(void);
@@ -204,8 +213,11 @@ int pbg_restore(pbg_handle *h, const void *buf, void *stream);
 
 /* Physics only (apply_action + stepSimulation), no task bookkeeping; for single-step parity tests. */
 int pbg_physics_step(pbg_handle *h, const float *actions_dev, void *stream);
-/* calc_state + reward of the current state without physics (uses the given actions for the
- * electricity terms); outputs as pbg_step.  For the 1e-5 observation/reward parity tier. */
+/* The task half of an env step on the current state, without physics: calc_state + reward + termination with the given
+ * actions in the electricity terms; outputs as pbg_step.  pbg_physics_step + pbg_observe == pbg_step without the episode
+ * counters / auto-reset.  NOT a pure read: like the reference's _step it latches this step's feet flags (quirk Q2), updates
+ * the stored potential, and for the Flagrun kinds advances flag_timeout / frame / on_ground counters and may move the flag or
+ * throw the cube.  For the 1e-5 observation/reward parity tier. */
 int pbg_observe(pbg_handle *h, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
                 float *reward_terms_dev, void *stream);
 /* feet_contact flags as the reference's robot.feet_contact, float[num_envs, nfeet] */
@@ -218,6 +230,29 @@ int pbg_physics_step_counts(pbg_handle *h, const float *actions_dev, int32_t *nc
 int pbg_max_contacts(int kind);
 
 int pbg_stats(pbg_handle *h, pbg_episode_stats *out_host, int32_t reset);
+
+/* Re-keys the counter RNG that draws the reset noise (when not injected), the Flagrun flag positions and the cube attacks;
+ * takes effect at the next reset.  The reference's env.seed(s) (rs/env_bases.py:41-44) re-seeds the np_random these come from. */
+int pbg_set_seed(pbg_handle *h, uint64_t seed);
+
+/* Task bookkeeping per env, double[num_envs, PBG_TASK_VIEW_DIM] on the device:
+ *   [0] potential (env.potential, rs/gym_locomotion_envs.py:67-68)   [1] walk_target_x   [2] walk_target_y
+ *   [3] flag_timeout (rs/robot_locomotors.py:204-218)   [4] frame   [5] on_ground_frame_counter (:250-273)
+ *   [6] steps of the running episode   [7] return of the running episode   [8] initial_z   [9] episode index
+ *   [10] cube attacks so far   [11] flag moves so far
+ * Lets a host shell mirror robot.walk_target_x/y, flag_timeout, frame and env.potential after each step. */
+#define PBG_TASK_VIEW_DIM 12
+int pbg_get_task_view(pbg_handle *h, double *out_dev, void *stream);
+
+/* Contact export (what getContactPoints(bodyA, -1, linkA, -1) lists, rs/robot_bases.py:280-281).  After
+ * pbg_enable_contact_export(h, 1) every pbg_step / pbg_physics_step* records, per env and contact-candidate slot, the
+ * distance of that candidate in the step's last collision pass, or +inf when it is not within its breaking threshold.
+ * Slots, in order: for every geom with geom_ground != 0, in geom order, one slot per sphere / two per capsule (end spheres)
+ * against the floor; 8 cube corners against the floor (worlds with the cube); the npair self-collision geom pairs; every
+ * geom against the cube (worlds with the cube).  pbg_get_contact_candidates copies float[num_envs, pbg_num_contact_slots]. */
+int pbg_num_contact_slots(const pbg_handle *h);
+int pbg_enable_contact_export(pbg_handle *h, int32_t enabled);
+int pbg_get_contact_candidates(pbg_handle *h, float *out_dev, void *stream);
 
 /* Measures the FP32 CUDA-core peak of `device` with an FFMA microbenchmark (TFLOP/s); the roofline
  * denominator MEASURED_PEAKS.json does not carry. */

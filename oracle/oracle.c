@@ -168,6 +168,9 @@ struct orc_env {
     /* contacts */
     contact ct[MAXCAND]; int nct;
     int cand_active[MAXCAND];
+    double feet_touch[MAXFEET];  /* foot-vs-floor candidates under the breaking threshold in the last collide(), BEFORE the solver cap */
+    int cap_overflow;            /* collide() calls in which max_contacts dropped candidates */
+    double feet_margin[MAXFEET]; /* min over the foot's floor candidates of |distance - breaking threshold| in the last collide() */
     /* task state */
     double feet_contact[MAXFEET];
     double initial_z, potential;
@@ -542,6 +545,7 @@ static void collide(orc_env *e) {
     const orc_model *m = &e->m;
     static __thread contact all[MAXCAND];
     int n = 0, slot = 0;
+    for (int f = 0; f < m->nfeet; f++) e->feet_margin[f] = 1e30;
     for (int g = 0; g < m->ng; g++) {
         int npt = m->g_type[g] == ORC_G_CAPSULE ? 2 : 1;
         v3 a, b; geom_world(e, g, a, b);
@@ -550,6 +554,10 @@ static void collide(orc_env *e) {
             if (!m->g_ground[g]) continue;
             const double *c = k ? b : a;
             double dist = c[2] - m->g_radius[g];
+            for (int f = 0; f < m->nfeet; f++) if (m->foot_link[f] == m->g_link[g]) {
+                double mg = fabs(dist - m->g_threshold[g]);
+                if (mg < e->feet_margin[f]) e->feet_margin[f] = mg;
+            }
             if (dist < m->g_threshold[g]) {
                 contact *ct = &all[n++];
                 ct->ga = g; ct->gb = -1; ct->la = m->g_link[g]; ct->lb = -1; ct->slot = slot;
@@ -615,8 +623,15 @@ static void collide(orc_env *e) {
         }
     }
     (void)nground;
+    /* what getContactPoints would report for the feet (rs/robot_bases.py:280-281, rs/gym_locomotion_envs.py:73) follows the
+     * threshold test, not the solver's row budget: taken before the cap */
+    for (int f = 0; f < m->nfeet; f++) {
+        e->feet_touch[f] = 0.0;
+        for (int i = 0; i < n; i++) if (all[i].lb == LINK_FLOOR && all[i].la == m->foot_link[f]) e->feet_touch[f] = 1.0;
+    }
     /* cap: keep the max_contacts deepest, preserving candidate order */
     int cap = m->max_contacts > 0 ? m->max_contacts : MAXCAND;
+    if (n > cap) e->cap_overflow++;
     while (n > cap) {
         int w = 0;
         for (int i = 1; i < n; i++) if (all[i].dist > all[w].dist) w = i;   /* first shallowest... */
@@ -1119,11 +1134,7 @@ static double calc_potential(orc_env *e) {
 
 static void update_feet_contact(orc_env *e) {
     const orc_model *m = &e->m;
-    for (int f = 0; f < m->nfeet; f++) {
-        double v = 0;
-        for (int c = 0; c < e->nct; c++) if (e->ct[c].lb == LINK_FLOOR && e->ct[c].la == m->foot_link[f]) v = 1.0;
-        e->feet_contact[f] = v;
-    }
+    for (int f = 0; f < m->nfeet; f++) e->feet_contact[f] = e->feet_touch[f];
 }
 
 int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double *terms) {
@@ -1231,7 +1242,7 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
         for (int k = 0; k < 3; k++) { e->xp[k] = m->cube_pos0[k]; e->xw[k] = 0; e->xv[k] = 0; e->xq[k] = 0; }
         e->xq[3] = 1.0;
     }
-    for (int f = 0; f < MAXFEET; f++) e->feet_contact[f] = 0;
+    for (int f = 0; f < MAXFEET; f++) { e->feet_contact[f] = 0; e->feet_touch[f] = 0; }
     e->steps = 0; e->nct = 0;
     e->floor_in_parts = floor_in_parts;
     e->walk_target_x = m->walk_target_x; e->walk_target_y = m->walk_target_y;
@@ -1348,3 +1359,26 @@ long orc_rollout(orc_env *e, long steps, uint64_t action_seed, double *ret_sum, 
     if (episodes) *episodes = eps;
     return steps;
 }
+
+/* Whole random-policy episodes for the statistical parity tier (T4): `n` episodes in a row (each: reset from the counter RNG,
+ * U(-1,1) actions keyed by (action_seed, env_index, episode * 4096 + t, n), until done or `cap` steps); per episode the return
+ * and the length.  Returns the number of env steps taken. */
+long orc_episodes(orc_env *e, int n, int cap, uint64_t action_seed, double *returns, int32_t *lengths) {
+    double obs[512], act[MAXD], rew; long total = 0;
+    for (int ep = 0; ep < n; ep++) {
+        orc_reset(e, 1, obs);
+        double rs = 0; int t = 0;
+        for (; t < cap; ) {
+            for (int k = 0; k < e->m.nact; k++)
+                act[k] = rng_uniform(action_seed, e->env_index, (uint32_t)(ep * 4096 + t), (uint32_t)k, -1.0f, 1.0f);
+            int done = orc_step(e, act, obs, &rew, NULL);
+            rs += rew; t++;
+            if (done) break;
+        }
+        returns[ep] = rs; lengths[ep] = t; total += t;
+    }
+    return total;
+}
+
+int orc_cap_overflows(const orc_env *e) { return e->cap_overflow; }
+void orc_feet_margin(const orc_env *e, double *out) { for (int f = 0; f < e->m.nfeet; f++) out[f] = e->feet_margin[f]; }

@@ -125,6 +125,13 @@ double orc_energy(orc_env *e);              /* kinetic + potential, for invarian
 void orc_mass_matrix_inv(orc_env *e, double *Minv);
 /* throughput helper for the CPU baseline: run `steps` env steps with U(-1,1) actions, auto-reset */
 long orc_rollout(orc_env *e, long steps, uint64_t action_seed, double *ret_sum, long *episodes);
+/* `n` whole random-policy episodes (reset, U(-1,1) actions until done or `cap` steps): per-episode return / length */
+long orc_episodes(orc_env *e, int n, int cap, uint64_t action_seed, double *returns, int32_t *lengths);
+/* collide() passes in which max_contacts dropped candidates since creation */
+int orc_cap_overflows(const orc_env *e);
+/* per foot: how close its nearest floor candidate was to flipping the feet flag in the last collision pass
+ * (min |distance - breaking threshold|); lets a test excuse exactly the flag disagreements that are round-off */
+void orc_feet_margin(const orc_env *e, double *out);
 
 #ifdef __cplusplus
 }

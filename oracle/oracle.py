@@ -108,12 +108,36 @@ def lib():
         L.orc_set_tape.argtypes = [C.c_void_p, _pd, C.c_int]
         L.orc_rollout.argtypes = [C.c_void_p, C.c_long, C.c_uint64, _pd, C.POINTER(C.c_long)]
         L.orc_rollout.restype = C.c_long
+        L.orc_episodes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, _pd, _pi]
+        L.orc_episodes.restype = C.c_long
+        L.orc_cap_overflows.argtypes = [C.c_void_p]
+        L.orc_feet_margin.argtypes = [C.c_void_p, _pd]
         _lib = L
     return _lib
 
 
 def _d(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def random_policy_episodes(env_id_or_spec, n_episodes: int, cap: int, seed: int = 0, threads: Optional[int] = None, **kw):
+    """n_episodes whole random-policy episodes of the oracle on `threads` host threads (ctypes releases the GIL inside
+    orc_episodes): (returns, lengths).  Thread k owns RNG stream env_index = k."""
+    import threading
+    threads = threads or min(os.cpu_count() or 1, 32)
+    per = [n_episodes // threads + (1 if k < n_episodes % threads else 0) for k in range(threads)]
+    envs = [OracleEnv(env_id_or_spec, seed=seed, env_index=k, **kw) for k in range(threads)]
+    out = [None] * threads
+
+    def work(k):
+        out[k] = envs[k].episodes(per[k], cap, action_seed=seed + 1) if per[k] else (np.zeros(0), np.zeros(0, np.int32))
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return np.concatenate([o[0] for o in out]), np.concatenate([o[1] for o in out])
 
 
 def _i(a):
@@ -331,6 +355,20 @@ class OracleEnv:
         out = np.zeros(n * n)
         lib().orc_mass_matrix_inv(self._h, out.ctypes.data_as(_pd))
         return out.reshape(n, n)
+
+    def episodes(self, n: int, cap: int, action_seed: int = 0):
+        """n whole random-policy episodes (each at most `cap` steps): (returns[n], lengths[n])."""
+        ret, ln = np.zeros(n), np.zeros(n, np.int32)
+        lib().orc_episodes(self._h, n, cap, action_seed, ret.ctypes.data_as(_pd), ln.ctypes.data_as(_pi))
+        return ret, ln
+
+    def feet_margin(self):
+        out = np.zeros(max(1, len(self.spec.foot_list)))
+        lib().orc_feet_margin(self._h, out.ctypes.data_as(_pd))
+        return out[:len(self.spec.foot_list)]
+
+    def cap_overflows(self) -> int:
+        return lib().orc_cap_overflows(self._h)
 
     def rollout(self, steps: int, action_seed: int = 0):
         rs, ep = C.c_double(0), C.c_long(0)

@@ -71,7 +71,13 @@ class PbgModel(C.Structure):
 
 class PbgEpisodeStats(C.Structure):
     _fields_ = [("return_sum", C.c_double), ("length_sum", C.c_double), ("episodes", C.c_int64),
-                ("truncated", C.c_int64), ("nonfinite", C.c_int64), ("steps", C.c_int64)]
+                ("truncated", C.c_int64), ("nonfinite", C.c_int64), ("steps", C.c_int64), ("contact_overflow", C.c_int64)]
+
+
+PBG_VERSION = 101          # include/pbg.h
+TASK_VIEW_DIM = 12         # PBG_TASK_VIEW_DIM
+TASK_VIEW_FIELDS = ("potential", "walk_target_x", "walk_target_y", "flag_timeout", "frame", "on_ground_frame_counter",
+                    "episode_steps", "episode_return", "initial_z", "episode", "attacks", "flag_moves")
 
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -137,6 +143,14 @@ def lib():
     L.pbg_snapshot_bytes.restype = C.c_int64
     L.pbg_snapshot.argtypes = [vp, vp, vp]
     L.pbg_restore.argtypes = [vp, vp, vp]
+    L.pbg_set_seed.argtypes = [vp, C.c_uint64]
+    L.pbg_get_task_view.argtypes = [vp, vp, vp]
+    L.pbg_num_contact_slots.argtypes = [vp]
+    L.pbg_enable_contact_export.argtypes = [vp, C.c_int32]
+    L.pbg_get_contact_candidates.argtypes = [vp, vp, vp]
+    if L.pbg_version() != PBG_VERSION:
+        raise BackendUnavailable("%s is version %d, this package needs %d: rebuild it (__graft_entry__.build())"
+                                 % (LIB_PATH, L.pbg_version(), PBG_VERSION))
     _lib = L
     return L
 
@@ -145,7 +159,8 @@ EXPORTS = ["pbg_version", "pbg_create", "pbg_destroy", "pbg_last_error", "pbg_nu
            "pbg_action_dim", "pbg_state_dim", "pbg_noise_dim", "pbg_reset", "pbg_reset_with", "pbg_step", "pbg_step_host",
            "pbg_set_auto_reset", "pbg_set_zero_copy", "pbg_last_host_path", "pbg_set_policy", "pbg_rollout_policy", "pbg_get_state", "pbg_set_state", "pbg_physics_step", "pbg_physics_step_counts",
            "pbg_max_contacts", "pbg_measure_fp32_peak", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count",
-           "pbg_snapshot_bytes", "pbg_snapshot", "pbg_restore"]
+           "pbg_snapshot_bytes", "pbg_snapshot", "pbg_restore", "pbg_set_seed", "pbg_get_task_view", "pbg_num_contact_slots",
+           "pbg_enable_contact_export", "pbg_get_contact_candidates"]
 
 
 def _d(a):
@@ -216,6 +231,22 @@ class ModelTables:
             for i in range(3):
                 m.cube_pos0[i] = cube.pos0[i]
         self.c = m
+
+    def contact_slots(self):
+        """(link name, other) per contact-candidate slot, in the order include/pbg.h documents for
+        pbg_get_contact_candidates; other is "floor", "cube" or the second link's name."""
+        rm, spec = self.reduced, self.spec
+        link = [rm.sub_names[s] for s in rm.geom_link]
+        out = []
+        for g in range(len(rm.geom_body)):
+            if rm.geom_ground[g]:
+                out += [(link[g], "floor")] * (2 if rm.geom_type[g] == mj.G_CAPSULE else 1)
+        if spec.cube is not None:
+            out += [("cube", "floor")] * 8
+        out += [(link[a], link[b]) for a, b in zip(rm.pair_a, rm.pair_b)]
+        if spec.cube is not None:
+            out += [(link[g], "cube") for g in range(len(rm.geom_body))]
+        return out
 
 
 def check(rc: int, handle=None):

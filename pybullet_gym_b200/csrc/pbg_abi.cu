@@ -34,7 +34,7 @@ using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1>;
 using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17>;
 
 struct KernelInfo {
-    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet, nnoise, ysz;
+    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet, nnoise, ysz, off_task, nslot;
     size_t smem;
     void (*launch)(const DevModel *, const StepBuffers &, const LaunchArgs &, cudaStream_t);
     cudaError_t (*prepare)();
@@ -55,7 +55,7 @@ static cudaError_t prepare_cfg() {
 template <class C>
 static KernelInfo info_of() {
     return KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
 }
 
 static bool kernel_for_kind(int kind, KernelInfo *out) {
@@ -98,6 +98,13 @@ struct pbg_handle {
     int zero_copy = 1;          // pbg_step_host: let the kernel read / write mapped pinned host buffers directly
     int last_host_path = 0;     // 1: zero-copy, 2: staged copies
     int64_t launches = 0;
+    // stream-ordering bookkeeping: the stream of the last stream-ordered call.  pbg_step_host (private stream) and
+    // pbg_stats (blocking copy) order themselves after it; see order_after_last()
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
+    cudaEvent_t order_ev = nullptr;
+    bool ready = false;         // a reset / set_state / restore has initialised the state
+    float *d_cand = nullptr;    // [E, nslot] contact-candidate distances of the last step (pbg_enable_contact_export)
     std::string err;
 };
 
@@ -385,6 +392,7 @@ int pbg_create(const pbg_model *model, int32_t num_envs, int32_t device, uint64_
     CREATE_TRY(cudaMalloc(&h->d_rew, size_t(num_envs) * sizeof(float)));
     CREATE_TRY(cudaMalloc(&h->d_done, size_t(num_envs)));
     CREATE_TRY(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
 #undef CREATE_TRY
     *out = h;
     return PBG_OK;
@@ -394,8 +402,9 @@ int pbg_destroy(pbg_handle *h) {
     if (!h) return PBG_OK;
     cudaSetDevice(h->device);
     cudaFree(h->dmodel); cudaFree(h->state); cudaFree(h->stats);
-    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->policy_buf);
+    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->policy_buf); cudaFree(h->d_cand);
     if (h->hstream) cudaStreamDestroy(h->hstream);
+    if (h->order_ev) cudaEventDestroy(h->order_ev);
     delete h;
     return PBG_OK;
 }
@@ -407,11 +416,37 @@ int pbg_state_dim(const pbg_handle *h) { return h ? h->k.canon : PBG_ERR_INVALID
 int pbg_noise_dim(const pbg_handle *h) { return h ? h->k.nnoise : PBG_ERR_INVALID; }
 int64_t pbg_launch_count(const pbg_handle *h) { return h ? h->launches : 0; }
 
+// Makes stream `s` wait for everything the handle's previous stream-ordered call enqueued on another stream (reset on
+// torch's stream followed by pbg_step_host on the private stream, ...).  The event is recorded lazily, here, on the
+// previous stream: it covers all work enqueued there so far and costs nothing on the common same-stream path.
+// A stream that is being captured into a CUDA graph is left alone (recording into the graph would tie the event to it).
+static int order_after_last(pbg_handle *h, cudaStream_t s) {
+    if (!h->have_last || h->last_stream == s) return PBG_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(h->last_stream, &cs) != cudaSuccess) { cudaGetLastError(); return PBG_OK; }
+    if (cs != cudaStreamCaptureStatusNone) return PBG_OK;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) { cudaGetLastError(); return PBG_OK; }
+    if (cs != cudaStreamCaptureStatusNone) return PBG_OK;      // a capture may not wait on an event from outside it
+    CUDA_TRY(h, cudaEventRecord(h->order_ev, h->last_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(s, h->order_ev, 0));
+    return PBG_OK;
+}
+
 static int launch(pbg_handle *h, int mode, StepBuffers &b, int floor_in_parts, void *stream) {
     if (!h) return PBG_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    const bool needs_state = mode == MODE_STEP || mode == MODE_PHYSICS || mode == MODE_OBSERVE || mode >= 100;
+    if (needs_state && !h->ready)
+        return fail(h, PBG_ERR_INVALID, "the handle has no state yet: call pbg_reset / pbg_reset_with (or pbg_set_state / pbg_restore) before stepping");
+    if (mode == MODE_RESET || mode == MODE_SET) h->ready = true;
+    {
+        int rc = order_after_last(h, (cudaStream_t)stream);
+        if (rc != PBG_OK) return rc;
+    }
+    h->last_stream = (cudaStream_t)stream; h->have_last = true;
     b.state = h->state;
     b.stats = h->stats;
+    b.cand_out = h->d_cand;
     LaunchArgs la;
     la.E = h->E; la.mode = mode; la.auto_reset = h->auto_reset; la.floor_in_parts = floor_in_parts;
     la.seed = h->seed; la.env_offset = h->env_offset; la.debug_env = h->debug_env; la.nsteps = 1;
@@ -470,6 +505,7 @@ int pbg_step_host(pbg_handle *h, const float *actions_host, float *obs_host, flo
     CUDA_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = h->hstream;
     const size_t E = h->E;
+    if (!h->ready) return fail(h, PBG_ERR_INVALID, "pbg_step_host: call pbg_reset first");
     if (h->zero_copy) {
         // Pinned host buffers are mapped into the device address space (UVA): the kernel reads the 32 B of actions per env
         // over PCIe at its start and posts obs / reward / done straight into host memory at its end -- no copy
@@ -553,6 +589,8 @@ int pbg_snapshot(pbg_handle *h, void *buf, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     SnapHeader hd{SNAP_MAGIC, (uint32_t)pbg_version(), h->kind, h->E, h->k.sstride, 0, h->seed, h->env_offset};
     const size_t sb = size_t(h->E) * h->k.sstride * sizeof(float);
+    { int rc = order_after_last(h, st); if (rc != PBG_OK) return rc; }
+    h->last_stream = st; h->have_last = true;
     char *p = static_cast<char *>(buf);
     CUDA_TRY(h, cudaMemcpyAsync(p, &hd, sizeof hd, cudaMemcpyDefault, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));       // hd lives on this stack frame
@@ -576,8 +614,10 @@ int pbg_restore(pbg_handle *h, const void *buf, void *stream) {
     if (hd.seed != h->seed || hd.env_offset != h->env_offset)
         return fail(h, PBG_ERR_INVALID, "pbg_restore: snapshot of a handle with another seed / env_offset (its reset RNG streams differ)");
     const size_t sb = size_t(h->E) * h->k.sstride * sizeof(float);
+    { int rc = order_after_last(h, st); if (rc != PBG_OK) return rc; }
     CUDA_TRY(h, cudaMemcpyAsync(h->state, p + sizeof hd, sb, cudaMemcpyDefault, st));
     CUDA_TRY(h, cudaMemcpyAsync(h->stats, p + sizeof hd + sb, 8 * sizeof(unsigned long long), cudaMemcpyDefault, st));
+    h->last_stream = st; h->have_last = true; h->ready = true;
     return PBG_OK;
 }
 
@@ -609,6 +649,8 @@ int pbg_get_feet_contact(pbg_handle *h, float *out_dev, void *stream) {
     // feet flags are the last NFEET floats before the padded end of the state row
     const int off = h->k.off_feet;
     const int n = h->E * h->k.nfeet;
+    { int rc = order_after_last(h, (cudaStream_t)stream); if (rc != PBG_OK) return rc; }
+    h->last_stream = (cudaStream_t)stream; h->have_last = true;
     gather_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, h->k.sstride, off, h->k.nfeet, out_dev, h->E);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
@@ -676,18 +718,86 @@ int pbg_measure_fp32_peak(int32_t device, double *tflops_out) {
     return PBG_OK;
 }
 
+int pbg_set_seed(pbg_handle *h, uint64_t seed) {
+    if (!h) return PBG_ERR_INVALID;
+    h->seed = seed;
+    return PBG_OK;
+}
+
+// task bookkeeping of every env as doubles (the potential is kept in fp64)
+__global__ void task_view_kernel(const float *state, int sstride, int off_task, double *out, int E) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const float *T = state + size_t(e) * sstride + off_task;
+    double *o = out + size_t(e) * PBG_TASK_VIEW_DIM;
+    o[0] = __hiloint2double(__float_as_int(T[T_POT_HI]), __float_as_int(T[T_POT_LO]));
+    o[1] = T[T_TX]; o[2] = T[T_TY]; o[3] = T[T_FLAGTIMEOUT];
+    o[4] = (double)__float_as_int(T[T_FRAME]); o[5] = (double)__float_as_int(T[T_ONGROUND]);
+    o[6] = (double)__float_as_int(T[T_STEPS]); o[7] = T[T_RETURN];
+    o[8] = T[T_INITZ]; o[9] = (double)__float_as_int(T[T_EPISODE]);
+    o[10] = (double)__float_as_int(T[T_ATTACKS]); o[11] = (double)__float_as_int(T[T_FLAGCNT]);
+}
+
+int pbg_get_task_view(pbg_handle *h, double *out_dev, void *stream) {
+    if (!h || !out_dev) return fail(h, PBG_ERR_INVALID, "pbg_get_task_view: NULL buffer");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    { int rc = order_after_last(h, (cudaStream_t)stream); if (rc != PBG_OK) return rc; }
+    h->last_stream = (cudaStream_t)stream; h->have_last = true;
+    task_view_kernel<<<(h->E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->state, h->k.sstride, h->k.off_task, out_dev, h->E);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    return PBG_OK;
+}
+
+int pbg_num_contact_slots(const pbg_handle *h) { return h ? h->k.nslot : PBG_ERR_INVALID; }
+
+int pbg_enable_contact_export(pbg_handle *h, int32_t enabled) {
+    if (!h) return PBG_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (enabled && !h->d_cand && h->k.nslot > 0) {
+        const size_t n = size_t(h->E) * h->k.nslot;
+        CUDA_TRY(h, cudaMalloc(&h->d_cand, n * sizeof(float)));
+        std::vector<float> inf(n, INFINITY);
+        CUDA_TRY(h, cudaMemcpy(h->d_cand, inf.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    } else if (!enabled && h->d_cand) {
+        CUDA_TRY(h, cudaDeviceSynchronize());
+        cudaFree(h->d_cand); h->d_cand = nullptr;
+    }
+    return PBG_OK;
+}
+
+int pbg_get_contact_candidates(pbg_handle *h, float *out_dev, void *stream) {
+    if (!h || !out_dev) return fail(h, PBG_ERR_INVALID, "pbg_get_contact_candidates: NULL buffer");
+    if (!h->d_cand) return fail(h, PBG_ERR_INVALID, "pbg_get_contact_candidates: call pbg_enable_contact_export(h, 1) first");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    { int rc = order_after_last(h, (cudaStream_t)stream); if (rc != PBG_OK) return rc; }
+    h->last_stream = (cudaStream_t)stream; h->have_last = true;
+    CUDA_TRY(h, cudaMemcpyAsync(out_dev, h->d_cand, size_t(h->E) * h->k.nslot * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return PBG_OK;
+}
+
 int pbg_stats(pbg_handle *h, pbg_episode_stats *out, int32_t reset) {
     if (!h || !out) return fail(h, PBG_ERR_INVALID, "pbg_stats: NULL argument");
     CUDA_TRY(h, cudaSetDevice(h->device));
     unsigned long long raw[8];
-    CUDA_TRY(h, cudaMemcpy(raw, h->stats, sizeof raw, cudaMemcpyDeviceToHost));
+    // blocking: ordered after the last stream-ordered call of this handle (torch side streams do not synchronise with
+    // the legacy default stream a plain cudaMemcpy runs on)
+    cudaStream_t s = h->have_last ? h->last_stream : (cudaStream_t)0;
+    {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) { cudaGetLastError(); s = 0; }
+        else if (cs != cudaStreamCaptureStatusNone) return fail(h, PBG_ERR_INVALID, "pbg_stats: the handle's stream is being captured into a CUDA graph");
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(raw, h->stats, sizeof raw, cudaMemcpyDeviceToHost, s));
+    if (reset) CUDA_TRY(h, cudaMemsetAsync(h->stats, 0, sizeof raw, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
     out->episodes = (int64_t)raw[0];
     out->length_sum = (double)raw[1];
     memcpy(&out->return_sum, &raw[2], sizeof(double));
     out->truncated = (int64_t)raw[3];
     out->nonfinite = (int64_t)raw[4];
     out->steps = (int64_t)raw[5];
-    if (reset) CUDA_TRY(h, cudaMemset(h->stats, 0, sizeof raw));
+    out->contact_overflow = (int64_t)raw[6];
     return PBG_OK;
 }
 

@@ -166,6 +166,7 @@ struct Env {
     unsigned up, down;
     float tau;          // joint force of this dof for the current env step
     int nc, nl;         // active contacts / limit rows of this env (group-uniform)
+    int ovf;            // this env step had a sub-step with more than MAXC candidates in contact (the solver kept the deepest)
     float *dbg;         // optional debug dump of the constraint rows (development only)
     unsigned long long rng_seed, rng_env;   // counter-RNG key / stream of this env
 
@@ -201,7 +202,7 @@ struct Env {
         for (int i = 0; i < 6; ++i) Ib[i] = m->inertia[b][i];
         const int k = gl < C::ND ? gl : 0;
         up = m->up[k]; down = m->down[k];
-        tau = 0.f; nc = 0; nl = 0; dbg = nullptr;
+        tau = 0.f; nc = 0; nl = 0; ovf = 0; dbg = nullptr;
     }
 
     // ---------------------------------------------------------------- forward kinematics
@@ -301,6 +302,7 @@ struct Env {
         bool act[PASSES];
         V3 pa[PASSES], pb[PASSES], nn[PASSES];
         int total = 0;
+        unsigned feet = 0;
 #pragma unroll
         for (int p = 0; p < PASSES; ++p) {
             const int s = p * C::LPE + gl;
@@ -377,9 +379,13 @@ struct Env {
             }
             if (s < C::NSLOT) cd[s] = act[p] ? dist[p] : CUDART_INF_F;
             total += __popc(gballot(act[p]));
+            // feet flags = what getContactPoints reports (rs/robot_bases.py:280-281): every foot candidate under its
+            // breaking threshold, whether or not the solver's MAXC budget below keeps it
+            if (act[p] && s < C::NCAND && m->c_foot[s] >= 0) feet |= 1u << m->c_foot[s];
         }
         __syncwarp();
         const int cap = C::MAXC;
+        if (total > cap) ovf = 1;
         if (wmax(total) > cap) {
             // keep the MAXC smallest by (distance, slot)
 #pragma unroll
@@ -396,7 +402,6 @@ struct Env {
             }
         }
         int base = 0;
-        unsigned feet = 0;
 #pragma unroll
         for (int p = 0; p < PASSES; ++p) {
             const int s = p * C::LPE + gl;
@@ -411,7 +416,6 @@ struct Env {
                 ct[0] = __int_as_float(ba); ct[1] = __int_as_float(bb); ct[2] = __int_as_float(s);
                 st3(ct + 4, pa[p] - xref); st3(ct + 7, pb[p] - xref); st3(ct + 10, nn[p]);
                 ct[13] = dist[p]; ct[14] = mu;
-                if (s < C::NCAND && m->c_foot[s] >= 0) feet |= 1u << m->c_foot[s];
             } else if (s < C::NSLOT) {
                 warm[s] = 0.f;
             }
@@ -1491,6 +1495,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
             if (ai >= 0) { const float av = act[ai]; tq += model->jtorque[j] * (isfinite(av) ? fminf(fmaxf(av, -1.f), 1.f) : CUDART_NAN_F); }
         }
         e.tau = tq;
+        e.ovf = 0;
         const int nsub = model->nsub;
         for (int s = 0; s < nsub; ++s) {
 #ifndef PBG_SYNC_MODE
@@ -1501,6 +1506,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
             e.substep(s == nsub - 1);
         }
     }
+    // optional: distance of every contact candidate slot in the step's last collision pass (+inf: not in contact);
+    // the shell's BodyPart.contact_list() (rs/robot_bases.py:280-281) is built from it
+    if (C::NSLOT > 0 && valid && B.cand_out && (mode_eff == MODE_STEP || mode == MODE_PHYSICS))
+        for (int i = gl; i < C::NSLOT; i += C::LPE) B.cand_out[env * C::NSLOT + i] = e.sm[C::sCD + i];
     if (mode == MODE_PHYSICS) {
         if (C::MAXC > 0 && gl < C::NFEET) S[C::oP + gl] = e.sm[C::sMISC + gl];
         __syncwarp();
@@ -1548,6 +1557,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
             trunc = !done && __float_as_int(T[T_STEPS]) >= model->max_steps;
         }
         const bool finished = done || trunc;
+        if (mode_eff == MODE_STEP && e.ovf && valid && gl == 0 && B.stats) atomicAdd(&B.stats[6], 1ull);
         if (policy_mode) { ret_acc += so_rew[0]; any_done = any_done || finished; }
         if (valid && gl == 0 && !policy_mode) {
             if (B.reward) B.reward[env] = so_rew[0];

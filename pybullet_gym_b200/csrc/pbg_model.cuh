@@ -81,6 +81,7 @@ struct StepBuffers {
     uint8_t *truncated;       // [E] optional
     float *feet_out;          // [E, nfeet] optional
     int *ncontact_out;        // [E] optional
+    float *cand_out;          // [E, NSLOT] optional: per contact-candidate slot, distance in the last collision pass (+inf: inactive)
     unsigned long long *stats;  // [8] device episode statistics
     float *canon;             // [E, state_dim] for get/set state
     float *debug;             // development: constraint-row dump of env `debug_env`

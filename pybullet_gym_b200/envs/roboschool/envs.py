@@ -40,12 +40,20 @@ class BaseBulletEnv:
     def _seed(self, seed=None):
         self.np_random = np.random.RandomState(seed)
         self.robot.np_random = self.np_random   # same generator for env and robot (env_bases.py:41-44)
+        # The Flagrun flag positions and cube attacks are drawn on the device from a counter RNG; the reference draws them
+        # from this np_random.  Key the device RNG by the same seed (OS entropy when unseeded, like RandomState(None)), so
+        # that differently seeded envs / worker processes see different targets and the same seed repeats them.
+        import os
+        self._backend_seed = int(seed) & 0xFFFFFFFFFFFFFFFF if seed is not None else int.from_bytes(os.urandom(8), "little")
+        if getattr(self, "_backend", None) is not None:
+            self._backend.seed(self._backend_seed)
         return [seed]
 
     def _ensure_backend(self):
         if self._backend is None:
             # the "physics client" is created lazily on the first reset (env_bases.py:46-56)
-            self._backend = VectorEnv(self.robot.spec.id, 1, device=self._device, seed=0, auto_reset=False)
+            self._backend = VectorEnv(self.robot.spec.id, 1, device=self._device, seed=self._backend_seed, auto_reset=False)
+            self._backend.enable_contact_export(True)       # BodyPart.contact_list()
             self.physicsClientId = 0
             self.ownsPhysicsClient = True
             self.robot._env = self
@@ -123,14 +131,24 @@ class WalkerBaseBulletEnv(BaseBulletEnv):
         r.feet_contact = np.zeros(len(r.foot_list), dtype=np.float32)
         r.initial_z = None
         first = "floor" not in r.parts
-        r._update_views(obs)
-        self.potential = r.calc_potential()
+        self._mirror(obs)
         if first:
             # quirk Q1: the floor joins robot.parts after the first reset (gym_locomotion_envs.py:30-31)
             r.parts["floor"] = R.BodyPart(r, "floor", None)
             self.parts, self.jdict, self.ordered_joints, self.robot_body = r.parts, r.jdict, r.ordered_joints, r.robot_body
         self.stateId = 0
         return obs
+
+    def _mirror(self, obs):
+        """Host views after a reset / step.  Targets, flag timeout, frame counters and the potential (fp64, with
+        FlagrunHarder's crawl bookkeeping, robot_locomotors.py:280-302) are the device's own values."""
+        r = self.robot
+        view = {k: v.cpu().numpy() for k, v in self._backend.task_view().items()}
+        if hasattr(r, "_mirror_task"):
+            r._mirror_task(view)
+        self.walk_target_x, self.walk_target_y = r.walk_target_x, r.walk_target_y
+        r._update_views(obs)
+        self.potential = float(view["potential"][0])
 
     def _step(self, a):
         a = np.asarray(a, dtype=np.float32)
@@ -139,9 +157,8 @@ class WalkerBaseBulletEnv(BaseBulletEnv):
         state = obs[0].cpu().numpy()
         terms = info["reward_terms"][0].cpu().numpy()
         r = self.robot
-        r._update_views(state)
+        self._mirror(state)
         r.feet_contact = self._backend.feet_contact()[0].cpu().numpy().astype(np.float32)
-        self.potential = r.calc_potential()
         self.rewards = [float(t) for t in terms]
         self.HUD(state, a, bool(done[0]))
         self.reward += sum(self.rewards)

@@ -66,8 +66,17 @@ class BodyPart:
     def pose(self):
         return self.bp_pose
 
+    def speed(self):
+        """COM linear velocity of the link (robot_bases.py:243-248)."""
+        if self.link_index is None:
+            return np.zeros(3)
+        return self.robot._com_velocities()[self.link_index].copy()
+
     def contact_list(self):
-        raise NotImplementedError("per-link contact lists are not exported; use robot.feet_contact")
+        """Contact points of this link after the last step, shaped like pybullet's getContactPoints tuples as far as the
+        reference reads them (robot_bases.py:280-281; gym_locomotion_envs.py:73 uses fields [2] = bodyB and [4] = linkB):
+        (contactFlag, bodyA, bodyB, linkA, linkB, posA, posB, normal, distance, normalForce)."""
+        return self.robot._contacts_of(self.name)
 
 
 class Joint:
@@ -148,6 +157,45 @@ class XmlBasedRobot:
             else:
                 self._cache["frames"] = mj.link_world_frames(self.bullet, s[:self.nd])
         return self._cache["frames"]
+
+    def _com_velocities(self):
+        s = self._state()
+        if "vel" not in self._cache:
+            nd = self.nd
+            if self.bullet.floating:
+                self._cache["vel"] = mj.link_com_velocities(self.bullet, s[13:13 + nd], s[13 + nd:13 + 2 * nd], s[0:3], s[3:7],
+                                                            s[7:10], s[10:13])
+            else:
+                self._cache["vel"] = mj.link_com_velocities(self.bullet, s[:nd], s[nd:2 * nd])
+        return self._cache["vel"]
+
+    # body ids as the reference's scene would hand them out: the stadium floor is loaded first (scene_stadium.py:28), then the robot
+    FLOOR_BODY, ROBOT_BODY, CUBE_BODY = 0, 1, 2
+
+    def _contacts_of(self, link_name):
+        be = self._env._backend if self._env is not None else None
+        if be is None or be._cand is None:
+            return []
+        if "cand" not in self._cache:
+            self._state()
+            self._cache["cand"] = be.contact_candidates()[0].cpu().numpy()
+            self._cache["slots"] = be.tables.contact_slots()
+        idx = {l.name: i - 1 for i, l in enumerate(self.bullet.links)}
+        out = []
+        for (a, b), d in zip(self._cache["slots"], self._cache["cand"]):
+            if not np.isfinite(d) or link_name not in (a, b):
+                continue
+            other = b if a == link_name else a
+            if other == "floor":
+                body_b, link_b = self.FLOOR_BODY, -1
+            elif other == "cube":
+                body_b, link_b = self.CUBE_BODY, -1
+            else:
+                body_b, link_b = self.ROBOT_BODY, idx.get(other, -1)
+            me = (self.FLOOR_BODY, -1) if link_name == "floor" else ((self.CUBE_BODY, -1) if link_name == "cube"
+                                                                      else (self.ROBOT_BODY, idx.get(link_name, -1)))
+            out.append((0, me[0], body_b, me[1], link_b, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), float(d), 0.0))
+        return out
 
     def _invalidate(self):
         self._cache = None
@@ -244,12 +292,23 @@ class HumanoidFlagrun(Humanoid):
         self.flag = None
         self.flag_timeout = 0
 
+    def _mirror_task(self, view):
+        """The flag lives on the device (flag_reposition, robot_locomotors.py:204-218): mirror its position / timeout."""
+        self.walk_target_x, self.walk_target_y = float(view["walk_target_x"][0]), float(view["walk_target_y"][0])
+        self.flag_timeout = float(view["flag_timeout"][0])
+
 
 class HumanoidFlagrunHarder(HumanoidFlagrun):
     def __init__(self):
         HumanoidFlagrun.__init__(self, "HumanoidFlagrunHarderPyBulletEnv-v0")
         self.aggressive_cube = None
         self.frame = 0
+        self.on_ground_frame_counter = 0
+
+    def _mirror_task(self, view):
+        HumanoidFlagrun._mirror_task(self, view)
+        self.frame = int(view["frame"][0])
+        self.on_ground_frame_counter = int(view["on_ground_frame_counter"][0])
 
 
 class InvertedPendulum(MJCFBasedRobot):

@@ -424,6 +424,34 @@ def link_world_frames(model: BulletModel, q: Optional[np.ndarray] = None, base_p
     return R, p
 
 
+def link_com_velocities(model: BulletModel, q, qd, base_pos=None, base_quat=None, base_omega=None, base_vel=None):
+    """World linear velocity of every link's COM -- what getBaseVelocity()[0] / getLinkState(computeLinkVelocity=1)[6]
+    return (rs/robot_bases.py:243-248).  q / qd follow dof_links() order; base_vel is the base COM velocity."""
+    dofs = model.dof_links()
+    qd = np.asarray(qd, float)
+    qdmap = {li: qd[k] for k, li in enumerate(dofs)}
+    R, p = link_world_frames(model, q, base_pos, base_quat)
+    n = len(model.links)
+    w = [np.zeros(3) for _ in range(n)]
+    vo = [np.zeros(3) for _ in range(n)]      # velocity of the link frame origin
+    out = np.zeros((n, 3))
+    for i, l in enumerate(model.links):
+        if l.parent < 0:
+            if l.jtype == JT_FREE and base_omega is not None:
+                w[i] = np.asarray(base_omega, float)
+                vo[i] = np.asarray(base_vel, float) - np.cross(w[i], R[i] @ l.com)
+        else:
+            pa = l.parent
+            w[i] = w[pa].copy()
+            vo[i] = vo[pa] + np.cross(w[pa], p[i] - p[pa])
+            if l.jtype == JT_REVOLUTE:
+                w[i] = w[i] + (R[i] @ l.axis) * qdmap[i]       # the axis as written (Bullet does not normalise it)
+            elif l.jtype == JT_PRISMATIC:
+                vo[i] = vo[i] + (R[i] @ l.axis) * qdmap[i]
+        out[i] = vo[i] + np.cross(w[i], R[i] @ l.com)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # reduced dynamics tree
 # ----------------------------------------------------------------------------------------------

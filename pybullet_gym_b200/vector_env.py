@@ -66,6 +66,8 @@ class VectorEnv:
         self.final_obs = torch.zeros(E, self.obs_dim, device=dev)
         self.truncated = torch.zeros(E, dtype=torch.uint8, device=dev)
         self._first_reset_done = False
+        self._ready = False          # a reset / set_state / restore has initialised the state
+        self._cand = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -111,7 +113,22 @@ class VectorEnv:
                 rc = self._L.pbg_reset(self._h, _ptr(m), int(floor_in_parts), _ptr(self.obs), self._stream())
         _lib.check(rc, self._h)
         self._first_reset_done = True
+        self._ready = True
         return self.obs
+
+    def seed(self, seed: int):
+        """Re-key the device counter RNG (reset noise, Flagrun flag positions, cube attacks); effective from the next reset."""
+        _lib.check(self._L.pbg_set_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF), self._h)
+
+    def _check_io(self, t: torch.Tensor, shape, dtype, name: str, cuda: bool):
+        """Cheap guards for the raw-pointer fast paths: a wrong device / dtype / stride / size would be silent garbage or an
+        out-of-bounds access that poisons the CUDA context."""
+        ok_dev = (t.device == self.device) if cuda else (t.device.type == "cpu")
+        if not (ok_dev and t.dtype == dtype and t.is_contiguous() and tuple(t.shape) == tuple(shape)):
+            raise ValueError("%s must be a contiguous %s tensor of shape %s on %s (got %s %s on %s, contiguous=%s)" % (
+                name, dtype, tuple(shape), self.device if cuda else "the host", t.dtype, tuple(t.shape), t.device, t.is_contiguous()))
+        if not self._ready:
+            raise RuntimeError("step before reset(): the env state is uninitialised")
 
     def step(self, actions: torch.Tensor):
         a = self._act(actions)
@@ -123,7 +140,9 @@ class VectorEnv:
         return self.obs, self.reward, self.done, info
 
     def step_fast(self, actions: torch.Tensor):
-        """step() without the optional outputs (reward terms, final obs, truncated)."""
+        """step() without the optional outputs (reward terms, final obs, truncated); `actions` must already be a contiguous
+        float32 [num_envs, action_dim] tensor on this env's device."""
+        self._check_io(actions, (self.num_envs, self.action_dim), torch.float32, "actions", True)
         with torch.cuda.device(self.device):
             rc = self._L.pbg_step(self._h, _ptr(actions), _ptr(self.obs), _ptr(self.reward), _ptr(self.done), None, None,
                                   None, self._stream())
@@ -133,7 +152,16 @@ class VectorEnv:
 
     def step_host(self, actions_host: torch.Tensor, obs_host: torch.Tensor, reward_host: torch.Tensor,
                   done_host: torch.Tensor):
-        """Host-buffer step through pbg_step_host: H2D actions, step, D2H obs/reward/done, synchronised."""
+        """Host-buffer step through pbg_step_host: H2D actions, step, D2H obs/reward/done, synchronised.  Ordered after
+        whatever this env enqueued before (reset() on torch's stream ...) by the library itself."""
+        E = self.num_envs
+        self._check_io(actions_host, (E, self.action_dim), torch.float32, "actions_host", False)
+        if obs_host is not None:
+            self._check_io(obs_host, (E, self.obs_dim), torch.float32, "obs_host", False)
+        if reward_host is not None:
+            self._check_io(reward_host, (E,), torch.float32, "reward_host", False)
+        if done_host is not None:
+            self._check_io(done_host, (E,), torch.uint8, "done_host", False)
         rc = self._L.pbg_step_host(self._h, _ptr(actions_host), _ptr(obs_host), _ptr(reward_host), _ptr(done_host))
         if rc:
             _lib.check(rc, self._h)
@@ -183,27 +211,45 @@ class VectorEnv:
         assert s.shape == (self.num_envs, self.state_dim)
         with torch.cuda.device(self.device):
             _lib.check(self._L.pbg_set_state(self._h, _ptr(s), self._stream()), self._h)
+        self._ready = True
+
+    def _io_tail(self):
+        return [self.obs, self.reward, self.done, self.terms, self.final_obs, self.truncated]
 
     def snapshot(self, pinned_host: bool = False) -> torch.Tensor:
-        """Opaque uint8 blob with the whole handle state (pbg_snapshot): physics, warm start, task bookkeeping, reset-RNG
-        counters, episode statistics.  On the device by default, in pinned host memory on request."""
+        """Opaque uint8 blob: the whole handle state (pbg_snapshot: physics, warm start, task bookkeeping, reset-RNG
+        counters, episode statistics) followed by this object's output buffers (obs, reward, done, reward terms, final obs,
+        truncated), so that restore() also brings back what the last step() returned.  On the device by default, in pinned
+        host memory on request."""
         n = int(self._L.pbg_snapshot_bytes(self._h))
-        buf = (torch.empty(n, dtype=torch.uint8).pin_memory() if pinned_host
-               else torch.empty(n, dtype=torch.uint8, device=self.device))
+        tail = torch.cat([t.reshape(-1).view(torch.uint8) for t in self._io_tail()])
+        total = n + tail.numel()
+        buf = (torch.empty(total, dtype=torch.uint8).pin_memory() if pinned_host
+               else torch.empty(total, dtype=torch.uint8, device=self.device))
         with torch.cuda.device(self.device):
             _lib.check(self._L.pbg_snapshot(self._h, _ptr(buf), self._stream()), self._h)
+            buf[n:].copy_(tail, non_blocking=True)
             if pinned_host:
                 torch.cuda.current_stream(self.device).synchronize()
         return buf
 
     def restore(self, blob: torch.Tensor, first_reset_done: bool = True):
         """Resume bit-identically from snapshot(); the blob may come from another VectorEnv of the same env id, batch size,
-        seed and env_offset.  The observation / reward buffers are not part of it: call observe() or step()."""
-        if blob.dtype != torch.uint8 or not blob.is_contiguous() or blob.numel() != int(self._L.pbg_snapshot_bytes(self._h)):
-            raise ValueError("not a snapshot of this env (size %d expected)" % int(self._L.pbg_snapshot_bytes(self._h)))
+        seed and env_offset.  self.obs / reward / done ... hold what they held when the snapshot was taken.  (observe() is
+        NOT a way to get the observation back: it is the task half of a step and has that step's side effects.)"""
+        n = int(self._L.pbg_snapshot_bytes(self._h))
+        tail_n = sum(t.numel() * t.element_size() for t in self._io_tail())
+        if blob.dtype != torch.uint8 or not blob.is_contiguous() or blob.numel() != n + tail_n:
+            raise ValueError("not a snapshot of this env (size %d expected)" % (n + tail_n))
         with torch.cuda.device(self.device):
             _lib.check(self._L.pbg_restore(self._h, _ptr(blob), self._stream()), self._h)
+            off = n
+            for t in self._io_tail():
+                nb = t.numel() * t.element_size()
+                t.reshape(-1).view(torch.uint8).copy_(blob[off:off + nb], non_blocking=True)
+                off += nb
         self._first_reset_done = bool(first_reset_done)    # host-side quirk flag Q1 (floor in robot.parts), not in the blob
+        self._ready = True
 
     def physics_step(self, actions: torch.Tensor, want_contacts: bool = False):
         a = self._act(actions)
@@ -232,6 +278,28 @@ class VectorEnv:
             with torch.cuda.device(self.device):
                 _lib.check(self._L.pbg_get_feet_contact(self._h, _ptr(out), self._stream()), self._h)
         return out[:, :n]
+
+    def task_view(self) -> dict:
+        """Task bookkeeping per env (pbg_get_task_view) as float64 tensors [E]: potential, walk_target_x/y, flag_timeout,
+        frame, on_ground_frame_counter, episode_steps, episode_return, initial_z, episode, attacks, flag_moves."""
+        out = torch.zeros(self.num_envs, _lib.TASK_VIEW_DIM, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pbg_get_task_view(self._h, _ptr(out), self._stream()), self._h)
+        return {f: out[:, i] for i, f in enumerate(_lib.TASK_VIEW_FIELDS)}
+
+    def enable_contact_export(self, enabled: bool = True):
+        _lib.check(self._L.pbg_enable_contact_export(self._h, int(enabled)), self._h)
+        self._cand = (torch.zeros(self.num_envs, max(1, self._L.pbg_num_contact_slots(self._h)), device=self.device)
+                      if enabled else None)
+
+    def contact_candidates(self) -> torch.Tensor:
+        """float[E, slots]: distance of every contact candidate in the last step's final collision pass, +inf where it is
+        not in contact; slot meaning: self.tables.contact_slots().  Needs enable_contact_export() before the step."""
+        if self._cand is None:
+            raise RuntimeError("call enable_contact_export() first")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pbg_get_contact_candidates(self._h, _ptr(self._cand), self._stream()), self._h)
+        return self._cand
 
     def stats(self, reset: bool = False) -> dict:
         st = _lib.PbgEpisodeStats()

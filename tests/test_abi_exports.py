@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 20
     for s in syms:
         assert hasattr(L, s), "libpbg_b200.so does not export %s" % s
-    assert L.pbg_version() == 100
+    assert L.pbg_version() == _lib.PBG_VERSION
     assert sorted(_lib.EXPORTS) == syms
 
 
