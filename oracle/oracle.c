@@ -170,6 +170,7 @@ struct orc_env {
     int cand_active[MAXCAND];
     double feet_touch[MAXFEET];  /* foot-vs-floor candidates under the breaking threshold in the last collide(), BEFORE the solver cap */
     int cap_overflow;            /* collide() calls in which max_contacts dropped candidates */
+    double done_margin;          /* distance of the last orc_observe's termination test from flipping (min over its comparisons) */
     double feet_margin[MAXFEET]; /* min over the foot's floor candidates of |distance - breaking threshold| in the last collide() */
     /* task state */
     double feet_contact[MAXFEET];
@@ -613,7 +614,9 @@ static void collide(orc_env *e) {
         v3 dl, d; v3sub(dl, cs, cb); m3mulv(d, Rx, dl);
         double len = v3norm(d), dist = len - m->g_radius[g];
         double thr = m->g_threshold[g] < m->cube_threshold ? m->g_threshold[g] : m->cube_threshold;
-        if (dist < thr && len > 1e-9) {
+        /* a capsule axis that passes through the box has len = 0 up to the bisection's resolution (1e-10 here, 2e-8 in the
+         * kernel's float32): no witness direction, no contact.  The cut-off sits above both resolutions. */
+        if (dist < thr && len > 1e-6) {
             contact *ct = &all[n++];
             ct->ga = g; ct->gb = -1; ct->la = m->g_link[g]; ct->lb = LINK_CUBE; ct->slot = slot;
             v3 csw, cbw; m3mulv(csw, Rx, cs); v3add(csw, csw, e->xp); m3mulv(cbw, Rx, cb); v3add(cbw, cbw, e->xp);
@@ -953,7 +956,16 @@ static int is_mjfloat(int kind) { return kind == ORC_KIND_ANT_MJ || kind == ORC_
 static int is_walker(int kind) { return (kind >= ORC_KIND_HOPPER && kind <= ORC_KIND_FLAGRUN_HARDER) || is_mjfloat(kind); }
 static double potential_leak(const orc_env *e);
 
+static void dmarg(orc_env *e, double v) { v = fabs(v); if (v < e->done_margin) e->done_margin = v; }
+
 static double alive_bonus(orc_env *e, double z, double pitch) {
+    switch (e->m.kind) {
+    case ORC_KIND_HOPPER: case ORC_KIND_WALKER2D: dmarg(e, z - 0.8); dmarg(e, fabs(pitch) - 1.0); break;
+    case ORC_KIND_HALFCHEETAH: dmarg(e, fabs(pitch) - 1.0); break;
+    case ORC_KIND_ANT: case ORC_KIND_ANT_MJ: dmarg(e, z - 0.26); break;
+    case ORC_KIND_FLAGRUN_HARDER: dmarg(e, z - 0.8); break;
+    default: dmarg(e, z - 0.78); break;
+    }
     switch (e->m.kind) {
     case ORC_KIND_HOPPER: case ORC_KIND_WALKER2D: return (z > 0.8 && fabs(pitch) < 1.0) ? 1 : -1;
     case ORC_KIND_HALFCHEETAH:
@@ -1141,6 +1153,7 @@ int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double
     const orc_model *m = &e->m;
     double t5[5] = {0, 0, 0, 0, 0};
     int done = 0;
+    e->done_margin = 1e30;
     if (is_mjwalker(m->kind)) {
         /* HopperMuJoCoEnv._step / Walker2DMuJoCoEnv._step (pybulletgym/envs/mujoco/gym_locomotion_envs.py:121-206) */
         double x = mjwalker_body_x(e);
@@ -1154,8 +1167,9 @@ int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double
         int ok = 1;
         for (int k = 0; k < m->obs_dim; k++) if (!isfinite(obs[k])) ok = 0;
         for (int k = 2; k < m->obs_dim; k++) if (!(fabs(obs[k]) < 100)) ok = 0;
-        if (m->kind == ORC_KIND_HOPPER_MJ) ok = ok && height > -0.3 && fabs(ang) < 0.2;
-        else ok = ok && 1.0 > height && height > -0.2 && -1.0 < ang && ang < 1.0;
+        if (m->kind == ORC_KIND_HOPPER_MJ) { ok = ok && height > -0.3 && fabs(ang) < 0.2; dmarg(e, height + 0.3); dmarg(e, fabs(ang) - 0.2); }
+        else { ok = ok && 1.0 > height && height > -0.2 && -1.0 < ang && ang < 1.0; dmarg(e, height - 1.0); dmarg(e, height + 0.2); dmarg(e, fabs(ang) - 1.0); }
+        for (int k = 2; k < m->obs_dim; k++) dmarg(e, fabs(obs[k]) - 100);
         done = !ok;
         *reward = t5[0] + t5[1] + t5[2];
     } else if (m->kind == ORC_KIND_REACHER) {
@@ -1177,11 +1191,11 @@ int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double
             double px = e->body_xyz[0], py = e->body_xyz[2];
             t5[0] = 10.0; t5[1] = -(0.01 * px * px + (py + 0.3 - 2) * (py + 0.3 - 2)); t5[2] = -0.0;
             if (m->kind == ORC_KIND_DOUBLE_PENDULUM_MJ) t5[2] = -(1e-3 * e->qd[1] * e->qd[1] + 5e-3 * e->qd[2] * e->qd[2]);
-            done = py + 0.3 <= 1;
+            done = py + 0.3 <= 1; dmarg(e, py + 0.3 - 1);
             *reward = t5[0] + t5[1] + t5[2];
         } else {
         if (m->kind == ORC_KIND_PENDULUM_SWINGUP) { t5[0] = cos(th); done = 0; }
-        else { t5[0] = 1.0; done = fabs(th) > 0.2; }
+        else { t5[0] = 1.0; done = fabs(th) > 0.2; dmarg(e, fabs(th) - 0.2); }
         *reward = t5[0];
         }
     } else {
@@ -1381,4 +1395,5 @@ long orc_episodes(orc_env *e, int n, int cap, uint64_t action_seed, double *retu
 }
 
 int orc_cap_overflows(const orc_env *e) { return e->cap_overflow; }
+double orc_done_margin(const orc_env *e) { return e->done_margin; }
 void orc_feet_margin(const orc_env *e, double *out) { for (int f = 0; f < e->m.nfeet; f++) out[f] = e->feet_margin[f]; }

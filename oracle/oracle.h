@@ -132,6 +132,9 @@ int orc_cap_overflows(const orc_env *e);
 /* per foot: how close its nearest floor candidate was to flipping the feet flag in the last collision pass
  * (min |distance - breaking threshold|); lets a test excuse exactly the flag disagreements that are round-off */
 void orc_feet_margin(const orc_env *e, double *out);
+/* how far the last orc_observe's termination test was from flipping: min |value - threshold| over the comparisons it made
+ * (z, pitch, pole angle ...; not the integer / flag inputs) */
+double orc_done_margin(const orc_env *e);
 
 #ifdef __cplusplus
 }

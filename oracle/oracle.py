@@ -112,6 +112,8 @@ def lib():
         L.orc_episodes.restype = C.c_long
         L.orc_cap_overflows.argtypes = [C.c_void_p]
         L.orc_feet_margin.argtypes = [C.c_void_p, _pd]
+        L.orc_done_margin.argtypes = [C.c_void_p]
+        L.orc_done_margin.restype = C.c_double
         _lib = L
     return _lib
 
@@ -248,8 +250,11 @@ class OracleEnv:
         self.obs_dim, self.nact = spec.obs_dim, spec.action_dim
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_destroy(self._h)
+        if getattr(self, "_h", None) and lib is not None:      # module globals may be gone at interpreter shutdown
+            try:
+                lib().orc_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def reset(self, noise=None, floor_in_parts: bool = True):
@@ -366,6 +371,9 @@ class OracleEnv:
         out = np.zeros(max(1, len(self.spec.foot_list)))
         lib().orc_feet_margin(self._h, out.ctypes.data_as(_pd))
         return out[:len(self.spec.foot_list)]
+
+    def done_margin(self) -> float:
+        return float(lib().orc_done_margin(self._h))
 
     def cap_overflows(self) -> int:
         return lib().orc_cap_overflows(self._h)

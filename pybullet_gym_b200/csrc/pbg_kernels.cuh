@@ -346,7 +346,9 @@ struct Env {
                     const V3 d = mulR(kb, xx - cc);
                     const float len = sqrtf(dot(d, d)), ra = m->p_ra[pi];
                     dist[p] = len - ra;
-                    act[p] = dist[p] < m->p_thr[pi] && len > 1e-9f;
+                    // an axis that passes through the box: len = 0 up to the bisection's resolution (2e-8 in float32), no
+                    // witness direction -> no contact; the cut-off sits above that resolution (same rule in oracle.c)
+                    act[p] = dist[p] < m->p_thr[pi] && len > 1e-6f;
                     const V3 n = (1.f / fmaxf(len, 1e-20f)) * d;
                     nn[p] = n; pa[p] = xb + mulR(kb, xx) - ra * n; pb[p] = xb + mulR(kb, cc);
                     }

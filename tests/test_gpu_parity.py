@@ -1,18 +1,19 @@
 """CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.  Run with -m gpu.
 
 Tiers (BASELINE.json north_star):
-  T1  calc_state / reward given identical state ............ 1e-5 abs (progress: 2e-5 * (1 + |x|), fp32 FK)
-  T2  single sub-step / single env step from identical state  stated below per quantity
-  T3  contact-free pendulum trajectory over a full episode . stated below
-  T4  contact envs: random-policy return / length distributions, two-sample KS, p > 0.01
+  T1  calc_state / reward / done / feet flags given identical state  1e-5 abs (progress: 2e-5 * (1 + |x|), fp32 FK);
+      done and feet flags exact except where the oracle itself sits within round-off of a threshold
+  T2  single sub-step / single env step from identical state  median bounds + EVERY sample bounded by K x the oracle's
+      own response to a 1e-7 perturbation of that same state
+  T3  contact-free pendulum trajectory over a full episode . 2e-4 after 100 steps, 1e-3 after 500 (all of the observation), drift-scaled at 1000
+  T4  contact envs: random-policy return / length distributions, 4096 CUDA vs 1024 oracle episodes, two-sample KS, p > 0.01
 The oracle's physics is parity-unpinned against pybullet (oracle/oracle.h); its task layer is pinned
 by tests/test_golden_task.py.
 
-Why T2 uses quantiles for contact states: the dynamics themselves amplify a 1e-7 (fp32 storage)
-perturbation of the state into up to ~4e-3 after one env step when stiff contacts / friction-cone
-switches are active (measured on the double-precision oracle in test_oracle_sensitivity_reference),
-so a max-norm bound at fp32 round-off level is not meaningful there; contact-free steps are held to
-1e-4 in max norm.
+Why T2's per-sample bound is relative to the oracle's own sensitivity: the dynamics themselves amplify a
+1e-7 (fp32 storage) perturbation of the state into up to ~4e-3 after one env step when stiff contacts /
+friction-cone switches are active (test_oracle_sensitivity_reference), so a fixed max-norm bound at fp32
+round-off level is not meaningful there; contact-free steps are held to 1e-4 in max norm.
 """
 import dataclasses
 
@@ -24,6 +25,8 @@ pytestmark = pytest.mark.gpu
 
 IDS = ["InvertedPendulumPyBulletEnv-v0", "InvertedDoublePendulumPyBulletEnv-v0", "ReacherPyBulletEnv-v0", "HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
        "AntPyBulletEnv-v0", "HumanoidPyBulletEnv-v0"]
+FLAGRUN_IDS = ["HumanoidFlagrunPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0"]
+PHYS_IDS = IDS + FLAGRUN_IDS
 TASK_IDS = IDS + ["HumanoidFlagrunPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0", "InvertedDoublePendulumMuJoCoEnv-v0",
                   "HopperMuJoCoEnv-v0", "Walker2DMuJoCoEnv-v0", "AntMuJoCoEnv-v0", "HumanoidMuJoCoEnv-v0"]
 E = 48
@@ -73,7 +76,10 @@ def test_device_rng_matches_oracle_rng(env_id, oracle_lib):
 
 @pytest.mark.parametrize("env_id", TASK_IDS)
 def test_observation_reward_parity_T1(env_id, oracle_lib):
-    """T1: calc_state + reward terms on identical states, states sampled along oracle rollouts."""
+    """T1: calc_state + reward terms + done on identical states, states sampled along oracle rollouts.  The whole
+    observation is compared, feet-flag tail included.  The flags calc_state sees are the ones each side latched from its OWN
+    previous physics step (quirk Q2), so an env takes part in the tail / HalfCheetah-done comparison only while the two sides'
+    flags agree; test_feet_flags_from_identical_state holds the flags themselves to the oracle."""
     env = _mk(env_id)
     rng = np.random.default_rng(3)
     nA = env.action_dim
@@ -82,7 +88,10 @@ def test_observation_reward_parity_T1(env_id, oracle_lib):
     orcs = _oracles(oracle_lib, env_id, E)
     for i, o in enumerate(orcs):
         o.reset(noise=noise[i].astype(np.float64), floor_in_parts=True)
-    worst_obs = worst_terms = worst_prog = 0.0
+    nf = len(env.spec.foot_list)
+    worst_obs = worst_terms = worst_prog = worst_tail = 0.0
+    same_flags = np.ones(E, bool)          # flags latched by the previous observe agree (both start from zeros)
+    n_done_cmp = n_done_true = n_tail_cmp = 0
     for t in range(30):
         a = (1.4 * rng.uniform(-1, 1, (E, nA))).astype(np.float32)          # |a| > 1: quirk Q3
         # advance both on their own physics (keeps feet flags / potentials in step), then pin the state
@@ -98,63 +107,173 @@ def test_observation_reward_parity_T1(env_id, oracle_lib):
         oobs = np.stack([r[0] for r in res])
         oterms = np.stack([r[3] for r in res])
         odone = np.array([r[2] for r in res])
-        nf = len(env.spec.foot_list)
-        body = slice(0, oobs.shape[1] - nf) if nf else slice(None)
+        margin = np.array([o.done_margin() for o in orcs])
+        body = slice(0, oobs.shape[1] - nf) if (nf and env.spec.kind < 11) else slice(None)
         worst_obs = max(worst_obs, np.abs(gobs[:, body] - oobs[:, body]).max())
+        if nf and env.spec.kind < 11 and same_flags.any():
+            tail = slice(oobs.shape[1] - nf, oobs.shape[1])
+            worst_tail = max(worst_tail, np.abs(gobs[same_flags, tail] - oobs[same_flags, tail]).max())
+            n_tail_cmp += int(same_flags.sum())
         if env.spec.kind in (12, 13):
             # MuJoCo-style walkers: terms[0] = dx / dt carries the fp32 error of x itself (x / 0.0165 * 6e-8)
             x = np.abs(ost[:, 0])
             worst_prog = max(worst_prog, (np.abs(gterms[:, 0] - oterms[:, 0]) / (1.0 + x)).max())
             gterms[:, 0] = oterms[:, 0]
-        worst_terms = max(worst_terms, np.abs(gterms[:, [0, 2, 3, 4]] - oterms[:, [0, 2, 3, 4]]).max())
+        # done: exact, except where the oracle's own test sits within fp32 round-off of its threshold (and, for the
+        # HalfCheetah, where the stale flags it reads differed)
+        cmp_ok = same_flags if env.spec.kind == 4 else np.ones(E, bool)
+        bad = (gdone.astype(bool) != odone) & cmp_ok
+        assert not (bad & (margin > 1e-5)).any(), (t, np.nonzero(bad)[0], margin[bad])
+        n_done_cmp += int(cmp_ok.sum()); n_done_true += int(odone.sum())
+        agree = ~bad & cmp_ok                  # the alive term flips with done: compare it where the decisions agree
+        worst_terms = max(worst_terms, np.abs(gterms[:, [2, 3, 4]] - oterms[:, [2, 3, 4]]).max())
+        if agree.any():
+            worst_terms = max(worst_terms, np.abs(gterms[agree, 0] - oterms[agree, 0]).max())
         if 2 <= env.spec.kind <= 8 or env.spec.kind in (14, 15):
-            x = np.abs(ost[:, 0] if env.spec.kind >= 5 else ost[:, 0])
+            x = np.abs(ost[:, 0])
             worst_prog = max(worst_prog, (np.abs(gterms[:, 1] - oterms[:, 1]) / (1.0 + x)).max())
-            # alive / done decisions agree except within float32 round-off of a threshold
-            assert (gdone.astype(bool) != odone).mean() <= 0.05
+        if nf:
+            gf = env.feet_contact().cpu().numpy()
+            of = np.stack([o.feet_contact() for o in orcs])
+            same_flags = (gf == of).all(axis=1)
     assert worst_obs < 1e-5, worst_obs
+    assert worst_tail == 0.0, worst_tail
     assert worst_terms < 1e-5, worst_terms
     assert worst_prog < 2e-5, worst_prog
+    if nf and env.spec.kind < 11:
+        assert n_tail_cmp > 0.8 * 30 * E, n_tail_cmp          # the excuse is the exception
+    assert n_done_cmp > 0.8 * 30 * E
 
 
-@pytest.mark.parametrize("env_id", IDS)
+@pytest.mark.parametrize("env_id", ["HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0", "AntPyBulletEnv-v0",
+                                    "HumanoidPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0"])
+def test_feet_flags_from_identical_state(env_id, oracle_lib):
+    """robot.feet_contact (rs/gym_locomotion_envs.py:69-78) after one physics step from an identical state, CUDA vs oracle.
+    With frame_skip = 1 the step's only collision pass runs on the identical state itself, so the flags must agree exactly
+    except for a foot whose nearest candidate lies within 1e-6 m of its breaking threshold (fp32 FK round-off); with the
+    real frame_skip = 4 the last pass runs after three sub-steps of each side's own dynamics, and a disagreement is
+    excused only within 10x that env's own position difference after the step (+1e-6)."""
+    from pybullet_gym_b200.spec import SPECS
+    spec = SPECS[env_id]
+    spec1 = dataclasses.replace(spec, scene=dataclasses.replace(spec.scene, frame_skip=1))
+    env4, env1 = _mk(env_id), _mk(env_id, spec=spec1)
+    rng = np.random.default_rng(17)
+    nA = env4.action_dim
+    noise = rng.uniform(-0.1, 0.1, (E, env4.noise_dim)).astype(np.float32)
+    env4.reset(joint_noise=torch.from_numpy(noise), floor_in_parts=True); env1.reset(joint_noise=torch.from_numpy(noise), floor_in_parts=True)
+    orcs, orcs1 = _oracles(oracle_lib, env_id, E), _oracles(oracle_lib, env_id, E, spec=spec1)
+    for i in range(E):
+        orcs[i].reset(noise=noise[i].astype(np.float64), floor_in_parts=True)
+        orcs1[i].reset(noise=noise[i].astype(np.float64), floor_in_parts=True)
+    nflag = n_on = n_excused1 = n_excused4 = 0
+    for t in range(60):
+        a = rng.uniform(-1, 1, (E, nA)).astype(np.float32)
+        ost = np.stack([o.get_state() for o in orcs]).astype(np.float32)
+        ta = torch.from_numpy(a)
+        for envx in (env4, env1):
+            envx.set_state(torch.from_numpy(ost))
+            envx.physics_step(ta)
+        g4 = env4.get_state().cpu().numpy()
+        env4.observe(ta); env1.observe(ta)               # latches the step's flags (quirk Q2)
+        gf4, gf1 = env4.feet_contact().cpu().numpy(), env1.feet_contact().cpu().numpy()
+        of4, of1, m4, m1, o4 = [], [], [], [], []
+        for i in range(E):
+            for o, fl, mg in ((orcs[i], of4, m4), (orcs1[i], of1, m1)):
+                o.set_state(ost[i].astype(np.float64))
+                o.physics_step(a[i].astype(np.float64))
+                mg.append(o.feet_margin())
+                if o is orcs[i]:
+                    o4.append(o.get_state())
+                o.observe(a[i].astype(np.float64))
+                fl.append(o.feet_contact())
+        of4, of1, m4, m1, o4 = np.stack(of4), np.stack(of1), np.stack(m4), np.stack(m1), np.stack(o4)
+        bad1 = gf1 != of1
+        assert not (bad1 & (m1 > 1e-6)).any(), (t, np.argwhere(bad1), m1[bad1])
+        poserr = np.abs(g4 - o4).max(axis=1)[:, None]
+        bad4 = gf4 != of4
+        assert not (bad4 & (m4 > 10 * poserr + 1e-6)).any(), (t, np.argwhere(bad4), m4[bad4], poserr[bad4.any(axis=1)])
+        nflag += of1.size; n_on += int(of1.sum()); n_excused1 += int(bad1.sum()); n_excused4 += int(bad4.sum())
+    assert n_on > 0.05 * nflag and n_on < 0.98 * nflag, (n_on, nflag)       # both outcomes are exercised
+    assert n_excused1 <= 0.001 * nflag and n_excused4 <= 0.01 * nflag, (n_excused1, n_excused4, nflag)
+
+
+def _throw_cube_at_robots(ost, rng, frac=0.5):
+    """FlagrunHarder T2 states: put the cube next to a fraction of the robots, moving at them (canonical state:
+    [base pos3 quat4 omega3 vel3][q 17][qd 17][cube pos3 quat4 omega3 vel3])."""
+    n = ost.shape[0]
+    pick = rng.uniform(size=n) < frac
+    ang = rng.uniform(-np.pi, np.pi, n)
+    d = np.stack([np.cos(ang), np.sin(ang), np.zeros(n)], 1)
+    pos = ost[:, 0:3] + 0.30 * d + np.stack([np.zeros(n), np.zeros(n), rng.uniform(-0.35, 0.25, n)], 1)
+    vel = -d * rng.uniform(2.0, 12.0, n)[:, None]
+    ost = ost.copy()
+    ost[pick, -13:-10] = pos[pick]
+    ost[pick, -6:-3] = 0.0
+    ost[pick, -3:] = vel[pick]
+    return ost
+
+
+T2_K = 500.0            # per-sample bound: K x (oracle's response to 1e-7 perturbations of the same state), floored at T2_FLOOR
+T2_FLOOR = 1e-4
+
+
+@pytest.mark.parametrize("env_id", PHYS_IDS)
 def test_single_substep_and_step_parity_T2(env_id, oracle_lib):
+    """T2: one sub-step (frame_skip = 1) and one env step (4 sub-steps) from identical states: ABA-equivalent dynamics, limit /
+    contact rows, 5 PGS sweeps, integration.  Every sample is bounded: its error may not exceed T2_K times what NPERT 1e-7-sized
+    perturbations of that same state do to the double-precision oracle (floor T2_FLOOR); medians are held to fixed bounds."""
     from pybullet_gym_b200.spec import SPECS
     spec = SPECS[env_id]
     spec1 = dataclasses.replace(spec, scene=dataclasses.replace(spec.scene, frame_skip=1))
     env4, env1 = _mk(env_id), _mk(env_id, spec=spec1)
     rng = np.random.default_rng(5)
     nA = env4.action_dim
+    NPERT = 4
     noise = rng.uniform(-0.1, 0.1, (E, env4.noise_dim)).astype(np.float32)
     env4.reset(joint_noise=torch.from_numpy(noise)); env1.reset(joint_noise=torch.from_numpy(noise))
     orcs = _oracles(oracle_lib, env_id, E)
     orcs1 = _oracles(oracle_lib, env_id, E, spec=spec1)
+    twin4 = [_oracles(oracle_lib, env_id, E) for _ in range(NPERT)]
+    twin1 = [_oracles(oracle_lib, env_id, E, spec=spec1) for _ in range(NPERT)]
     for i, o in enumerate(orcs):
-        o.reset(noise=noise[i].astype(np.float64))
-        orcs1[i].reset(noise=noise[i].astype(np.float64))
-    errs1, errs4, free4 = [], [], []
+        for x in [o, orcs1[i]] + [tw[i] for tw in twin4 + twin1]:
+            x.reset(noise=noise[i].astype(np.float64))
+    errs1, errs4, free4, sens1, sens4 = [], [], [], [], []
     for t in range(40):
         a = rng.uniform(-1, 1, (E, nA)).astype(np.float32)
         ost = np.stack([o.get_state() for o in orcs]).astype(np.float32)
+        if env_id == "HumanoidFlagrunHarderPyBulletEnv-v0" and t % 4 == 1:
+            ost = _throw_cube_at_robots(ost, rng).astype(np.float32)
         for envx in (env4, env1):
             envx.set_state(torch.from_numpy(ost))
-        for i in range(E):
-            orcs[i].set_state(ost[i].astype(np.float64)); orcs1[i].set_state(ost[i].astype(np.float64))
         n4 = env4.physics_step(torch.from_numpy(a), want_contacts=True).cpu().numpy()
         env1.physics_step(torch.from_numpy(a))
         g4, g1 = env4.get_state().cpu().numpy(), env1.get_state().cpu().numpy()
+        pert = [rng.normal(size=ost.shape) * 1e-7 * (1 + np.abs(ost)) for _ in range(NPERT)]
+        o4, o1, s4, s1, on4 = [], [], [], [], []
         for i in range(E):
-            orcs[i].physics_step(a[i].astype(np.float64)); orcs1[i].physics_step(a[i].astype(np.float64))
-        o4 = np.stack([o.get_state() for o in orcs]); o1 = np.stack([o.get_state() for o in orcs1])
-        on4 = np.array([o.num_contacts() for o in orcs])
+            ai, si = a[i].astype(np.float64), ost[i].astype(np.float64)
+            orcs[i].set_state(si); orcs1[i].set_state(si)
+            orcs[i].physics_step(ai); orcs1[i].physics_step(ai)
+            r4, r1 = orcs[i].get_state(), orcs1[i].get_state()
+            d4 = d1 = 0.0
+            for k in range(NPERT):
+                twin4[k][i].set_state(si + pert[k][i]); twin1[k][i].set_state(si + pert[k][i])
+                twin4[k][i].physics_step(ai); twin1[k][i].physics_step(ai)
+                d4 = max(d4, _rel(twin4[k][i].get_state(), r4).max()); d1 = max(d1, _rel(twin1[k][i].get_state(), r1).max())
+            o4.append(r4); o1.append(r1); s4.append(d4); s1.append(d1); on4.append(orcs[i].num_contacts())
+        o4, o1, on4 = np.stack(o4), np.stack(o1), np.array(on4)
         errs1.append(_rel(g1, o1).max(axis=1)); errs4.append(_rel(g4, o4).max(axis=1))
+        sens1.append(np.array(s1)); sens4.append(np.array(s4))
         free4.append((on4 == 0) & (n4 == 0))
         assert np.isfinite(g4).all()
     e1, e4, fr = np.concatenate(errs1), np.concatenate(errs4), np.concatenate(free4)
-    # one sub-step (ABA-equivalent dynamics + limit/contact rows + 5 PGS sweeps + integration)
-    assert np.median(e1) < 2e-5 and np.quantile(e1, 0.99) < 5e-3, (np.median(e1), np.quantile(e1, 0.99), e1.max())
-    # one env step = 4 sub-steps
-    assert np.median(e4) < 1e-4 and np.quantile(e4, 0.95) < 2e-2, (np.median(e4), np.quantile(e4, 0.95), e4.max())
+    b1, b4 = np.maximum(T2_FLOOR, T2_K * np.concatenate(sens1)), np.maximum(T2_FLOOR, T2_K * np.concatenate(sens4))
+    print("\n  [T2 %s] sub-step: median %.1e max %.1e worst err/bound %.2f | step: median %.1e max %.1e worst err/bound %.2f"
+          % (env_id, np.median(e1), e1.max(), (e1 / b1).max(), np.median(e4), e4.max(), (e4 / b4).max()))
+    assert np.median(e1) < 2e-5 and np.median(e4) < 1e-4, (np.median(e1), np.median(e4))
+    assert (e1 <= b1).all(), ("sub-step", np.argmax(e1 / b1), (e1 / b1).max(), e1.max())
+    assert (e4 <= b4).all(), ("step", np.argmax(e4 / b4), (e4 / b4).max(), e4.max())
     if env_id in ("InvertedPendulumPyBulletEnv-v0", "InvertedDoublePendulumPyBulletEnv-v0", "ReacherPyBulletEnv-v0",
                   "AntPyBulletEnv-v0") and fr.any():
         # contact-free env steps (pendulum always; Ant while airborne) are held to a max-norm bound
@@ -162,7 +281,7 @@ def test_single_substep_and_step_parity_T2(env_id, oracle_lib):
 
 
 def test_oracle_sensitivity_reference(oracle_lib):
-    """Documents the conditioning T2's quantile bounds rest on: the double-precision oracle, perturbed
+    """Documents the conditioning T2's per-sample bounds rest on: the double-precision oracle, perturbed
     by a float32-storage-sized 1e-7, moves by > 1e-5 after one Ant env step once contacts are active."""
     rng = np.random.default_rng(0)
     a_env, b_env = oracle_lib.OracleEnv("AntPyBulletEnv-v0", max_contacts=8), oracle_lib.OracleEnv("AntPyBulletEnv-v0", max_contacts=8)
@@ -178,7 +297,9 @@ def test_oracle_sensitivity_reference(oracle_lib):
 
 
 def test_pendulum_full_episode_trajectory_T3(oracle_lib):
-    """Contact-free cart-pole, 1000 steps, fixed action tape (small actions keep it from diverging fast)."""
+    """Contact-free cart-pole, 1000 steps, fixed action tape (small actions keep it from diverging fast): the whole
+    observation (x, vx, cos, sin, theta_dot) within 2e-4 after 100 steps, 1e-3 after 500, and after the full episode within
+    max(1e-3, 100 x the drift of the double-precision oracle under a 1e-7 perturbation of the reset angle)."""
     env_id = "InvertedPendulumSwingupPyBulletEnv-v0"      # never terminates: a full 1000-step episode
     n = 16
     env = _mk(env_id, n=n)
@@ -186,19 +307,31 @@ def test_pendulum_full_episode_trajectory_T3(oracle_lib):
     noise = rng.uniform(-0.1, 0.1, (n, 1)).astype(np.float32)
     env.reset(joint_noise=torch.from_numpy(noise))
     orcs = [oracle_lib.OracleEnv(env_id) for _ in range(n)]
+    twins = [[oracle_lib.OracleEnv(env_id) for _ in range(n)] for _ in range(3)]
     for i, o in enumerate(orcs):
         o.reset(noise=noise[i].astype(np.float64))
+        for tw in twins:
+            tw[i].reset(noise=noise[i].astype(np.float64) + rng.normal() * 1e-7)
     tape = rng.uniform(-1, 1, (1000, n, 1)).astype(np.float32) * 0.3
-    err100 = 0.0
+    err100 = err500 = drift = 0.0
     for t in range(1000):
         obs, rew, done, _ = env.step(torch.from_numpy(tape[t]))
         res = [o.step(tape[t, i].astype(np.float64)) for i, o in enumerate(orcs)]
+        for tw in twins:
+            for i in range(n):
+                drift = max(drift, np.abs(tw[i].step(tape[t, i].astype(np.float64))[0] - res[i][0]).max())
         if t == 99:
             err100 = np.abs(obs.cpu().numpy() - np.stack([r[0] for r in res])).max()
+        if t == 499:
+            err500 = np.abs(obs.cpu().numpy() - np.stack([r[0] for r in res])).max()
     oobs = np.stack([r[0] for r in res])
     gobs = obs.cpu().numpy()
     assert err100 < 2e-4, err100                       # 100 steps: fp32 round-off accumulates ~1e-6 per step
-    assert np.abs(gobs[:, :4] - oobs[:, :4]).max() < 5e-2, np.abs(gobs - oobs).max()   # full episode drift bound
+    assert err500 < 1e-3, err500                       # 500 steps, every component
+    # full episode: the swinging pole is mildly chaotic -- a 1e-7 perturbation of the reset angle moves the double-precision
+    # oracle itself by ~1e-3 after 1000 steps -- so the bound follows that drift
+    bound = max(1e-3, 100.0 * drift)
+    assert np.abs(gobs - oobs).max() < bound, (np.abs(gobs - oobs).max(axis=0), drift)
     assert np.isfinite(gobs).all()
 
 
@@ -207,56 +340,75 @@ def _ks_pvalue(a, b):
     return ks_2samp(a, b).pvalue
 
 
-@pytest.mark.parametrize("env_id", ["HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
-                                    "AntPyBulletEnv-v0", "HumanoidPyBulletEnv-v0"])
+T4_CAP = {"HopperPyBulletEnv-v0": 1000, "Walker2DPyBulletEnv-v0": 1000, "HalfCheetahPyBulletEnv-v0": 1000,
+          "AntPyBulletEnv-v0": 300, "HumanoidPyBulletEnv-v0": 300, "HumanoidFlagrunPyBulletEnv-v0": 300,
+          "HumanoidFlagrunHarderPyBulletEnv-v0": 300}
+
+
+@pytest.mark.parametrize("env_id", list(T4_CAP))
 def test_random_policy_distributions_T4(env_id, oracle_lib):
-    """T4: episode length and return distributions under U(-1,1) actions, CUDA vs oracle (two-sample KS)."""
-    short = env_id != "AntPyBulletEnv-v0"
-    n = 1024 if short else 256
-    cap = 200 if short else 120          # Ant rarely terminates: compare the first `cap` steps' return
+    """T4: episode length and return distributions under U(-1,1) actions, 4096 CUDA episodes vs 1024 oracle episodes
+    (two-sample KS, p > 0.01 on both).  Whole episodes (TimeLimit 1000) for Hopper / Walker2D / HalfCheetah; the first 300
+    steps for the Ant and the Humanoids, whose random-policy episodes are cut by the cap rarely / never."""
+    n, m, cap = 4096, 1024, T4_CAP[env_id]
     env = _mk(env_id, n=n, seed=100)
     env.reset(floor_in_parts=True)
     gen = torch.Generator(device="cuda").manual_seed(0)
     ret = torch.zeros(n, device="cuda"); length = torch.zeros(n, device="cuda"); alive = torch.ones(n, device="cuda")
     for t in range(cap):
         a = torch.rand(n, env.action_dim, device="cuda", generator=gen) * 2 - 1
-        obs, rew, done, _ = env.step(a)
+        obs, rew, done = env.step_fast(a)
         ret += alive * rew; length += alive
         alive = alive * (1 - done.float())
+        if t % 50 == 49 and float(alive.sum()) == 0:
+            break
     g_ret, g_len = ret.cpu().numpy(), length.cpu().numpy()
     from pybullet_gym_b200 import _lib
     from pybullet_gym_b200.spec import SPECS
     mc = _lib.lib().pbg_max_contacts(SPECS[env_id].kind)
-    m = 256 if short else 96
-    rng = np.random.default_rng(1)
-    o_ret, o_len = [], []
-    for i in range(m):
-        o = oracle_lib.OracleEnv(env_id, seed=200, env_index=i, max_contacts=mc)
-        o.reset(floor_in_parts=True)
-        r_sum, n_steps = 0.0, 0
-        for t in range(cap):
-            obs, r, d, _ = o.step(rng.uniform(-1, 1, env.action_dim))
-            r_sum += r; n_steps += 1
-            if d:
-                break
-        o_ret.append(r_sum); o_len.append(n_steps)
-    p_len, p_ret = _ks_pvalue(g_len, np.array(o_len)), _ks_pvalue(g_ret, np.array(o_ret))
+    o_ret, o_len = oracle_lib.random_policy_episodes(env_id, m, cap, seed=200, max_contacts=mc)
+    p_len, p_ret = _ks_pvalue(g_len, o_len), _ks_pvalue(g_ret, o_ret)
+    print("\n  [T4 %s] len %.1f vs %.1f  return %.2f vs %.2f  p_len %.3f p_ret %.3f" % (env_id, g_len.mean(), o_len.mean(), g_ret.mean(), o_ret.mean(), p_len, p_ret))
     assert p_len > 0.01 and p_ret > 0.01, (p_len, p_ret, g_len.mean(), np.mean(o_len), g_ret.mean(), np.mean(o_ret))
 
 
+GOLD_K = 200.0
+
+
 @pytest.mark.parametrize("env_id", IDS)
-def test_golden_reference_rollout_prefix(env_id):
-    """The CUDA path replays the reset noise / actions of the golden files (recorded from the reference's
-    own Python on oracle physics): reset observation to 1e-5, first steps within fp32 drift."""
-    import glob, json, os
+def test_golden_reference_rollouts_whole_episodes(env_id, oracle_lib):
+    """The CUDA path replays the reset noise / actions of the golden files (recorded from the reference's own Python on
+    oracle physics) over the WHOLE recorded episodes, free running.  Reset observation to 1e-5.  At step t the deviation
+    may not exceed GOLD_K x the drift of the double-precision oracle itself when its reset noise is perturbed by 1e-7
+    (max over 3 twins; floor 2e-5 (t + 1)): contact dynamics amplify round-off, so the bound follows the trajectory's own
+    conditioning instead of a fixed number.  done flags must agree wherever the bound is below the threshold margin."""
+    import json, os
     path = os.path.join(os.path.dirname(__file__), "golden", "task_%s.json" % env_id.split("PyBullet")[0])
     g = json.load(open(path))
     env = _mk(env_id, n=1)
+    rng = np.random.default_rng(23)
+    worst_ratio = 0.0
+    nsteps = 0
     for ei, ep in enumerate(g["episodes"]):
+        noise = np.array(ep["noise"], np.float64)
         obs0 = env.reset(joint_noise=torch.tensor([ep["noise"]], dtype=torch.float32), floor_in_parts=ei > 0)
         assert np.abs(obs0.cpu().numpy()[0] - np.array(ep["obs0"])).max() < 1e-5
-        for t, st in enumerate(ep["steps"][:3]):
+        twins = [oracle_lib.OracleEnv(env_id) for _ in range(3)]
+        for tw in twins:
+            tw.reset(noise=noise + rng.normal(size=noise.shape) * 1e-7, floor_in_parts=ei > 0)
+        drift = 0.0
+        for t, st in enumerate(ep["steps"]):
+            a = np.array(st["a"], np.float64)
+            gold = np.array(st["obs"])
             obs, rew, done, info = env.step(torch.tensor([st["a"]], dtype=torch.float32))
-            assert np.abs(obs.cpu().numpy()[0] - np.array(st["obs"])).max() < 2e-3
-            assert abs(float(rew[0]) - st["reward"]) < 5e-3
-            assert bool(done[0]) == st["done"]
+            for tw in twins:
+                drift = max(drift, np.abs(tw.step(a)[0] - gold).max())          # running max: drift does not shrink
+            bound = max(2e-5 * (t + 1), GOLD_K * drift)
+            err = np.abs(obs.cpu().numpy()[0] - gold).max()
+            worst_ratio = max(worst_ratio, err / bound)
+            assert err <= bound, (ei, t, err, bound)
+            assert abs(float(rew[0]) - st["reward"]) <= 100 * bound + 1e-4, (ei, t, float(rew[0]), st["reward"], bound)
+            if bound < 1e-3:
+                assert bool(done[0]) == st["done"], (ei, t)
+            nsteps += 1
+    print("\n  [golden %s] %d steps, worst err / bound %.3f" % (env_id, nsteps, worst_ratio))
