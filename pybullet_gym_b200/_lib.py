@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import subprocess
 from typing import Optional
 
@@ -80,19 +81,46 @@ TASK_VIEW_FIELDS = ("potential", "walk_target_x", "walk_target_y", "flag_timeout
                     "episode_steps", "episode_return", "initial_z", "episode", "attacks", "flag_moves")
 
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+BUILD_DIR = os.path.join(CSRC, "_build")
 
 
-def build_extension(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into libpbg_b200.so for sm_100a (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
-    srcs.append(os.path.join(INCLUDE, "pbg.h"))
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+def build_extension(force: bool = False, verbose: bool = False, jobs: Optional[int] = None, extra_flags=()) -> str:
+    """Compile csrc/*.cu into libpbg_b200.so for sm_100a (cross-compiles without a GPU).  One object per translation unit
+    (pbg_abi.cu + one pbg_k_*.cu per kernel configuration group), compiled in parallel, objects cached under csrc/_build."""
+    from concurrent.futures import ThreadPoolExecutor
+    headers = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")] + [os.path.join(INCLUDE, "pbg.h")]
+    units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+    flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+    stamp = os.path.join(BUILD_DIR, "flags.txt")
+    if (open(stamp).read() if os.path.exists(stamp) else None) != " ".join(flags):
+        force = True
+
+    def obj_of(u):
+        return os.path.join(BUILD_DIR, os.path.basename(u)[:-3] + ".o")
+
+    stale = [u for u in units if force or not os.path.exists(obj_of(u))
+             or os.path.getmtime(obj_of(u)) < max(hdr_time, os.path.getmtime(u))]
+    objs = [obj_of(u) for u in units]
+    if not stale and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(o) for o in objs):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH, os.path.join(CSRC, "pbg_abi.cu")]
-    subprocess.check_call(cmd)
+
+    def compile_one(u):
+        r = subprocess.run(["nvcc"] + flags + ["-c", "-o", obj_of(u), u], capture_output=True, text=True)
+        return u, r
+
+    # the big units first, so that the longest compile starts at once
+    stale.sort(key=lambda u: -os.path.getsize(u) - (1 << 20) * any(k in u for k in ("harder", "humanoid")))
+    with ThreadPoolExecutor(max_workers=jobs or min(len(stale) or 1, os.cpu_count() or 1)) as ex:
+        for u, r in ex.map(compile_one, stale):
+            if verbose and (r.stdout or r.stderr):
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed on %s:\n%s" % (u, r.stdout + r.stderr))
+    subprocess.check_call(["nvcc", "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    open(stamp, "w").write(" ".join(flags))
     return LIB_PATH
 
 

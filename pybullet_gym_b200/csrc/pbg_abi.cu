@@ -1,7 +1,7 @@
 // C ABI of libpbg_b200.so (see include/pbg.h): host-side model flattening, state allocation and
 // kernel dispatch.  One handle = one env kind x num_envs worlds on one device.
 #include "../../include/pbg.h"
-#include "pbg_kernels.cuh"
+#include "pbg_cfgs.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -11,69 +11,22 @@
 
 using namespace pbg;
 
-// kernel configurations: NB, NJ, FLOATING, NLIM, MAXC, LPE, NCAND, NPAIR, NFEET, NACT, OBS, WARPS per CTA, CTAs per SM
-// 14 warps x 2 envs = 28 envs per CTA = one CTA per SM (7.2 KB shared memory per env): 148 CTAs hold 4144 envs.
-using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5, 4, 4>;
-using CfgDoublePendulum = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 9, 4, 4, 0, 2>;
-using CfgDoublePendulumMJ = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 11, 4, 4, 0, 2>;
-using CfgReacher = KCfg<4, 4, 0, 3, 0, 16, 0, 0, 0, 2, 9, 4, 4, 0, 4>;
-using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15, 14, 1>;
-using CfgHopperMJ = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 11, 14, 1, 0, 6>;
-using CfgWalkerMJ = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 17, 14, 1, 0, 9>;
-using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1>;
-using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1>;
-#ifndef PBG_ANT_WARPS
-#define PBG_ANT_WARPS 14
-#define PBG_ANT_BLOCKS 1
-#endif
-using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28, PBG_ANT_WARPS, PBG_ANT_BLOCKS>;
-using CfgAntMJ = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 111, PBG_ANT_WARPS, PBG_ANT_BLOCKS>;
-using CfgHumanoidMJ = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 376, 7, 1>;
-using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1>;
-// HumanoidFlagrunHarder: the humanoid + the cube (one more free body, 8 corner candidates, 17 geom-vs-cube pairs)
-using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17>;
-
-struct KernelInfo {
-    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet, nnoise, ysz, off_task, nslot;
-    size_t smem;
-    void (*launch)(const DevModel *, const StepBuffers &, const LaunchArgs &, cudaStream_t);
-    cudaError_t (*prepare)();
-};
-
-template <class C>
-static void launch_cfg(const DevModel *m, const StepBuffers &b, const LaunchArgs &la, cudaStream_t s) {
-    const int blocks = (la.E + C::EPB - 1) / C::EPB;
-    if (la.mode == MODE_POLICY) env_kernel<C, true><<<blocks, C::THREADS, C::SMEM_BYTES, s>>>(m, b, la);
-    else env_kernel<C, false><<<blocks, C::THREADS, C::SMEM_BYTES, s>>>(m, b, la);
-}
-template <class C>
-static cudaError_t prepare_cfg() {
-    cudaError_t e = cudaFuncSetAttribute(env_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(env_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-}
-template <class C>
-static KernelInfo info_of() {
-    return KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
-}
-
 static bool kernel_for_kind(int kind, KernelInfo *out) {
     switch (kind) {
-    case PBG_KIND_PENDULUM: case PBG_KIND_PENDULUM_SWINGUP: *out = info_of<CfgPendulum>(); return true;
-    case PBG_KIND_DOUBLE_PENDULUM: *out = info_of<CfgDoublePendulum>(); return true;
-    case PBG_KIND_DOUBLE_PENDULUM_MJ: *out = info_of<CfgDoublePendulumMJ>(); return true;
-    case PBG_KIND_REACHER: *out = info_of<CfgReacher>(); return true;
-    case PBG_KIND_HOPPER: *out = info_of<CfgHopper>(); return true;
-    case PBG_KIND_WALKER2D: *out = info_of<CfgWalker>(); return true;
-    case PBG_KIND_HOPPER_MJ: *out = info_of<CfgHopperMJ>(); return true;
-    case PBG_KIND_WALKER2D_MJ: *out = info_of<CfgWalkerMJ>(); return true;
-    case PBG_KIND_HALFCHEETAH: *out = info_of<CfgCheetah>(); return true;
-    case PBG_KIND_ANT: *out = info_of<CfgAnt>(); return true;
-    case PBG_KIND_ANT_MJ: *out = info_of<CfgAntMJ>(); return true;
-    case PBG_KIND_HUMANOID_MJ: *out = info_of<CfgHumanoidMJ>(); return true;
-    case PBG_KIND_HUMANOID: case PBG_KIND_FLAGRUN: *out = info_of<CfgHumanoid>(); return true;
-    case PBG_KIND_FLAGRUN_HARDER: *out = info_of<CfgHarder>(); return true;
+    case PBG_KIND_PENDULUM: case PBG_KIND_PENDULUM_SWINGUP: *out = info_Pendulum(); return true;
+    case PBG_KIND_DOUBLE_PENDULUM: *out = info_DoublePendulum(); return true;
+    case PBG_KIND_DOUBLE_PENDULUM_MJ: *out = info_DoublePendulumMJ(); return true;
+    case PBG_KIND_REACHER: *out = info_Reacher(); return true;
+    case PBG_KIND_HOPPER: *out = info_Hopper(); return true;
+    case PBG_KIND_WALKER2D: *out = info_Walker(); return true;
+    case PBG_KIND_HOPPER_MJ: *out = info_HopperMJ(); return true;
+    case PBG_KIND_WALKER2D_MJ: *out = info_WalkerMJ(); return true;
+    case PBG_KIND_HALFCHEETAH: *out = info_Cheetah(); return true;
+    case PBG_KIND_ANT: *out = info_Ant(); return true;
+    case PBG_KIND_ANT_MJ: *out = info_AntMJ(); return true;
+    case PBG_KIND_HUMANOID_MJ: *out = info_HumanoidMJ(); return true;
+    case PBG_KIND_HUMANOID: case PBG_KIND_FLAGRUN: *out = info_Humanoid(); return true;
+    case PBG_KIND_FLAGRUN_HARDER: *out = info_Harder(); return true;
     default: return false;
     }
 }
