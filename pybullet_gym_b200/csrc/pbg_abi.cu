@@ -702,6 +702,15 @@ int pbg_get_task_view(pbg_handle *h, double *out_dev, void *stream) {
     return PBG_OK;
 }
 
+// development only (not in pbg.h): per-phase cycle counters of builds made with -DPBG_PHASE_CLOCKS
+extern "C" int pbg_debug_phases(pbg_handle *h, unsigned long long *out32, int reset) {
+    if (!h || !out32) return PBG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    h->k.phases(out32, reset);
+    return PBG_OK;
+}
+
 int pbg_num_contact_slots(const pbg_handle *h) { return h ? h->k.nslot : PBG_ERR_INVALID; }
 
 int pbg_enable_contact_export(pbg_handle *h, int32_t enabled) {

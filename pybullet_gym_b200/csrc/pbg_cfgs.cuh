@@ -11,6 +11,7 @@ struct KernelInfo {
     size_t smem;
     void (*launch)(const DevModel *, const StepBuffers &, const LaunchArgs &, cudaStream_t);
     cudaError_t (*prepare)();
+    void (*phases)(unsigned long long *out32, int reset);   // development builds (-DPBG_PHASE_CLOCKS): per-phase cycle sums
 };
 
 #define PBG_FOR_EACH_CFG(X) \

@@ -23,7 +23,11 @@ using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1>;
 using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28, PBG_ANT_WARPS, PBG_ANT_BLOCKS>;
 using CfgAntMJ = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 111, PBG_ANT_WARPS, PBG_ANT_BLOCKS>;
 using CfgHumanoidMJ = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 376, 7, 1>;
+#ifdef PBG_EXP_HUM14
+using CfgHumanoid = KCfg<18, 17, 1, 17, 7, 32, 30, 66, 2, 17, 44, 14, 1>;   // timing probe: 14 warps per SM, contact cap 7
+#else
 using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1>;
+#endif
 // HumanoidFlagrunHarder: the humanoid + the cube (one more free body, 8 corner candidates, 17 geom-vs-cube pairs)
 using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17>;
 
@@ -39,10 +43,20 @@ static cudaError_t prepare_cfg() {
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(env_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
 }
+static void read_phases(unsigned long long *out32, int reset) {
+#ifdef PBG_PHASE_CLOCKS
+    cudaMemcpyFromSymbol(out32, g_phase, 32 * sizeof(unsigned long long));
+    if (reset == 2) { cudaMemcpyFromSymbol(out32, g_warpclk, 4096 * 3 * sizeof(unsigned)); return; }
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_phase, z, sizeof z); }
+#else
+    for (int i = 0; i < 32; ++i) out32[i] = 0;
+    (void)reset;
+#endif
+}
 template <class C>
 static KernelInfo info_of() {
     return KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>};
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases};
 }
 
 

@@ -21,6 +21,20 @@
 
 namespace pbg {
 
+// Development builds (-DPBG_PHASE_CLOCKS): per-phase cycle counters summed over warps (lane 0 of each warp adds its clock64
+// deltas) and the duration of every warp of the last launch; read through pbg_debug_phases (tools/ab.py, tools/warpclk.py).
+#ifdef PBG_PHASE_CLOCKS
+__device__ unsigned long long g_phase[32];
+__device__ unsigned g_warpclk[4096 * 3];      // per warp of the last launch: cycles, smid, most rows beyond LPE
+#define PBG_PHASE(id) do { const long long _c = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase[id], (unsigned long long)(_c - _pc)); _pc = _c; } while (0)
+#define PBG_PHASE_BEGIN long long _pc = clock64()
+#define PBG_PHASE_RESET _pc = clock64()
+#else
+#define PBG_PHASE(id) do { } while (0)
+#define PBG_PHASE_BEGIN do { } while (0)
+#define PBG_PHASE_RESET do { } while (0)
+#endif
+
 // XP_ > 0: the world also holds HumanoidFlagrunHarder's cube (rs/robot_locomotors.py:236-266), a second free
 // body that is the last body / the last six dofs / the last eight ground candidates / the last XP_ pairs.
 template <int NB_, int NJ_, int FLOATING_, int NLIM_, int MAXC_, int LPE_, int NCAND_, int NPAIR_, int NFEET_,
@@ -166,6 +180,7 @@ struct Env {
     unsigned up, down;
     float tau;          // joint force of this dof for the current env step
     int nc, nl;         // active contacts / limit rows of this env (group-uniform)
+    int dbg_nov;        // development: most rows beyond LPE any sub-step of this env step had (warp-wide)
     int ovf;            // this env step had a sub-step with more than MAXC candidates in contact (the solver kept the deepest)
     float *dbg;         // optional debug dump of the constraint rows (development only)
     unsigned long long rng_seed, rng_env;   // counter-RNG key / stream of this env
@@ -583,9 +598,12 @@ struct Env {
     __device__ void substep(bool last) {
         const float h = m->h;
         float *S = st();
+        PBG_PHASE_BEGIN;
         fk(true);
+        PBG_PHASE(1);
         const V3 xref = ld3(kin(m->torso_body) + 9);
         collide(xref, last);
+        PBG_PHASE(2);
 
         // --- body wrench + composite inertia entries (lane = body)
         float *acc = sm + C::sACC;
@@ -652,6 +670,7 @@ struct Env {
         }
         __syncwarp();
 
+        PBG_PHASE(3);
         // --- motion subspace S_k, H_k = Ic S_k, f_k = tau_k - S_k . W (lane = dof)
         float *SH = sm + C::sSH;
         float *fv = sm + C::sF;
@@ -709,6 +728,7 @@ struct Env {
             if (gl == C::ND) val = fv[l];
             Mr[l] = val;
         }
+        PBG_PHASE(4);
         // --- Cholesky, rows in registers, column exchange through shared memory
         float *col = sm + C::sCOL;
         float *inv = sm + C::sINV;
@@ -731,6 +751,7 @@ struct Env {
             for (int c = 0; c < C::ND; ++c) Lm[gl * C::LST + c] = Mr[c];
         }
         __syncwarp();
+        PBG_PHASE(5);
         float *u = uvec();
         {
             // free acceleration qdd = L^-T y_f (y_f = L^-1 f is the augmented row), then
@@ -765,9 +786,13 @@ struct Env {
         }
         __syncwarp();
 
+        PBG_PHASE(6);
         // --- constraint rows (lane = row, two slots)
         const int nr = nl + 3 * nc;
         const int nrmax = wmax(nr);
+#ifdef PBG_PHASE_CLOCKS
+        dbg_nov = max(dbg_nov, nrmax - C::LPE);
+#endif
         float *Ym = sm + C::sY;
         float *Am = sm + C::sA;
         float *lam = sm + C::sLAM;
@@ -779,6 +804,7 @@ struct Env {
         else build_rows<2>(xref, h, rhs, dinv, lo, hi, lmb, mu, Yr);
         __syncwarp();
 
+        PBG_PHASE(7);
         // --- Delassus matrix A = Y Y^T and warm-started residual r = A lambda0
         float r[2] = {0.f, 0.f};
         if (nrmax > 0) {
@@ -801,6 +827,7 @@ struct Env {
         }
         __syncwarp();
 
+        PBG_PHASE(8);
         // --- projected Gauss-Seidel on lambda, Bullet's row order: limit rows (alternating
         // direction), contact normals, friction rows (btMultiBodyConstraintSolver::solveSingleIteration).
         // Every lane evaluates the update of its own row from registers each step; the row whose turn
@@ -909,6 +936,7 @@ struct Env {
         }
         __syncwarp();
 
+        PBG_PHASE(9);
         // --- du = L^-T (Y^T lambda)   (lane = dof), second clamp (btMultiBody::processDeltaVeeMultiDof2)
         float g = 0.f;
         if (gl < C::ND) {
@@ -944,6 +972,7 @@ struct Env {
         if (C::FLOATING && gl < 3) S[gl] += h * u[3 + gl];
         if (C::HASX && gl >= 3 && gl < 6) S[C::oX + gl - 3] += h * u[C::XD0 + gl];
         __syncwarp();
+        PBG_PHASE(10);
     }
 
     // ---------------------------------------------------------------- task layer
@@ -1394,6 +1423,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Env<C> e;
+    PBG_PHASE_BEGIN;
+#ifdef PBG_PHASE_CLOCKS
+    const long long _kstart = clock64();
+#endif
     e.m = model;
     e.gl = lane & (C::LPE - 1);
     e.grp = lane / C::LPE;
@@ -1419,6 +1452,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     __syncwarp();
     float *T = S + C::oT;
     const int mode = la.mode;
+    PBG_PHASE(12);
 
     if (mode == MODE_GET) {
         float *cs = B.canon + env * C::CANON;
@@ -1497,14 +1531,14 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
             if (ai >= 0) { const float av = act[ai]; tq += model->jtorque[j] * (isfinite(av) ? fminf(fmaxf(av, -1.f), 1.f) : CUDART_NAN_F); }
         }
         e.tau = tq;
-        e.ovf = 0;
+        e.ovf = 0; e.dbg_nov = -100;
         const int nsub = model->nsub;
         for (int s = 0; s < nsub; ++s) {
 #ifndef PBG_SYNC_MODE
 #define PBG_SYNC_MODE 1
 #endif
             // re-align the CTA's warps (instruction-cache locality); mode 1: every substep, 2: every other, 0: never
-            if (C::WARPS > 2 && (PBG_SYNC_MODE == 1 || (PBG_SYNC_MODE == 2 && (s & 1) == 0))) __syncthreads();
+            { PBG_PHASE_BEGIN; if (C::WARPS > 2 && (PBG_SYNC_MODE == 1 || (PBG_SYNC_MODE == 2 && (s & 1) == 0))) __syncthreads(); PBG_PHASE(0); }
             e.substep(s == nsub - 1);
         }
     }
@@ -1529,6 +1563,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     // calc_state must still see the previous step's feet flags (quirk Q2: the reference updates
     // robot.feet_contact after calc_state / alive_bonus); this step's flags were staged by the last
     // substep's collide() and replace them after pass 0.
+    PBG_PHASE_RESET;
     if (mode == MODE_OBSERVE) e.nc = 0;
     const bool reset_mode = mode == MODE_RESET;
     const bool mask_on = reset_mode && (!B.mask || B.mask[env]);
@@ -1584,6 +1619,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     }
     __syncwarp();
     (void)last_step;
+    PBG_PHASE(11);
   }
     if (threadIdx.x == 0 && B.stats && mode_eff == MODE_STEP) {
         // env steps taken, counted on the device so that CUDA-graph replays of pbg_step count too
@@ -1594,12 +1630,21 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
         if (B.reward) B.reward[env] = ret_acc;            // sum of the rewards of the nsteps steps
         if (B.done) B.done[env] = any_done ? 1 : 0;       // an episode ended (and restarted) during the rollout
     }
+    PBG_PHASE_RESET;
     if (valid) {
         if (obs) for (int i = gl; i < C::OBS; i += C::LPE) obs[i] = i < C::OBSNZ ? so_obs[i] : 0.f;
         if (store_state)
             for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
                 reinterpret_cast<float4 *>(gs)[i] = reinterpret_cast<const float4 *>(S)[i];
     }
+    PBG_PHASE(13);
+#ifdef PBG_PHASE_CLOCKS
+    {
+        const int wid = blockIdx.x * C::WARPS + warp;
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if ((threadIdx.x & 31) == 0 && wid < 4096) { g_warpclk[3 * wid] = (unsigned)(clock64() - _kstart); g_warpclk[3 * wid + 1] = smid; g_warpclk[3 * wid + 2] = (unsigned)(e.dbg_nov + 100); }
+    }
+#endif
 }
 
 }  // namespace pbg
