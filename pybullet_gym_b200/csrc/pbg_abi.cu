@@ -171,6 +171,9 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
         for (int c = 0; c < 6; ++c) d->up[XD0 + c] = d->anc[XB];
         for (int i = 0; i < 3; ++i) d->cube_pos0[i] = (float)pm->cube_pos0[i];
     }
+    // the kernel's factorisation skips structural zeros by a compile-time topology: it must be this model's
+    for (int kk = 0; kk < d->nd; ++kk)
+        if ((d->up[kk] & ((1u << kk) - 1u)) != k.low[kk]) return "the model's kinematic tree does not match the kernel's compile-time topology";
     for (int kk = 0; kk < d->nd; ++kk) {
         unsigned dn = 0;
         for (int l = 0; l < d->nd; ++l) if ((d->up[l] >> kk) & 1u) dn |= 1u << l;

@@ -12,6 +12,7 @@ struct KernelInfo {
     void (*launch)(const DevModel *, const StepBuffers &, const LaunchArgs &, cudaStream_t);
     cudaError_t (*prepare)();
     void (*phases)(unsigned long long *out32, int reset);   // development builds (-DPBG_PHASE_CLOCKS): per-phase cycle sums
+    unsigned low[32];         // the kernel's compile-time tree topology: dofs below k coupled with dof k (KCfg::low)
 };
 
 #define PBG_FOR_EACH_CFG(X) \

@@ -10,26 +10,26 @@ namespace pbg {
 using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5, 4, 4>;
 using CfgDoublePendulum = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 9, 4, 4, 0, 2>;
 using CfgDoublePendulumMJ = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 11, 4, 4, 0, 2>;
-using CfgReacher = KCfg<4, 4, 0, 3, 0, 16, 0, 0, 0, 2, 9, 4, 4, 0, 4>;
+using CfgReacher = KCfg<4, 4, 0, 3, 0, 16, 0, 0, 0, 2, 9, 4, 4, 0, 4, TopoReacher>;
 using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15, 14, 1>;
 using CfgHopperMJ = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 11, 14, 1, 0, 6>;
-using CfgWalkerMJ = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 17, 14, 1, 0, 9>;
-using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1>;
-using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1>;
+using CfgWalkerMJ = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 17, 14, 1, 0, 9, TopoBiped2D>;
+using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1, 0, 6, TopoBiped2D>;
+using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1, 0, 6, TopoBiped2D>;
 #ifndef PBG_ANT_WARPS
 #define PBG_ANT_WARPS 14
 #define PBG_ANT_BLOCKS 1
 #endif
-using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28, PBG_ANT_WARPS, PBG_ANT_BLOCKS>;
-using CfgAntMJ = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 111, PBG_ANT_WARPS, PBG_ANT_BLOCKS>;
-using CfgHumanoidMJ = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 376, 7, 1>;
+using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28, PBG_ANT_WARPS, PBG_ANT_BLOCKS, 0, 8, TopoAnt>;
+using CfgAntMJ = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 111, PBG_ANT_WARPS, PBG_ANT_BLOCKS, 0, 8, TopoAnt>;
+using CfgHumanoidMJ = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 376, 7, 1, 0, 17, TopoHumanoid>;
 #ifdef PBG_EXP_HUM14
-using CfgHumanoid = KCfg<18, 17, 1, 17, 7, 32, 30, 66, 2, 17, 44, 14, 1>;   // timing probe: 14 warps per SM, contact cap 7
+using CfgHumanoid = KCfg<18, 17, 1, 17, 7, 32, 30, 66, 2, 17, 44, 14, 1, 0, 17, TopoHumanoid>;   // timing probe: 14 warps per SM, contact cap 7
 #else
-using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1>;
+using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 0, 17, TopoHumanoid>;
 #endif
 // HumanoidFlagrunHarder: the humanoid + the cube (one more free body, 8 corner candidates, 17 geom-vs-cube pairs)
-using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17>;
+using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17, 17, TopoHumanoid>;
 
 template <class C>
 static void launch_cfg(const DevModel *m, const StepBuffers &b, const LaunchArgs &la, cudaStream_t s) {
@@ -55,8 +55,10 @@ static void read_phases(unsigned long long *out32, int reset) {
 }
 template <class C>
 static KernelInfo info_of() {
-    return KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases};
+    KernelInfo ki = KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases, {0}};
+    for (int k = 0; k < C::ND; ++k) ki.low[k] = C::low(k);
+    return ki;
 }
 
 

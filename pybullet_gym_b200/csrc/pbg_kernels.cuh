@@ -35,16 +35,51 @@ __device__ unsigned g_warpclk[4096 * 3];      // per warp of the last launch: cy
 #define PBG_PHASE_RESET do { } while (0)
 #endif
 
+// Compile-time tree topology of a robot: low(k) = bit mask of the dofs below k that dof k is coupled with in the joint-space
+// inertia matrix (its ancestors in the kinematic tree; the six dofs of a floating base count as a chain).  M = L^T L is
+// factorised leaves first (Featherstone's branch-induced sparsity), so L[k][i] is structurally zero unless i is in low(k):
+// the unrolled factorisation / substitution loops skip those entries at compile time.  pbg_create checks the masks against
+// the compiled model (DevModel.up) and refuses a model that does not match.
+struct TopoDense {      // serial chains (pendula, Hopper) and the fallback: everything below k
+    static constexpr __host__ __device__ unsigned low(int k) { return (1u << k) - 1u; }
+};
+struct TopoReacher {    // arm (joint0 -> joint1) and the target's two slides, unconnected
+    static constexpr __host__ __device__ unsigned low(int k) { return k == 1 ? 0x1u : (k == 3 ? 0x4u : 0u); }
+};
+struct TopoBiped2D {    // Walker2D / HalfCheetah: root chain 0-2, first leg 3-5, second leg 6-8 (hangs off the root chain)
+    static constexpr __host__ __device__ unsigned low(int k) {
+        return k < 6 ? (1u << k) - 1u : (k == 6 ? 0x7u : (k == 7 ? 0x47u : 0xc7u));
+    }
+};
+struct TopoAnt {        // base 0-5, four legs of (hip, ankle)
+    static constexpr __host__ __device__ unsigned low(int k) {
+        return k < 6 ? (1u << k) - 1u : (((k - 6) & 1) ? (0x3fu | (1u << (k - 1))) : 0x3fu);
+    }
+};
+struct TopoHumanoid {   // base 0-5, abdomen 6-8, right leg 9-12, left leg 13-16 (both off the abdomen), right arm 17-19, left arm 20-22
+    static constexpr __host__ __device__ unsigned low(int k) {
+        return k < 13 ? (1u << k) - 1u
+             : k < 17 ? (0x1ffu | (((1u << (k - 13)) - 1u) << 13))
+             : k < 20 ? (0x3fu | (((1u << (k - 17)) - 1u) << 17))
+                      : (0x3fu | (((1u << (k - 20)) - 1u) << 20));
+    }
+};
+
 // XP_ > 0: the world also holds HumanoidFlagrunHarder's cube (rs/robot_locomotors.py:236-266), a second free
 // body that is the last body / the last six dofs / the last eight ground candidates / the last XP_ pairs.
 template <int NB_, int NJ_, int FLOATING_, int NLIM_, int MAXC_, int LPE_, int NCAND_, int NPAIR_, int NFEET_,
-          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_>
+          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_, class TOPO_ = TopoDense>
 struct KCfg {
     static constexpr int NNOISE = NNOISE_;                     // injectable reset draws per env (pbg_reset_with)
     static constexpr int HASX = XP_ > 0 ? 1 : 0;
     static constexpr int NB = NB_ + HASX, NJ = NJ_, FLOATING = FLOATING_, NLIM = NLIM_;
     static constexpr int XD0 = NJ_ + 6 * FLOATING_;            // first cube dof
     static constexpr int ND = XD0 + 6 * HASX;
+    // structural coupling masks (see Topo* above); the cube's six dofs are a chain of their own
+    static constexpr __host__ __device__ unsigned low(int k) {
+        return (HASX && k >= XD0) ? (((1u << (k - XD0)) - 1u) << XD0) : TOPO_::low(k);
+    }
+    static constexpr __host__ __device__ bool coupled(int hi, int lo) { return ((low(hi) >> lo) & 1u) != 0u; }
     static constexpr int MAXC = MAXC_, LPE = LPE_, NCAND = NCAND_ + 8 * HASX, NPAIR = NPAIR_ + XP_, NSLOT = NCAND + NPAIR;
     static constexpr int NFEET = NFEET_, NACT = NACT_, OBS = OBS_;
     // observations wider than the 64-float staging area are MuJoCo-style layouts whose tail is zero padding
@@ -449,13 +484,14 @@ struct Env {
         __syncwarp();
     }
 
-    // x = L^-T g, lane k holds g_k / x_k (one shuffle per column)
-    __device__ __forceinline__ float backsolve(float g, const float *Lm, const float *inv) const {
+    // x = L^-1 g with M = L^T L, lane k holds g_k / x_k (one shuffle per column).  Lt[i * LST + k] = L[k][i]: lane k reads
+    // consecutive words; entries outside the tree's sparsity pattern are stored zeros.
+    __device__ __forceinline__ float fwdsolve(float g, const float *Lt, const float *inv) const {
 #pragma unroll
-        for (int k = C::ND - 1; k >= 0; --k) {
-            const float xk = shfl(g, k) * inv[k];
-            if (gl == k) g = xk;
-            else if (gl < k) g -= Lm[k * C::LST + gl] * xk;
+        for (int i = 0; i < C::ND; ++i) {
+            const float xi = shfl(g, i) * inv[i];
+            if (gl == i) g = xi;
+            else if (gl > i) g -= Lt[i * C::LST + gl] * xi;
         }
         return g;
     }
@@ -547,17 +583,20 @@ struct Env {
 #pragma unroll
             for (int sl = 0; sl < NS; ++sl) rel[sl] += J[sl][k] * uk;
         }
-        // forward substitution Y = L^-1 J^T, one L load for all slots
+        // Y = L^-T J^T by back substitution (M = L^T L), one L load for all slots; L[i][k] = Lt[k * LST + i] is structurally
+        // zero unless k is an ancestor of i: those terms are skipped at compile time
 #pragma unroll
-        for (int k = 0; k < C::ND; ++k) {
+        for (int k = C::ND - 1; k >= 0; --k) {
             float sacc[NS];
 #pragma unroll
             for (int sl = 0; sl < NS; ++sl) sacc[sl] = J[sl][k];
 #pragma unroll
-            for (int mm = 0; mm < k; ++mm) {
-                const float lkm = Lm[k * C::LST + mm];
+            for (int i = C::ND - 1; i > k; --i) {
+                if (C::coupled(i, k)) {
+                    const float lik = Lm[k * C::LST + i];
 #pragma unroll
-                for (int sl = 0; sl < NS; ++sl) sacc[sl] -= lkm * J[sl][mm];
+                    for (int sl = 0; sl < NS; ++sl) sacc[sl] -= lik * J[sl][i];
+                }
             }
             const float ik = inv[k];
 #pragma unroll
@@ -714,51 +753,56 @@ struct Env {
         }
         __syncwarp();
 
-        // --- joint-space inertia row of this dof (registers), augmented row ND = f
+        // --- joint-space inertia: lane k keeps M[l][k] for the dofs l it supports (its descendants; the part of its row /
+        // column the leaves-first factorisation reads), in registers
         float Mr[C::ND];
 #pragma unroll
         for (int l = 0; l < C::ND; ++l) {
-            const float4 s0 = *reinterpret_cast<const float4 *>(SH + l * 12);
             const float4 s1 = *reinterpret_cast<const float4 *>(SH + l * 12 + 4);
             const float4 s2 = *reinterpret_cast<const float4 *>(SH + l * 12 + 8);
-            // S_l = (s0.xyzw, s1.xy)  H_l = (s1.zw, s2.xyzw)
-            const float a_up = s0.x * Hk[0] + s0.y * Hk[1] + s0.z * Hk[2] + s0.w * Hk[3] + s1.x * Hk[4] + s1.y * Hk[5];
+            // H_l = (s1.zw, s2.xyzw)
             const float a_dn = Sk[0] * s1.z + Sk[1] * s1.w + Sk[2] * s2.x + Sk[3] * s2.y + Sk[4] * s2.z + Sk[5] * s2.w;
-            float val = ((up >> l) & 1u) ? a_up : (((down >> l) & 1u) ? a_dn : 0.f);
-            if (gl == C::ND) val = fv[l];
-            Mr[l] = val;
+            Mr[l] = ((down >> l) & 1u) ? a_dn : 0.f;
         }
         PBG_PHASE(4);
-        // --- Cholesky, rows in registers, column exchange through shared memory
+        // --- M = L^T L, leaves first (pivots from the last dof down): lane i ends up with column i of L, L[k][i] in Mr[k].
+        // At pivot k every lane scales its entry of row k and publishes it; the rank-1 update then touches only the columns
+        // that are ancestors of k (compile-time mask), so no fill-in appears outside the tree's pattern.  The right-hand side
+        // f rides along as one more column: yf = L^-T f falls out of the same sweep (lane k holds yf_k after pivot k).
         float *col = sm + C::sCOL;
         float *inv = sm + C::sINV;
+        float Mf = gl < C::ND ? fv[gl] : 0.f;
+        float yf = 0.f;
 #pragma unroll
-        for (int j = 0; j < C::ND; ++j) {
-            const float djj = shfl(Mr[j], j);
-            const float iv = rsqrtf(fmaxf(djj, 1e-20f));
-            const float lij = Mr[j] * iv;
-            Mr[j] = lij;
-            float *cb = col + (j & 1) * (C::NDP + 4);
-            cb[gl < C::NDP + 4 ? gl : 0] = lij;
-            if (gl == j) inv[j] = iv;
-            __syncwarp();
+        for (int k = C::ND - 1; k >= 0; --k) {
+            const float dkk = shfl(Mr[k], k);
+            const float iv = rsqrtf(fmaxf(dkk, 1e-20f));
+            const float lki = gl <= k ? Mr[k] * iv : 0.f; // L[k][lane]; nothing above the diagonal
+            Mr[k] = lki;
+            const float yk = shfl(Mf, k) * iv;            // yf_k
+            if (gl == k) { inv[k] = iv; yf = yk; }
+            if (C::low(k) != 0u) {
+                float *cb = col + (k & 1) * (C::NDP + 4);
+                cb[gl < C::NDP + 4 ? gl : 0] = lki;
+                __syncwarp();
+                Mf -= lki * yk;
 #pragma unroll
-            for (int c = j + 1; c < C::ND; ++c) Mr[c] -= lij * cb[c];
+                for (int c = 0; c < k; ++c)
+                    if (C::coupled(k, c)) Mr[c] -= lki * cb[c];
+            }
         }
-        float *Lm = sm + C::sL;
-        if (gl <= C::ND) {
+        float *Lm = sm + C::sL;          // Lt[i][k] = L[k][i]
+        if (gl < C::ND) {
 #pragma unroll
-            for (int c = 0; c < C::ND; ++c) Lm[gl * C::LST + c] = Mr[c];
+            for (int c = 0; c < C::ND; ++c) Lm[gl * C::LST + c] = c >= gl ? Mr[c] : 0.f;
         }
         __syncwarp();
         PBG_PHASE(5);
         float *u = uvec();
         {
-            // free acceleration qdd = L^-T y_f (y_f = L^-1 f is the augmented row), then
-            // u <- clamp(u + h qdd): btMultiBody::applyDeltaVeeMultiDof clamps every generalized
-            // velocity to +-maxCoordinateVelocity right here, before the constraint rows are built
-            float g = (gl < C::ND) ? Lm[C::ND * C::LST + gl] : 0.f;
-            g = backsolve(g, Lm, inv);
+            // free acceleration qdd = L^-1 yf, then u <- clamp(u + h qdd): btMultiBody::applyDeltaVeeMultiDof clamps every
+            // generalized velocity to +-maxCoordinateVelocity right here, before the constraint rows are built
+            const float g = fwdsolve(yf, Lm, inv);
             if (gl < C::ND) {
                 const float mv = m->maxvel;
                 { const float un = u[gl] + h * g; u[gl] = un > mv ? mv : (un < -mv ? -mv : un); }   // btClamp: a NaN stays a NaN
@@ -942,7 +986,7 @@ struct Env {
         if (gl < C::ND) {
             for (int i = 0; i < nr; ++i) g += Ym[i * C::LST + gl] * lam[i];
         }
-        if (wmax(nr) > 0) g = backsolve(g, Lm, inv);
+        if (wmax(nr) > 0) g = fwdsolve(g, Lm, inv);
         __syncwarp();
         if (gl < C::ND) {
             const float mv = m->maxvel;
