@@ -169,6 +169,7 @@ struct orc_env {
     contact ct[MAXCAND]; int nct;
     int cand_active[MAXCAND];
     double feet_touch[MAXFEET];  /* foot-vs-floor candidates under the breaking threshold in the last collide(), BEFORE the solver cap */
+    int max_rows;                /* > 0: constraint-row budget of the solver (limit rows first, contacts get the rest) */
     int cap_overflow;            /* collide() calls in which max_contacts dropped candidates */
     double done_margin;          /* distance of the last orc_observe's termination test from flipping (min over its comparisons) */
     double feet_margin[MAXFEET]; /* min over the foot's floor candidates of |distance - breaking threshold| in the last collide() */
@@ -634,6 +635,20 @@ static void collide(orc_env *e) {
     }
     /* cap: keep the max_contacts deepest, preserving candidate order */
     int cap = m->max_contacts > 0 ? m->max_contacts : MAXCAND;
+    if (e->max_rows > 0) {
+        /* row budget (the CUDA kernels of the humanoid kinds hold at most max_rows constraint rows): the violated joint limits
+         * of this sub-step come first, every contact needs three rows */
+        int nlim = 0;
+        for (int d = 0; d < e->nd; d++) {
+            int l = e->link_of_dof[d];
+            if (!(m->lower[l] <= m->upper[l])) continue;
+            if (e->q[d] - m->lower[l] <= 0) nlim++;
+            if (m->upper[l] - e->q[d] <= 0) nlim++;
+        }
+        int room = (e->max_rows - nlim) / 3;
+        if (room < 0) room = 0;
+        if (room < cap) cap = room;
+    }
     if (n > cap) e->cap_overflow++;
     while (n > cap) {
         int w = 0;
@@ -1395,5 +1410,6 @@ long orc_episodes(orc_env *e, int n, int cap, uint64_t action_seed, double *retu
 }
 
 int orc_cap_overflows(const orc_env *e) { return e->cap_overflow; }
+void orc_set_max_rows(orc_env *e, int max_rows) { e->max_rows = max_rows; }
 double orc_done_margin(const orc_env *e) { return e->done_margin; }
 void orc_feet_margin(const orc_env *e, double *out) { for (int f = 0; f < e->m.nfeet; f++) out[f] = e->feet_margin[f]; }

@@ -129,6 +129,9 @@ long orc_rollout(orc_env *e, long steps, uint64_t action_seed, double *ret_sum, 
 long orc_episodes(orc_env *e, int n, int cap, uint64_t action_seed, double *returns, int32_t *lengths);
 /* collide() passes in which max_contacts dropped candidates since creation */
 int orc_cap_overflows(const orc_env *e);
+/* constraint-row budget (0 = none): with nl violated joint limits in a sub-step, at most (max_rows - nl) / 3 contacts are kept
+ * (the deepest), on top of max_contacts; mirrors pbg_max_rows() of the CUDA library */
+void orc_set_max_rows(orc_env *e, int max_rows);
 /* per foot: how close its nearest floor candidate was to flipping the feet flag in the last collision pass
  * (min |distance - breaking threshold|); lets a test excuse exactly the flag disagreements that are round-off */
 void orc_feet_margin(const orc_env *e, double *out);

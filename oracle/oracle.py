@@ -111,6 +111,7 @@ def lib():
         L.orc_episodes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, _pd, _pi]
         L.orc_episodes.restype = C.c_long
         L.orc_cap_overflows.argtypes = [C.c_void_p]
+        L.orc_set_max_rows.argtypes = [C.c_void_p, C.c_int]
         L.orc_feet_margin.argtypes = [C.c_void_p, _pd]
         L.orc_done_margin.argtypes = [C.c_void_p]
         L.orc_done_margin.restype = C.c_double
@@ -242,11 +243,13 @@ class OracleModel:
 
 
 class OracleEnv:
-    def __init__(self, env_id_or_spec, seed: int = 0, env_index: int = 0, max_contacts: int = 0, bm=None, **overrides):
+    def __init__(self, env_id_or_spec, seed: int = 0, env_index: int = 0, max_contacts: int = 0, bm=None, max_rows: int = 0, **overrides):
         spec = SPECS[env_id_or_spec] if isinstance(env_id_or_spec, str) else env_id_or_spec
         self.model = OracleModel(spec, bm=bm, max_contacts=max_contacts, **overrides)
         self.spec = spec
         self._h = lib().orc_create(C.byref(self.model.c), seed, env_index)
+        if max_rows:
+            lib().orc_set_max_rows(self._h, int(max_rows))
         self.obs_dim, self.nact = spec.obs_dim, spec.action_dim
 
     def __del__(self):

@@ -142,6 +142,7 @@ def lib():
     vp = C.c_void_p
     L.pbg_version.restype = C.c_int
     L.pbg_max_contacts.argtypes = [C.c_int]
+    L.pbg_max_rows.argtypes = [C.c_int]
     L.pbg_create.argtypes = [C.POINTER(PbgModel), C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(vp)]
     L.pbg_destroy.argtypes = [vp]
     L.pbg_last_error.argtypes = [vp]
@@ -186,7 +187,7 @@ def lib():
 EXPORTS = ["pbg_version", "pbg_create", "pbg_destroy", "pbg_last_error", "pbg_num_envs", "pbg_obs_dim",
            "pbg_action_dim", "pbg_state_dim", "pbg_noise_dim", "pbg_reset", "pbg_reset_with", "pbg_step", "pbg_step_host",
            "pbg_set_auto_reset", "pbg_set_zero_copy", "pbg_last_host_path", "pbg_set_policy", "pbg_rollout_policy", "pbg_get_state", "pbg_set_state", "pbg_physics_step", "pbg_physics_step_counts",
-           "pbg_max_contacts", "pbg_measure_fp32_peak", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count",
+           "pbg_max_contacts", "pbg_max_rows", "pbg_measure_fp32_peak", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count",
            "pbg_snapshot_bytes", "pbg_snapshot", "pbg_restore", "pbg_set_seed", "pbg_get_task_view", "pbg_num_contact_slots",
            "pbg_enable_contact_export", "pbg_get_contact_candidates"]
 
@@ -275,6 +276,11 @@ class ModelTables:
         if spec.cube is not None:
             out += [(link[g], "cube") for g in range(len(rm.geom_body))]
         return out
+
+
+def solver_budget(kind: int) -> dict:
+    """The kernel's solver budgets for an env kind, as keyword arguments of oracle.OracleEnv (tests compare like with like)."""
+    return {"max_contacts": lib().pbg_max_contacts(kind), "max_rows": lib().pbg_max_rows(kind)}
 
 
 def check(rc: int, handle=None):

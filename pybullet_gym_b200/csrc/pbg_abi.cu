@@ -314,6 +314,12 @@ int pbg_max_contacts(int kind) {
     return k.maxc;
 }
 
+int pbg_max_rows(int kind) {
+    KernelInfo k;
+    if (!kernel_for_kind(kind, &k)) return PBG_ERR_UNSUPPORTED;
+    return k.maxr;
+}
+
 const char *pbg_last_error(const pbg_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
 int pbg_create(const pbg_model *model, int32_t num_envs, int32_t device, uint64_t seed, uint64_t env_offset, pbg_handle **out) {

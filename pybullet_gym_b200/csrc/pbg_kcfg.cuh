@@ -22,12 +22,11 @@ using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1, 0, 6, TopoBip
 #endif
 using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28, PBG_ANT_WARPS, PBG_ANT_BLOCKS, 0, 8, TopoAnt>;
 using CfgAntMJ = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 111, PBG_ANT_WARPS, PBG_ANT_BLOCKS, 0, 8, TopoAnt>;
-using CfgHumanoidMJ = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 376, 7, 1, 0, 17, TopoHumanoid>;
-#ifdef PBG_EXP_HUM14
-using CfgHumanoid = KCfg<18, 17, 1, 17, 7, 32, 30, 66, 2, 17, 44, 14, 1, 0, 17, TopoHumanoid>;   // timing probe: 14 warps per SM, contact cap 7
-#else
-using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 0, 17, TopoHumanoid>;
-#endif
+using CfgHumanoidMJ = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 376, 14, 1, 0, 17, TopoHumanoid, 40>;
+// The humanoid kinds run 14 envs (warps) per SM -- 2048 envs are one wave of 147 CTAs -- which needs <= 16.2 KB of shared memory
+// per env: a row budget of 40 (17 possible limit rows + 12 x 3 contact rows would be 53; random-policy rollouts peak at 26 rows,
+// the robot lying on the ground in FlagrunHarder reaches 42 and keeps the full 53 with 7 envs per SM).
+using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 14, 1, 0, 17, TopoHumanoid, 40>;
 // HumanoidFlagrunHarder: the humanoid + the cube (one more free body, 8 corner candidates, 17 geom-vs-cube pairs)
 using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17, 17, TopoHumanoid>;
 
@@ -56,7 +55,7 @@ static void read_phases(unsigned long long *out32, int reset) {
 template <class C>
 static KernelInfo info_of() {
     KernelInfo ki = KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases, {0}};
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::MAXR, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases, {0}};
     for (int k = 0; k < C::ND; ++k) ki.low[k] = C::low(k);
     return ki;
 }

@@ -68,7 +68,7 @@ struct TopoHumanoid {   // base 0-5, abdomen 6-8, right leg 9-12, left leg 13-16
 // XP_ > 0: the world also holds HumanoidFlagrunHarder's cube (rs/robot_locomotors.py:236-266), a second free
 // body that is the last body / the last six dofs / the last eight ground candidates / the last XP_ pairs.
 template <int NB_, int NJ_, int FLOATING_, int NLIM_, int MAXC_, int LPE_, int NCAND_, int NPAIR_, int NFEET_,
-          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_, class TOPO_ = TopoDense>
+          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_, class TOPO_ = TopoDense, int MAXROWS_ = 0>
 struct KCfg {
     static constexpr int NNOISE = NNOISE_;                     // injectable reset draws per env (pbg_reset_with)
     static constexpr int HASX = XP_ > 0 ? 1 : 0;
@@ -85,7 +85,10 @@ struct KCfg {
     // observations wider than the 64-float staging area are MuJoCo-style layouts whose tail is zero padding
     // (pybulletgym/envs/mujoco/robot_locomotors.py:222-319): only the first OBSNZ entries are staged
     static constexpr int OBSNZ = OBS_ <= 64 ? OBS_ : 11 + 2 * NJ_;
-    static constexpr int MAXR = NLIM + 3 * MAXC;
+    // constraint rows per env.  MAXROWS_ > 0 is a row budget below the worst case NLIM + 3 MAXC (it buys shared memory: the
+    // Delassus matrix is MAXR^2): the violated joint limits of a sub-step come first, contacts get (MAXR - nl) / 3 of the rest
+    static constexpr int MAXR = MAXROWS_ > 0 ? MAXROWS_ : NLIM + 3 * MAXC;
+    static_assert(MAXR <= NLIM + 3 * MAXC && MAXR >= NLIM, "row budget");
     static constexpr int MAXRP = MAXR > 0 ? MAXR : 1;
     static constexpr int NDP = (ND + 3) / 4 * 4;
     static constexpr int LST = NDP + 4;            // row stride of L / Y: float4 rows, conflict-free
@@ -436,9 +439,11 @@ struct Env {
             if (act[p] && s < C::NCAND && m->c_foot[s] >= 0) feet |= 1u << m->c_foot[s];
         }
         __syncwarp();
-        const int cap = C::MAXC;
+        // solver budget: MAXC contacts, and no more than the row budget leaves after this sub-step's limit rows (nl)
+        const int room = (C::MAXR - nl) / 3;
+        const int cap = room < C::MAXC ? room : C::MAXC;
         if (total > cap) ovf = 1;
-        if (wmax(total) > cap) {
+        if (__any_sync(FULL, total > cap)) {
             // keep the MAXC smallest by (distance, slot)
 #pragma unroll
             for (int p = 0; p < PASSES; ++p) {
@@ -638,6 +643,25 @@ struct Env {
         const float h = m->h;
         float *S = st();
         PBG_PHASE_BEGIN;
+        // --- joint limit rows (lane = joint): a side is a row only while violated (C4.4)
+        float *lim = sm + C::sLIM;
+        {
+            bool lact = false; float pen = 0.f; int side = 0;
+            if (gl < C::NJ && m->jlimited[gl]) {
+                const float q = S[C::oQ + gl];
+                const float pl = q - m->jlo[gl], pu = m->jhi[gl] - q;
+                if (pl <= 0.f) { lact = true; pen = pl; side = 0; }
+                else if (pu <= 0.f) { lact = true; pen = pu; side = 1; }
+            }
+            const unsigned bal = gballot(lact);
+            if (C::NLIM > 0 && lact) {
+                const int idx = __popc(bal & ((1u << gl) - 1u));
+                lim[2 * idx] = __int_as_float((gl + 6 * C::FLOATING) | (side << 8));
+                lim[2 * idx + 1] = pen;
+            }
+            nl = __popc(bal);
+        }
+        __syncwarp();
         fk(true);
         PBG_PHASE(1);
         const V3 xref = ld3(kin(m->torso_body) + 9);
@@ -783,7 +807,7 @@ struct Env {
             if (gl == k) { inv[k] = iv; yf = yk; }
             if (C::low(k) != 0u) {
                 float *cb = col + (k & 1) * (C::NDP + 4);
-                cb[gl < C::NDP + 4 ? gl : 0] = lki;
+                if (gl < C::ND) cb[gl] = lki;
                 __syncwarp();
                 Mf -= lki * yk;
 #pragma unroll
@@ -807,26 +831,6 @@ struct Env {
                 const float mv = m->maxvel;
                 { const float un = u[gl] + h * g; u[gl] = un > mv ? mv : (un < -mv ? -mv : un); }   // btClamp: a NaN stays a NaN
             }
-        }
-        __syncwarp();
-
-        // --- joint limit rows (lane = joint): a side is a row only while violated (C4.4)
-        float *lim = sm + C::sLIM;
-        {
-            bool lact = false; float pen = 0.f; int side = 0;
-            if (gl < C::NJ && m->jlimited[gl]) {
-                const float q = S[C::oQ + gl];
-                const float pl = q - m->jlo[gl], pu = m->jhi[gl] - q;
-                if (pl <= 0.f) { lact = true; pen = pl; side = 0; }
-                else if (pu <= 0.f) { lact = true; pen = pu; side = 1; }
-            }
-            const unsigned bal = gballot(lact);
-            if (C::NLIM > 0 && lact) {
-                const int idx = __popc(bal & ((1u << gl) - 1u));
-                lim[2 * idx] = __int_as_float((gl + 6 * C::FLOATING) | (side << 8));
-                lim[2 * idx + 1] = pen;
-            }
-            nl = __popc(bal);
         }
         __syncwarp();
 

@@ -19,8 +19,8 @@ def _pair(oracle_lib, n, seed=1):
     from pybullet_gym_b200.spec import SPECS
     from pybullet_gym_b200.vector_env import VectorEnv
     env = VectorEnv(ENV_ID, n, device="cuda:0", seed=seed, auto_reset=False)
-    mc = _lib.lib().pbg_max_contacts(SPECS[ENV_ID].kind)
-    orcs = [oracle_lib.OracleEnv(ENV_ID, seed=seed, env_index=i, max_contacts=mc) for i in range(n)]
+    budget = _lib.solver_budget(SPECS[ENV_ID].kind)
+    orcs = [oracle_lib.OracleEnv(ENV_ID, seed=seed, env_index=i, **budget) for i in range(n)]
     return env, orcs
 
 

@@ -40,9 +40,9 @@ def _mk(env_id, n=E, spec=None, auto_reset=False, seed=1):
 def _oracles(oracle_lib, env_id, n, spec=None):
     from pybullet_gym_b200 import _lib
     from pybullet_gym_b200.spec import SPECS
-    mc = _lib.lib().pbg_max_contacts(SPECS[env_id].kind)
+    budget = _lib.solver_budget(SPECS[env_id].kind)      # same contact cap / row budget as the kernel
     # same RNG key as _mk(): seed 1, stream = env index (matters for the Flagrun target draws)
-    return [oracle_lib.OracleEnv(spec if spec is not None else env_id, seed=1, env_index=i, max_contacts=mc) for i in range(n)]
+    return [oracle_lib.OracleEnv(spec if spec is not None else env_id, seed=1, env_index=i, **budget) for i in range(n)]
 
 
 def _rel(g, o):
@@ -360,8 +360,7 @@ def _t4_sample(env_id, oracle_lib, n, m, cap, gpu_seed, act_seed, orc_seed):
     g_ret, g_len = ret.cpu().numpy(), length.cpu().numpy()
     from pybullet_gym_b200 import _lib
     from pybullet_gym_b200.spec import SPECS
-    mc = _lib.lib().pbg_max_contacts(SPECS[env_id].kind)
-    o_ret, o_len = oracle_lib.random_policy_episodes(env_id, m, cap, seed=orc_seed, max_contacts=mc)
+    o_ret, o_len = oracle_lib.random_policy_episodes(env_id, m, cap, seed=orc_seed, **_lib.solver_budget(SPECS[env_id].kind))
     return g_len, o_len, g_ret, o_ret
 
 

@@ -19,8 +19,7 @@ for env_id, cap in (("HumanoidFlagrunHarderPyBulletEnv-v0", 300), ("HumanoidFlag
         ret += alive * rew; length += alive
         alive = alive * (1 - done.float())
     g_ret, g_len = ret.cpu().numpy(), length.cpu().numpy()
-    mc = _lib.lib().pbg_max_contacts(SPECS[env_id].kind)
-    o_ret, o_len = O.random_policy_episodes(env_id, m, cap, seed=77, max_contacts=mc)
+    o_ret, o_len = O.random_policy_episodes(env_id, m, cap, seed=77, **_lib.solver_budget(SPECS[env_id].kind))
     print(env_id, "len %.2f vs %.2f  ret %.2f vs %.2f (std %.1f)  p_len %.4f p_ret %.4f" % (g_len.mean(), o_len.mean(), g_ret.mean(), o_ret.mean(), o_ret.std(),
           ks_2samp(g_len, o_len).pvalue, ks_2samp(g_ret, o_ret).pvalue))
     qs = [.01, .05, .25, .5, .75, .95, .99]
