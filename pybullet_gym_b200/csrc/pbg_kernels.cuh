@@ -638,6 +638,95 @@ struct Env {
         }
     }
 
+    // ---------------------------------------------------------------- projected Gauss-Seidel
+    // Bullet's row order (btMultiBodyConstraintSolver::solveSingleIteration): joint-limit rows (direction alternating per
+    // sweep), contact normals, friction rows.  Lane = row: every lane evaluates the update of its own row from registers each
+    // step, the row whose turn it is publishes its impulse change with one shuffle, and all lanes fold it into their residual
+    // r = A lambda.  A friction row is bounded by mu times its contact's normal impulse as it stands after this sweep's normal
+    // rows (they all precede the friction rows), and skipped while that impulse is zero: the bound is fetched once per sweep.
+    // TWO: the warp holds an env with more than LPE rows; rows LPE.. live in a second register slot and are always friction
+    // rows (NLIM + MAXC <= LPE), all normals in the first.
+    template <bool TWO>
+    __device__ __forceinline__ void pgs(const int nrmax, const float (&rhs)[2], const float (&dinv)[2], const float (&lo)[2],
+                                        const float (&hi)[2], float (&lmb)[2], const float (&mu)[2], float (&r)[2]) {
+        static_assert(C::NLIM + C::MAXC <= C::LPE, "limit and normal rows must fit the first register slot");
+        const int niter = m->niter;
+        const int nr = nl + 3 * nc;
+        const float *Ag = sm + C::sA + gl;                                   // this lane's column of A
+        const bool fr0 = gl >= nl + nc && gl < nr;
+        const int myn0 = fr0 ? nl + ((gl - nl - nc) >> 1) : 0;
+        const bool fr1 = TWO && C::LPE + gl < nr;
+        const int myn1 = fr1 ? nl + ((C::LPE + gl - nl - nc) >> 1) : 0;
+        const float rhs0 = rhs[0], dinv0 = dinv[0], mu0 = mu[0], rhs1 = rhs[1], dinv1 = dinv[1], mu1 = mu[1];
+        float lam0 = lmb[0], r0 = r[0], lam1 = lmb[1], r1 = r[1];
+        float lo0 = lo[0], hi0 = hi[0];
+        const int nlmax = wmax(nl), ncmax = wmax(nc);
+        const int nf0 = (nr < C::LPE ? nr : C::LPE) - nl - nc;               // friction rows of the first slot
+        const int nf0max = wmax(nf0);
+        for (int it = 0; it < niter; ++it) {
+            for (int t = 0; t < nlmax; ++t) {
+                const bool on = t < nl;
+                const int i = on ? ((it & 1) ? t : nl - 1 - t) : 0;
+                const float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
+                float dl = shfl(cd, i);              // unconditional: both env groups of the warp take part
+                if (!on) dl = 0.f;
+                if (gl == i) lam0 += dl;
+                const float *arow = Ag + i * C::MAXRP;
+                r0 = fmaf(arow[0], dl, r0);
+                if (TWO) r1 = fmaf(arow[C::LPE], dl, r1);
+            }
+            {
+                const float *arow = Ag + nl * C::MAXRP;
+#pragma unroll 2
+                for (int j = 0; j < ncmax; ++j) {
+                    const bool on = j < nc;
+                    const float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
+                    float dl = shfl(cd, on ? nl + j : 0);
+                    if (!on) dl = 0.f;
+                    if (gl == nl + j) lam0 += dl;
+                    r0 = fmaf(on ? arow[0] : 0.f, dl, r0);                   // a row index past this env's rows may point at stale storage
+                    if (TWO) r1 = fmaf(on ? arow[C::LPE] : 0.f, dl, r1);
+                    arow += C::MAXRP;
+                }
+            }
+            const float ln0 = shfl(lam0, myn0);
+            if (fr0) { hi0 = mu0 * ln0; lo0 = -hi0; }
+            const bool skip0 = fr0 && !(ln0 > 0.f);
+            {
+                const float *arow = Ag + (nl + nc) * C::MAXRP;
+#pragma unroll 2
+                for (int j = 0; j < nf0max; ++j) {
+                    const bool on = j < nf0;
+                    float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
+                    if (skip0) cd = 0.f;
+                    float dl = shfl(cd, on ? nl + nc + j : 0);
+                    if (!on) dl = 0.f;
+                    if (gl == nl + nc + j) lam0 += dl;
+                    r0 = fmaf(on ? arow[0] : 0.f, dl, r0);
+                    if (TWO) r1 = fmaf(on ? arow[C::LPE] : 0.f, dl, r1);
+                    arow += C::MAXRP;
+                }
+            }
+            if (TWO) {
+                const float ln1 = shfl(lam0, myn1);
+                const float hi1 = fr1 ? mu1 * ln1 : 0.f, lo1 = -hi1;
+                const bool skip1 = !(ln1 > 0.f);
+                const float *arow = Ag + C::LPE * C::MAXRP;
+#pragma unroll 2
+                for (int t = C::LPE; t < nrmax; ++t) {
+                    float cd = fminf(fmaxf(lam1 + fmaf(-r1, dinv1, rhs1), lo1), hi1) - lam1;
+                    if (skip1) cd = 0.f;
+                    const float dl = shfl(cd, t - C::LPE);       // 0 from a lane without a second row
+                    if (gl == t - C::LPE) lam1 += dl;
+                    r0 = fmaf(arow[0], dl, r0);
+                    r1 = fmaf(arow[C::LPE], dl, r1);
+                    arow += C::MAXRP;
+                }
+            }
+        }
+        lmb[0] = lam0; r[0] = r0; lmb[1] = lam1; r[1] = r1;
+    }
+
     // ---------------------------------------------------------------- dynamics of one substep
     __device__ void substep(bool last) {
         const float h = m->h;
@@ -876,99 +965,9 @@ struct Env {
         __syncwarp();
 
         PBG_PHASE(8);
-        // --- projected Gauss-Seidel on lambda, Bullet's row order: limit rows (alternating
-        // direction), contact normals, friction rows (btMultiBodyConstraintSolver::solveSingleIteration).
-        // Every lane evaluates the update of its own row from registers each step; the row whose turn
-        // it is publishes its impulse change with one shuffle and all lanes fold it into their
-        // residual r = A lambda.  Friction rows track their normal row's impulse as it changes.
-        {
-            const int niter = m->niter;
-            const bool two = nrmax > C::LPE;
-            int myn[2]; float ln[2], lo_e[2], hi_e[2]; bool fr[2];
-#pragma unroll
-            for (int sl = 0; sl < 2; ++sl) {
-                const int i = sl * C::LPE + gl;
-                fr[sl] = i >= nl + nc && i < nr;
-                myn[sl] = fr[sl] ? nl + ((i - nl - nc) >> 1) : -1;
-                const int src = myn[sl] < 0 ? 0 : myn[sl];
-                const float a0 = shfl(lmb[0], src & (C::LPE - 1)), a1 = shfl(lmb[1], src & (C::LPE - 1));
-                ln[sl] = fr[sl] ? (src >= C::LPE ? a1 : a0) : 1.f;
-                lo_e[sl] = fr[sl] ? -mu[sl] * ln[sl] : lo[sl];
-                hi_e[sl] = fr[sl] ? mu[sl] * ln[sl] : hi[sl];
-            }
-            const int nlmax = wmax(nl);
-            const float *Ag = Am + gl;                       // this lane's column of A
-            const int myn0 = myn[0], myn1 = myn[1];
-            if (!two) {
-                // ---- every lane owns at most one row (slot 0)
-                float rhs0 = rhs[0], dinv0 = dinv[0], lam0 = lmb[0], r0 = r[0], mu0 = mu[0];
-                float lo0 = lo_e[0], hi0 = hi_e[0], ln0 = ln[0];
-                const int nrest = nr - nl;                   // contact rows of this env (normals + friction)
-                const int nrestmax = wmax(nrest);
-                for (int it = 0; it < niter; ++it) {
-                    // joint-limit rows, direction alternates per iteration
-                    for (int t = 0; t < nlmax; ++t) {
-                        const bool on = t < nl;
-                        const int i = on ? ((it & 1) ? t : nl - 1 - t) : 0;
-                        const float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
-                        float dl = shfl(cd, i);              // unconditional: both env groups of the warp take part
-                        if (!on) dl = 0.f;
-                        if (gl == i) lam0 += dl;
-                        r0 = fmaf(Ag[i * C::MAXRP], dl, r0);
-                    }
-                    // contact normals, then friction rows: row index = nl + j
-                    const float *ap = Ag + nl * C::MAXRP;
-#pragma unroll 2
-                    for (int j = 0; j < nrestmax; ++j) {
-                        const bool on = j < nrest;
-                        const int i = on ? nl + j : 0;
-                        float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
-                        if (!(ln0 > 0.f)) cd = 0.f;          // a friction row is skipped while its normal impulse is 0
-                        float dl = shfl(cd, i);
-                        if (!on) dl = 0.f;
-                        if (gl == i) lam0 += dl;
-                        r0 = fmaf(on ? ap[0] : 0.f, dl, r0);
-                        ap += C::MAXRP;
-                        if (i == myn0) { ln0 += dl; hi0 = mu0 * ln0; lo0 = -hi0; }
-                    }
-                }
-                lmb[0] = lam0; r[0] = r0;
-            } else {
-                const int t0end = C::LPE;
-                for (int it = 0; it < niter; ++it) {
-                    // rows 0 .. LPE-1 live in register slot 0
-#pragma unroll 2
-                    for (int t = 0; t < t0end; ++t) {
-                        int i = t;
-                        if (t < nl) i = (it & 1) ? t : nl - 1 - t;
-                        const float d = fmaf(-r[0], dinv[0], rhs[0]);
-                        float cd = fminf(fmaxf(lmb[0] + d, lo_e[0]), hi_e[0]) - lmb[0];
-                        if (!(ln[0] > 0.f)) cd = 0.f;
-                        const float dl = shfl(cd, i);
-                        if (gl == i) lmb[0] += dl;
-                        const float *arow = Ag + i * C::MAXRP;
-                        r[0] = fmaf(arow[0], dl, r[0]);
-                        if (i == myn0) { ln[0] += dl; hi_e[0] = mu[0] * ln[0]; lo_e[0] = -hi_e[0]; }
-                        r[1] = fmaf(arow[C::LPE], dl, r[1]);
-                        if (i == myn1) { ln[1] += dl; hi_e[1] = mu[1] * ln[1]; lo_e[1] = -hi_e[1]; }
-                    }
-                    // rows LPE .. 2 LPE-1 live in register slot 1 (never limit rows: nl <= NLIM <= LPE)
-#pragma unroll 2
-                    for (int t = C::LPE; t < nrmax; ++t) {
-                        const float d = fmaf(-r[1], dinv[1], rhs[1]);
-                        float cd = fminf(fmaxf(lmb[1] + d, lo_e[1]), hi_e[1]) - lmb[1];
-                        if (!(ln[1] > 0.f)) cd = 0.f;
-                        const float dl = shfl(cd, t - C::LPE);
-                        if (gl == t - C::LPE) lmb[1] += dl;
-                        const float *arow = Ag + t * C::MAXRP;
-                        r[0] = fmaf(arow[0], dl, r[0]);
-                        r[1] = fmaf(arow[C::LPE], dl, r[1]);
-                        if (t == myn0) { ln[0] += dl; hi_e[0] = mu[0] * ln[0]; lo_e[0] = -hi_e[0]; }
-                        if (t == myn1) { ln[1] += dl; hi_e[1] = mu[1] * ln[1]; lo_e[1] = -hi_e[1]; }
-                    }
-                }
-            }
-        }
+        // --- projected Gauss-Seidel on lambda (see pgs() below)
+        if (nrmax > C::LPE) pgs<true>(nrmax, rhs, dinv, lo, hi, lmb, mu, r);
+        else pgs<false>(nrmax, rhs, dinv, lo, hi, lmb, mu, r);
         // --- publish lambda, store warm-start impulses
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
