@@ -93,9 +93,9 @@ def _settled_oracles(env_id, threads):
 def real_reference_available():
     """Pin day: the moment the reference's own stack (pybullet + gym + pybulletgym) imports, the CPU arm is the real thing."""
     try:
-        import pybullet  # noqa: F401
+        import pybullet
         import gym  # noqa: F401
-        return True
+        return hasattr(pybullet, "connect") and not getattr(pybullet, "IS_PBG_STUB", False)
     except Exception:
         return False
 

@@ -136,6 +136,9 @@ class WalkerBaseBulletEnv(BaseBulletEnv):
             # quirk Q1: the floor joins robot.parts after the first reset (gym_locomotion_envs.py:30-31)
             r.parts["floor"] = R.BodyPart(r, "floor", None)
             self.parts, self.jdict, self.ordered_joints, self.robot_body = r.parts, r.jdict, r.ordered_joints, r.robot_body
+        # (body id, link index) of the ground objects, as the reference collects them for the feet test
+        # (gym_locomotion_envs.py:33-36): the stadium floor is body 0, base link
+        self.ground_ids = set([(R.XmlBasedRobot.FLOOR_BODY, -1)])
         self.stateId = 0
         return obs
 

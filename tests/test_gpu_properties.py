@@ -126,6 +126,62 @@ def test_gym_shell_attribute_surface():
     assert np.array_equal(env2.reset(), obs0)
 
 
+def test_flagrun_shell_mirrors_the_device_flag():
+    """HumanoidFlagrun's flag lives on the device (flag_reposition, rs/robot_locomotors.py:204-218): after every reset / step the
+    shell's walk_target_x/y, flag_timeout and env.potential are the kernel's own values, so env.potential equals
+    -walk_target_dist / dt also right after the flag has moved; env.seed(s) keys the flag draws."""
+    from pybullet_gym_b200.envs import make
+    env = make("HumanoidFlagrunPyBulletEnv-v0"); env.seed(11)
+    env.reset()
+    u = env.unwrapped
+    r = u.robot
+    t0 = (r.walk_target_x, r.walk_target_y)
+    assert t0 != (1e3, 0.0) and abs(t0[0]) <= 25.0 and abs(t0[1]) <= 25.0          # the first calc_state repositions the flag
+    assert u.potential == pytest.approx(-r.walk_target_dist / u.scene.dt, rel=1e-6)
+    timeouts, moved = [r.flag_timeout], False
+    for t in range(160):                                                              # flag_timeout = 600 / frame_skip = 150 steps
+        obs, rew, done, info = env.step(np.zeros(17, dtype=np.float32))
+        timeouts.append(r.flag_timeout)
+        assert (u.walk_target_x, u.walk_target_y) == (r.walk_target_x, r.walk_target_y)
+        assert u.potential == pytest.approx(-r.walk_target_dist / u.scene.dt, rel=1e-5, abs=1e-3)
+        if (r.walk_target_x, r.walk_target_y) != t0:
+            moved = True
+            break
+    assert moved and timeouts[1] == timeouts[0] - 1                                   # counts down, then the flag moves
+    # same seed -> same flags; another seed -> other flags
+    again = make("HumanoidFlagrunPyBulletEnv-v0"); again.seed(11); again.reset()
+    other = make("HumanoidFlagrunPyBulletEnv-v0"); other.seed(12); other.reset()
+    assert (again.unwrapped.robot.walk_target_x, again.unwrapped.robot.walk_target_y) == t0
+    assert (other.unwrapped.robot.walk_target_x, other.unwrapped.robot.walk_target_y) != t0
+    harder = make("HumanoidFlagrunHarderPyBulletEnv-v0"); harder.seed(1); harder.reset()
+    for t in range(5):
+        harder.step(np.zeros(17, dtype=np.float32))
+    assert harder.unwrapped.robot.frame == 5 and harder.unwrapped.robot.on_ground_frame_counter == 0
+
+
+def test_body_part_speed_and_contact_list():
+    """BodyPart.speed() (rs/robot_bases.py:243-248) and contact_list() (:280-281) on the shell: the Ant dropped on the floor
+    reports floor contacts for its feet in the shape rs/gym_locomotion_envs.py:73 reads (fields [2] = bodyB, [4] = linkB), and
+    feet_contact is exactly "the foot has a floor contact"."""
+    from pybullet_gym_b200.envs import make
+    env = make("AntPyBulletEnv-v0"); env.seed(0); env.reset()
+    u = env.unwrapped
+    r = u.robot
+    prev_z = r.parts["torso"].pose().xyz()[2]
+    for t in range(40):
+        env.step(np.zeros(8, dtype=np.float32))
+        z = r.parts["torso"].pose().xyz()[2]
+        vz = r.parts["torso"].speed()[2]
+        if 1 < t < 8 and r.feet_contact.sum() == 0:
+            assert vz < -0.1 and abs(vz - (z - prev_z) / u.scene.dt) < 0.25     # free fall: end-of-step velocity ~ finite difference of the pose
+        prev_z = z
+    for i, f in enumerate(r.feet):
+        contact_ids = set((x[2], x[4]) for x in f.contact_list())         # the reference's own expression
+        assert bool(u.ground_ids & contact_ids) == bool(r.feet_contact[i]), (f.name, contact_ids, r.feet_contact)
+    assert r.feet_contact.sum() >= 3                                  # settled on its feet
+    assert np.allclose(r.parts["floor"].speed(), 0.0)
+
+
 def test_step_host_round_trip():
     env = _mk("AntPyBulletEnv-v0", 256, seed=4)
     ref = _mk("AntPyBulletEnv-v0", 256, seed=4)

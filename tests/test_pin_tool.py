@@ -48,3 +48,31 @@ def test_dump_on_the_stub_client_compares_clean(tmp_path, oracle_lib):
     # contact-free: the one-step replay is exact; with contacts only the warm-start impulses (not part of the state) differ
     assert report["InvertedPendulumPyBulletEnv-v0"]["one_step_max"] < 1e-12
     assert report["AntPyBulletEnv-v0"]["one_step_median"] < 1e-2 and report["HopperPyBulletEnv-v0"]["one_step_median"] < 1e-2
+
+
+def _real_pybullet():
+    """True only for a real pybullet wheel (the stub of tools/fake_pybullet.py marks itself)."""
+    try:
+        import pybullet
+        import gym  # noqa: F401
+    except Exception:
+        return False
+    return not getattr(pybullet, "IS_PBG_STUB", False) and hasattr(pybullet, "connect")
+
+
+@pytest.mark.skipif(not _real_pybullet(), reason="pin day: needs a real pybullet wheel + gym (not installable in the build image)")
+def test_pin_day_compare_against_real_pybullet(tmp_path, oracle_lib):
+    """The day `import pybullet` works this test IS the physics pin: dump the reference's own envs (link / joint / dynamics
+    tables, engine parameters, a state-by-state rollout tape) and require (a) the MJCF compiler's tables to match what
+    loadMJCF built, (b) the oracle's one-step replay from every dumped state to stay within the single-step tier."""
+    sys.path.insert(0, TOOLS)
+    for ref in (os.path.join(os.path.dirname(TOOLS), "baseline", "_ref"), REF):
+        if os.path.isdir(ref) and ref not in sys.path:
+            sys.path.insert(0, ref)
+    import pin_pybullet as pin
+    path = str(tmp_path / "pins.json")
+    pin.dump(path)
+    report, bad = pin.compare(path, verbose=True)
+    assert bad == 0, {k: v["table_rows"] for k, v in report.items()}
+    for env_id, rep in report.items():
+        assert rep["one_step_median"] < 1e-3, (env_id, rep["one_step_median"], rep["one_step_max"])

@@ -278,6 +278,7 @@ def _euler_from_quaternion(q):
 def install():
     """Register the stub modules.  Call before importing pybulletgym."""
     pb = types.ModuleType("pybullet")
+    pb.IS_PBG_STUB = True          # so that nothing mistakes this for a real wheel (tests/test_pin_tool.py, bench.py)
     pb.POSITION_CONTROL, pb.VELOCITY_CONTROL, pb.TORQUE_CONTROL = POSITION_CONTROL, VELOCITY_CONTROL, TORQUE_CONTROL
     pb.GUI, pb.DIRECT = 1, 2
     pb.URDF_USE_SELF_COLLISION, pb.URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS = 8, 32

@@ -28,11 +28,15 @@ configs={
  "warm0.85": (None,dict(warmstarting_factor=0.85)),
  "erp_contact0.2": (None,dict(contact_erp=0.2)),
  "split": (None,dict(limit_split_impulse=True)),
+ # fillMultiBodyConstraint may read m_erp2 (= setDefaultContactERP 0.9) instead of m_erp (0.2) for the joint-limit rows
+ "erp_limit0.9": (None,dict(erp=0.9)),
+ "erp_limit0.9_nosplit": (None,dict(erp=0.9, limit_split_impulse=False)),
 }
+names_all=["Hopper","Walker2D","HalfCheetah","Ant","Humanoid","HumanoidFlagrun"]
 sel=[c for c in (sys.argv[1:] or list(configs)) if c in configs]
 for c in sel:
     r,s=configs[c]
-    print(c, {n: run(n,r,s) for n in names}, flush=True)
+    print(c, {n: run(n,r,s) for n in (names_all if c.startswith("erp_limit") or c == "base" else names)}, flush=True)
 
 # torque-scale probe
 import sys
