@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PBG_VERSION 101
+#define PBG_VERSION 102
 
 typedef enum {
     PBG_OK = 0,
@@ -51,7 +51,8 @@ enum {
     PBG_KIND_FLAGRUN_HARDER = 8, PBG_KIND_DOUBLE_PENDULUM = 9, PBG_KIND_REACHER = 10,
     PBG_KIND_DOUBLE_PENDULUM_MJ = 11,  /* pybulletgym/envs/mujoco/gym_pendulum_envs.py:40-75 */
     PBG_KIND_HOPPER_MJ = 12, PBG_KIND_WALKER2D_MJ = 13,  /* pybulletgym/envs/mujoco/gym_locomotion_envs.py:121-206 */
-    PBG_KIND_ANT_MJ = 14, PBG_KIND_HUMANOID_MJ = 15      /* pybulletgym/envs/mujoco/gym_locomotion_envs.py:246-260 */
+    PBG_KIND_ANT_MJ = 14, PBG_KIND_HUMANOID_MJ = 15,     /* pybulletgym/envs/mujoco/gym_locomotion_envs.py:246-260 */
+    PBG_KIND_HALFCHEETAH_MJ = 16                         /* pybulletgym/envs/mujoco/gym_locomotion_envs.py:211-244 */
 };
 
 enum { PBG_JT_FIXED = 0, PBG_JT_REVOLUTE = 1, PBG_JT_PRISMATIC = 2, PBG_JT_FREE = 3 };
@@ -117,6 +118,13 @@ typedef struct pbg_model {
     /* links (indices into sub_*) whose COM the task layer reads besides torso_sub: Reacher's fingertip and
      * target (rs/robot_manipulators.py:17-18,33); -1: unused */
     int32_t aux_sub[2];
+    /* Torsional friction (changeDynamics(spinningFriction=, rollingFriction=), mujoco/robot_locomotors.py:207-210): when
+     * torsional_friction != 0 every ground contact gets, between its normal row and its two lateral friction rows, one row
+     * about the contact normal bounded by spin * lambda_n and two rows about the tangents bounded by roll * lambda_n, with
+     * Bullet's combination rule spin = geom_spin * ground_friction + ground_spinning_friction * geom_friction (same for roll). */
+    int32_t torsional_friction;
+    const double *geom_spin, *geom_roll;      /* [ng] */
+    double ground_spinning_friction, ground_rolling_friction;
 } pbg_model;
 
 typedef struct pbg_handle pbg_handle;

@@ -568,7 +568,8 @@ static void collide(orc_env *e) {
                 v3set(ct->pb, c[0], c[1], 0.0);
                 ct->dist = dist; ct->mu = m->g_friction[g] * m->ground_friction;
                 /* btManifoldResult::calculateCombinedRolling/SpinningFriction: rollA*fricB + rollB*fricA, floor has 0 */
-                ct->mu_spin = m->torsional ? m->g_spin[g] * m->ground_friction : 0; ct->mu_roll = m->torsional ? m->g_roll[g] * m->ground_friction : 0;
+                ct->mu_spin = m->torsional ? m->g_spin[g] * m->ground_friction + m->ground_spin * m->g_friction[g] : 0;
+                ct->mu_roll = m->torsional ? m->g_roll[g] * m->ground_friction + m->ground_roll * m->g_friction[g] : 0;
             }
         }
     }
@@ -1106,11 +1107,13 @@ static double reacher_potential(const orc_env *e) { return -100.0 * v3norm(e->bo
 
 /* MuJoCo-style Hopper / Walker2D (pybulletgym/envs/mujoco/robot_locomotors.py:86-165): qpos[1:] ++ clip(qvel, +-10) over
  * all dofs (root joints included), float32 storage */
-static int is_mjwalker(int kind) { return kind == ORC_KIND_HOPPER_MJ || kind == ORC_KIND_WALKER2D_MJ; }
+static int is_mjwalker(int kind) { return kind == ORC_KIND_HOPPER_MJ || kind == ORC_KIND_WALKER2D_MJ || kind == ORC_KIND_HALFCHEETAH_MJ; }
 static void mjwalker_calc_state(orc_env *e, double *obs) {
     int nd = e->nd, o = 0;
     for (int k = 1; k < nd; k++) obs[o++] = (double)(float)e->q[k];
-    for (int k = 0; k < nd; k++) { float v = (float)e->qd[k]; v = v < -10.f ? -10.f : (v > 10.f ? 10.f : v); obs[o++] = v; }
+    /* mujoco/robot_locomotors.py:183-190: the HalfCheetah concatenates qvel unclipped */
+    int clipv = e->m.kind != ORC_KIND_HALFCHEETAH_MJ;
+    for (int k = 0; k < nd; k++) { float v = (float)e->qd[k]; if (clipv) v = v < -10.f ? -10.f : (v > 10.f ? 10.f : v); obs[o++] = v; }
 }
 static double mjwalker_body_x(orc_env *e) { fk(e); return e->c[e->m.torso_link][0]; }   /* robot_body.get_pose()[0] */
 
@@ -1178,6 +1181,13 @@ int orc_observe(orc_env *e, const double *a, double *obs, double *reward, double
         double ss = 0; for (int n = 0; n < m->nact; n++) ss += a[n] * a[n];
         t5[2] = -1e-3 * ss;
         mjwalker_calc_state(e, obs);
+        if (m->kind == ORC_KIND_HALFCHEETAH_MJ) {
+            /* HalfCheetahMuJoCoEnv._step (mujoco/gym_locomotion_envs.py:216-244): rewards = [potential, power_cost], done = False */
+            t5[1] = -0.1 * ss; t5[2] = 0.0;
+            *reward = t5[0] + t5[1];
+            if (terms) memcpy(terms, t5, sizeof(t5));
+            return 0;
+        }
         double height = obs[0], ang = obs[1];
         int ok = 1;
         for (int k = 0; k < m->obs_dim; k++) if (!isfinite(obs[k])) ok = 0;

@@ -31,7 +31,8 @@ enum { ORC_G_SPHERE = 0, ORC_G_CAPSULE = 1, ORC_G_BOX = 2 };
 enum { ORC_KIND_PENDULUM = 0, ORC_KIND_PENDULUM_SWINGUP = 1, ORC_KIND_HOPPER = 2, ORC_KIND_WALKER2D = 3,
        ORC_KIND_HALFCHEETAH = 4, ORC_KIND_ANT = 5, ORC_KIND_HUMANOID = 6, ORC_KIND_FLAGRUN = 7,
        ORC_KIND_FLAGRUN_HARDER = 8, ORC_KIND_DOUBLE_PENDULUM = 9, ORC_KIND_REACHER = 10, ORC_KIND_DOUBLE_PENDULUM_MJ = 11,
-       ORC_KIND_HOPPER_MJ = 12, ORC_KIND_WALKER2D_MJ = 13, ORC_KIND_ANT_MJ = 14, ORC_KIND_HUMANOID_MJ = 15 };
+       ORC_KIND_HOPPER_MJ = 12, ORC_KIND_WALKER2D_MJ = 13, ORC_KIND_ANT_MJ = 14, ORC_KIND_HUMANOID_MJ = 15,
+       ORC_KIND_HALFCHEETAH_MJ = 16 };
 
 /* Bullet-shaped model + scene + task constants.  All arrays are owned by the caller. */
 typedef struct {
@@ -67,6 +68,7 @@ typedef struct {
     /* torsional friction rows (spinning about the normal, rolling about the two tangents), SURVEY C1.11 / C6-9 */
     int32_t torsional;
     const double *g_spin, *g_roll;            /* [ng] 2nd / 3rd MJCF friction numbers */
+    double ground_spin, ground_roll;          /* the floor's spinning / rolling friction (changeDynamics on the floor body) */
     /* HumanoidFlagrunHarder's aggressive cube: a second free body (rs/robot_locomotors.py:236-266,
      * gym_utils.py:9-16, assets/things/cube_small.urdf).  cube = 0: absent */
     int32_t cube;

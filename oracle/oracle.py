@@ -50,7 +50,7 @@ class OrcModel(C.Structure):
         ("walk_target_x", C.c_double), ("walk_target_y", C.c_double),
         ("max_episode_steps", C.c_int32),
         ("stadium_halflen", C.c_double), ("stadium_halfwidth", C.c_double),
-        ("torsional", C.c_int32), ("g_spin", _pd), ("g_roll", _pd),
+        ("torsional", C.c_int32), ("g_spin", _pd), ("g_roll", _pd), ("ground_spin", C.c_double), ("ground_roll", C.c_double),
         ("cube", C.c_int32),
         ("cube_half", C.c_double), ("cube_mass", C.c_double), ("cube_inertia", C.c_double),
         ("cube_friction", C.c_double), ("cube_threshold", C.c_double), ("cube_pos0", C.c_double * 3),
@@ -224,6 +224,7 @@ class OracleModel:
         m.max_episode_steps = spec.max_episode_steps
         m.stadium_halflen, m.stadium_halfwidth = sc.stadium_halflen, sc.stadium_halfwidth
         m.torsional = int(getattr(sc, 'torsional_friction', False))
+        m.ground_spin, m.ground_roll = sc.ground_spinning_friction, sc.ground_rolling_friction
         for i in range(2):
             m.aux_link[i] = bm.link_index(spec.aux_links[i]) if i < len(spec.aux_links) else -1
         cube = spec.cube

@@ -67,6 +67,8 @@ class PbgModel(C.Structure):
         ("cube_half", C.c_double), ("cube_mass", C.c_double), ("cube_inertia", C.c_double),
         ("cube_friction", C.c_double), ("cube_threshold", C.c_double), ("cube_pos0", C.c_double * 3),
         ("aux_sub", C.c_int32 * 2),
+        ("torsional_friction", C.c_int32), ("geom_spin", _pd), ("geom_roll", _pd),
+        ("ground_spinning_friction", C.c_double), ("ground_rolling_friction", C.c_double),
     ]
 
 
@@ -75,7 +77,7 @@ class PbgEpisodeStats(C.Structure):
                 ("truncated", C.c_int64), ("nonfinite", C.c_int64), ("steps", C.c_int64), ("contact_overflow", C.c_int64)]
 
 
-PBG_VERSION = 101          # include/pbg.h
+PBG_VERSION = 102          # include/pbg.h
 TASK_VIEW_DIM = 12         # PBG_TASK_VIEW_DIM
 TASK_VIEW_FIELDS = ("potential", "walk_target_x", "walk_target_y", "flag_timeout", "frame", "on_ground_frame_counter",
                     "episode_steps", "episode_return", "initial_z", "episode", "attacks", "flag_moves")
@@ -225,6 +227,7 @@ class ModelTables:
         k["geom_body"], k["geom_type"], k["geom_ground"] = _i(rm.geom_body), _i(rm.geom_type), _i(rm.geom_ground)
         k["geom_radius"], k["geom_p0"], k["geom_p1"] = _d(rm.geom_radius), _d(rm.geom_p0), _d(rm.geom_p1)
         k["geom_friction"], k["geom_threshold"] = _d(rm.geom_friction), _d(rm.geom_threshold)
+        k["geom_spin"], k["geom_roll"] = _d(rm.geom_spin), _d(rm.geom_roll)
         k["pair_a"], k["pair_b"] = _i(rm.pair_a), _i(rm.pair_b)
         m = PbgModel()
         m.nb, m.nj, m.floating = rm.nb, rm.nj, int(rm.floating)
@@ -233,10 +236,9 @@ class ModelTables:
         for name, arr in k.items():
             setattr(m, name, arr.ctypes.data_as(_pd if arr.dtype == np.float64 else _pi))
         sc = spec.scene
-        if sc.torsional_friction:
-            # spinning / rolling friction rows exist in the CPU oracle only (a probe for pin C6-9); refusing is better than
-            # silently stepping a different contact model on the GPU
-            raise NotImplementedError("SceneSpec.torsional_friction is an oracle-only probe; the CUDA path has no torsional rows")
+        # torsional friction rows: only the kernel configurations built with them accept the switch (pbg_create checks)
+        m.torsional_friction = int(sc.torsional_friction)
+        m.ground_spinning_friction, m.ground_rolling_friction = sc.ground_spinning_friction, sc.ground_rolling_friction
         m.gravity, m.timestep, m.frame_skip, m.num_solver_iterations = sc.gravity, sc.timestep, sc.frame_skip, sc.num_solver_iterations
         m.contact_erp, m.erp, m.linear_slop, m.warmstarting_factor = sc.contact_erp, sc.erp, sc.linear_slop, sc.warmstarting_factor
         m.link_damping, m.max_coordinate_velocity = rm.link_damping, sc.max_coordinate_velocity

@@ -22,6 +22,7 @@ static bool kernel_for_kind(int kind, KernelInfo *out) {
     case PBG_KIND_HOPPER_MJ: *out = info_HopperMJ(); return true;
     case PBG_KIND_WALKER2D_MJ: *out = info_WalkerMJ(); return true;
     case PBG_KIND_HALFCHEETAH: *out = info_Cheetah(); return true;
+    case PBG_KIND_HALFCHEETAH_MJ: *out = info_CheetahMJ(); return true;
     case PBG_KIND_ANT: *out = info_Ant(); return true;
     case PBG_KIND_ANT_MJ: *out = info_AntMJ(); return true;
     case PBG_KIND_HUMANOID_MJ: *out = info_HumanoidMJ(); return true;
@@ -92,6 +93,8 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
                  pm->floating, pm->kind, k.nb - k.hasx, k.nj, k.floating);
         return buf;
     }
+    if ((pm->torsional_friction != 0) != (k.tors != 0)) return "the kernel of this env kind and the model disagree about torsional friction rows";
+    if (k.tors && (!pm->geom_spin || !pm->geom_roll)) return "torsional friction needs geom_spin / geom_roll";
     if ((pm->cube != 0) != (k.hasx != 0)) return "the kernel of this env kind and the model disagree about the cube";
     if (pm->action_dim != k.nact || pm->obs_dim != k.obs || pm->nfeet != k.nfeet) return "action/obs/feet dims do not match the kernel";
     if (pm->ns > MSUB) return "too many Bullet links";
@@ -241,6 +244,12 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
             d->c_rad[nc] = (float)pm->geom_radius[g];
             d->c_thr[nc] = (float)pm->geom_threshold[g];
             d->c_mu[nc] = (float)(pm->geom_friction[g] * pm->ground_friction);
+            if (k.tors) {
+                // btManifoldResult::calculateCombinedSpinning/RollingFriction: spinA * fricB + spinB * fricA
+                d->c_spin[nc] = (float)(pm->geom_spin[g] * pm->ground_friction + pm->ground_spinning_friction * pm->geom_friction[g]);
+                d->c_roll[nc] = (float)(pm->geom_roll[g] * pm->ground_friction + pm->ground_rolling_friction * pm->geom_friction[g]);
+                if (!(d->c_spin[nc] > 0.f) || !(d->c_roll[nc] > 0.f)) return "torsional friction rows need positive spinning and rolling coefficients on every ground contact";
+            }
             ++nc;
         }
     }

@@ -7,7 +7,7 @@
 namespace pbg {
 
 struct KernelInfo {
-    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet, nnoise, ysz, off_task, nslot, maxr;
+    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet, nnoise, ysz, off_task, nslot, maxr, tors;
     size_t smem;
     void (*launch)(const DevModel *, const StepBuffers &, const LaunchArgs &, cudaStream_t);
     cudaError_t (*prepare)();
@@ -17,7 +17,7 @@ struct KernelInfo {
 
 #define PBG_FOR_EACH_CFG(X) \
     X(Pendulum) X(DoublePendulum) X(DoublePendulumMJ) X(Reacher) X(Hopper) X(HopperMJ) X(WalkerMJ) X(Walker) X(Cheetah) \
-    X(Ant) X(AntMJ) X(HumanoidMJ) X(Humanoid) X(Harder)
+    X(Ant) X(AntMJ) X(HumanoidMJ) X(Humanoid) X(Harder) X(CheetahMJ)
 #define PBG_DECL_INFO(name) KernelInfo info_##name();
 PBG_FOR_EACH_CFG(PBG_DECL_INFO)
 #undef PBG_DECL_INFO

@@ -16,6 +16,8 @@ using CfgHopperMJ = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 11, 14, 1, 0, 6>;
 using CfgWalkerMJ = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 17, 14, 1, 0, 9, TopoBiped2D>;
 using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1, 0, 6, TopoBiped2D>;
 using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1, 0, 6, TopoBiped2D>;
+// HalfCheetahMuJoCoEnv: the cheetah with torsional friction rows (6 rows per contact: up to 42 rows -> one env per warp)
+using CfgCheetahMJ = KCfg<9, 9, 0, 6, 6, 32, 16, 0, 6, 6, 17, 14, 1, 0, 9, TopoBiped2D, 0, 1>;
 #ifndef PBG_ANT_WARPS
 #define PBG_ANT_WARPS 14
 #define PBG_ANT_BLOCKS 1
@@ -55,7 +57,7 @@ static void read_phases(unsigned long long *out32, int reset) {
 template <class C>
 static KernelInfo info_of() {
     KernelInfo ki = KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::MAXR, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases, {0}};
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::MAXR, C::TORS, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases, {0}};
     for (int k = 0; k < C::ND; ++k) ki.low[k] = C::low(k);
     return ki;
 }

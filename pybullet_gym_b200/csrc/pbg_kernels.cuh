@@ -68,7 +68,7 @@ struct TopoHumanoid {   // base 0-5, abdomen 6-8, right leg 9-12, left leg 13-16
 // XP_ > 0: the world also holds HumanoidFlagrunHarder's cube (rs/robot_locomotors.py:236-266), a second free
 // body that is the last body / the last six dofs / the last eight ground candidates / the last XP_ pairs.
 template <int NB_, int NJ_, int FLOATING_, int NLIM_, int MAXC_, int LPE_, int NCAND_, int NPAIR_, int NFEET_,
-          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_, class TOPO_ = TopoDense, int MAXROWS_ = 0>
+          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_, class TOPO_ = TopoDense, int MAXROWS_ = 0, int TORS_ = 0>
 struct KCfg {
     static constexpr int NNOISE = NNOISE_;                     // injectable reset draws per env (pbg_reset_with)
     static constexpr int HASX = XP_ > 0 ? 1 : 0;
@@ -86,9 +86,14 @@ struct KCfg {
     // (pybulletgym/envs/mujoco/robot_locomotors.py:222-319): only the first OBSNZ entries are staged
     static constexpr int OBSNZ = OBS_ <= 64 ? OBS_ : 11 + 2 * NJ_;
     // constraint rows per env.  MAXROWS_ > 0 is a row budget below the worst case NLIM + 3 MAXC (it buys shared memory: the
-    // Delassus matrix is MAXR^2): the violated joint limits of a sub-step come first, contacts get (MAXR - nl) / 3 of the rest
-    static constexpr int MAXR = MAXROWS_ > 0 ? MAXROWS_ : NLIM + 3 * MAXC;
-    static_assert(MAXR <= NLIM + 3 * MAXC && MAXR >= NLIM, "row budget");
+    // Delassus matrix is MAXR^2): the violated joint limits of a sub-step come first, contacts get (MAXR - nl) / RPC of the rest
+    // TORS_: every contact also gets Bullet's torsional friction rows (one spinning about the normal, two rolling about the
+    // tangents), placed between the normal rows and the lateral friction rows: RPC rows per contact
+    static constexpr int TORS = TORS_ ? 1 : 0;
+    static constexpr int RPC = 3 + 3 * TORS;
+    static constexpr int MAXR = MAXROWS_ > 0 ? MAXROWS_ : NLIM + RPC * MAXC;
+    static_assert(MAXR <= NLIM + RPC * MAXC && MAXR >= NLIM, "row budget");
+    static_assert(!TORS || NPAIR_ + XP_ == 0, "torsional rows are implemented for ground contacts only");
     static constexpr int MAXRP = MAXR > 0 ? MAXR : 1;
     static constexpr int NDP = (ND + 3) / 4 * 4;
     static constexpr int LST = NDP + 4;            // row stride of L / Y: float4 rows, conflict-free
@@ -440,7 +445,7 @@ struct Env {
         }
         __syncwarp();
         // solver budget: MAXC contacts, and no more than the row budget leaves after this sub-step's limit rows (nl)
-        const int room = (C::MAXR - nl) / 3;
+        const int room = (C::MAXR - nl) / C::RPC;
         const int cap = room < C::MAXC ? room : C::MAXC;
         if (total > cap) ovf = 1;
         if (__any_sync(FULL, total > cap)) {
@@ -473,6 +478,7 @@ struct Env {
                 ct[0] = __int_as_float(ba); ct[1] = __int_as_float(bb); ct[2] = __int_as_float(s);
                 st3(ct + 4, pa[p] - xref); st3(ct + 7, pb[p] - xref); st3(ct + 10, nn[p]);
                 ct[13] = dist[p]; ct[14] = mu;
+                if (C::TORS) { ct[3] = s < C::NCAND ? m->c_spin[s] : 0.f; ct[15] = s < C::NCAND ? m->c_roll[s] : 0.f; }
             } else if (s < C::NSLOT) {
                 warm[s] = 0.f;
             }
@@ -514,7 +520,7 @@ struct Env {
         const float *Lm = sm + C::sL, *inv = sm + C::sINV;
         float *Ym = sm + C::sY, *lam = sm + C::sLAM;
         const float *warm = S + C::oW;
-        const int nr = nl + 3 * nc;
+        const int nr = nl + C::RPC * nc;
         float J[NS][C::ND], pen[NS];
         int kind[NS], slot[NS];
         V3 d[NS], pA[NS], pB[NS], pAx[NS], pBx[NS];
@@ -541,9 +547,14 @@ struct Env {
                 const int ci = i - nl;
                 int c;
                 const float *ct;
-                if (ci < nc) { kind[sl] = 1; c = ci; ct = sm + C::sCT + c * C::CTS; d[sl] = ld3(ct + 10); }
+                float coef = 0.f;
+                if (ci < nc) { kind[sl] = 1; c = ci; ct = sm + C::sCT + c * C::CTS; d[sl] = ld3(ct + 10); coef = ct[14]; }
                 else {
-                    kind[sl] = 2; c = (ci - nc) >> 1; ct = sm + C::sCT + c * C::CTS;
+                    // bounded rows: [torsional: spin about n, roll about t1, roll about t2 per contact] then [lateral t1, t2]
+                    int bi = ci - nc, ax;
+                    if (C::TORS && bi < 3 * nc) { kind[sl] = 3; c = bi / 3; ax = bi - 3 * c; }
+                    else { kind[sl] = 2; bi -= 3 * C::TORS * nc; c = bi >> 1; ax = 1 + (bi & 1); }
+                    ct = sm + C::sCT + c * C::CTS;
                     const V3 n = ld3(ct + 10);
                     V3 t1, t2;   // btPlaneSpace1
                     if (fabsf(n.z) > 0.70710678f) {
@@ -553,12 +564,13 @@ struct Env {
                         const float aa = n.x * n.x + n.y * n.y, k = rsqrtf(aa);
                         t1 = mk(-n.y * k, n.x * k, 0.f); t2 = mk(-n.z * t1.y, n.z * t1.x, aa * k);
                     }
-                    d[sl] = ((ci - nc) & 1) ? t2 : t1;
+                    d[sl] = ax == 0 ? n : (ax == 1 ? t1 : t2);
+                    coef = kind[sl] == 2 ? ct[14] : (ax == 0 ? ct[3] : ct[15]);
                 }
                 const int ba = __float_as_int(ct[0]), bb = __float_as_int(ct[1]);
                 slot[sl] = __float_as_int(ct[2]);
                 pen[sl] = ct[13] + m->slop;
-                mu[sl] = ct[14];
+                mu[sl] = coef;
                 pA[sl] = ld3(ct + 4); pB[sl] = ld3(ct + 7);
                 ma[sl] = m->anc[ba]; mb[sl] = bb >= 0 ? m->anc[bb] : 0u;
                 pAx[sl] = pA[sl]; pBx[sl] = pB[sl];     // the same points seen from the cube's centre
@@ -573,7 +585,7 @@ struct Env {
 #pragma unroll
             for (int sl = 0; sl < NS; ++sl) {
                 float val = 0.f;
-                if ((ma[sl] >> k) & 1u) val += dot(d[sl], sv + cross(so, xk ? pAx[sl] : pA[sl]));
+                if ((ma[sl] >> k) & 1u) val += (C::TORS && kind[sl] == 3) ? dot(d[sl], so) : dot(d[sl], sv + cross(so, xk ? pAx[sl] : pA[sl]));
                 if (C::NPAIR > 0) { if ((mb[sl] >> k) & 1u) val -= dot(d[sl], sv + cross(so, xk ? pBx[sl] : pB[sl])); }
                 if (kind[sl] == 0) val = (k == ldof[sl]) ? ldir[sl] : 0.f;
                 J[sl][k] = val;
@@ -625,7 +637,7 @@ struct Env {
                 if (pen[sl] > 0.f) velerr -= pen[sl] * ih; else poserr = -pen[sl] * m->erp_contact * ih;
                 rhs[sl] = (poserr + velerr) * di; lo[sl] = 0.f; hi[sl] = 1e10f;
                 lmb[sl] = warm[slot[sl]] * m->warm;
-            } else if (kind[sl] == 2) {
+            } else if (kind[sl] >= 2) {
                 rhs[sl] = -rel[sl] * di;
             } else {
                 dinv[sl] = 0.f;
@@ -646,17 +658,23 @@ struct Env {
     // rows (they all precede the friction rows), and skipped while that impulse is zero: the bound is fetched once per sweep.
     // TWO: the warp holds an env with more than LPE rows; rows LPE.. live in a second register slot and are always friction
     // rows (NLIM + MAXC <= LPE), all normals in the first.
+    // contact index of the bi-th bounded (torsional / lateral friction) row of this env, see build_rows
+    __device__ __forceinline__ int bounded_row_contact(int bi) const {
+        if (C::TORS) { if (bi < 3 * nc) return bi / 3; bi -= 3 * nc; }
+        return bi >> 1;
+    }
+
     template <bool TWO>
     __device__ __forceinline__ void pgs(const int nrmax, const float (&rhs)[2], const float (&dinv)[2], const float (&lo)[2],
                                         const float (&hi)[2], float (&lmb)[2], const float (&mu)[2], float (&r)[2]) {
         static_assert(C::NLIM + C::MAXC <= C::LPE, "limit and normal rows must fit the first register slot");
         const int niter = m->niter;
-        const int nr = nl + 3 * nc;
+        const int nr = nl + C::RPC * nc;
         const float *Ag = sm + C::sA + gl;                                   // this lane's column of A
         const bool fr0 = gl >= nl + nc && gl < nr;
-        const int myn0 = fr0 ? nl + ((gl - nl - nc) >> 1) : 0;
+        const int myn0 = fr0 ? nl + bounded_row_contact(gl - nl - nc) : 0;
         const bool fr1 = TWO && C::LPE + gl < nr;
-        const int myn1 = fr1 ? nl + ((C::LPE + gl - nl - nc) >> 1) : 0;
+        const int myn1 = fr1 ? nl + bounded_row_contact(C::LPE + gl - nl - nc) : 0;
         const float rhs0 = rhs[0], dinv0 = dinv[0], mu0 = mu[0], rhs1 = rhs[1], dinv1 = dinv[1], mu1 = mu[1];
         float lam0 = lmb[0], r0 = r[0], lam1 = lmb[1], r1 = r[1];
         float lo0 = lo[0], hi0 = hi[0];
@@ -925,7 +943,7 @@ struct Env {
 
         PBG_PHASE(6);
         // --- constraint rows (lane = row, two slots)
-        const int nr = nl + 3 * nc;
+        const int nr = nl + C::RPC * nc;
         const int nrmax = wmax(nr);
 #ifdef PBG_PHASE_CLOCKS
         dbg_nov = max(dbg_nov, nrmax - C::LPE);
@@ -1298,6 +1316,8 @@ struct Env {
 
     // MuJoCo-style Hopper / Walker2D (pybulletgym/envs/mujoco/robot_locomotors.py:86-165, gym_locomotion_envs.py:121-206):
     // obs = qpos[1:] ++ clip(qvel, +-10) over all dofs (root joints included); reward = [dx / dt, 1, -1e-3 |a|^2].
+    // HalfCheetah (kind 16, mujoco/robot_locomotors.py:169-211, gym_locomotion_envs.py:211-244): qvel unclipped,
+    // reward = [dx / dt, -0.1 |a|^2], never done.
     __device__ bool mjwalker_task(const float *act, float *obs_out, float *rew_out, float *terms_out, bool reset_pass, bool pred) {
         float *S = st();
         float *T = S + C::oT;
@@ -1305,16 +1325,17 @@ struct Env {
         const float *kt = kin(m->torso_body);
         const float x = kt[9] + mulR(kt, ld3(m->torso_off)).x;       // robot_body.get_pose()[0]: torso link COM
         const float q = gl < C::NJ ? S[C::oQ + gl] : 0.f;
-        const float qd = gl < C::NJ ? fminf(fmaxf(S[C::oU + gl], -10.f), 10.f) : 0.f;
+        const bool cheetah = m->kind == 16;
+        const float qd = gl < C::NJ ? (cheetah ? S[C::oU + gl] : fminf(fmaxf(S[C::oU + gl], -10.f), 10.f)) : 0.f;
         const float aval = (act && gl < C::NACT) ? act[gl] : 0.f;
         const float ss = gsum(aval * aval);
         // done = not (finite and |state[2:]| < 100 and height / angle window)
-        bool bad = gl < C::NJ && (!(isfinite(q) && isfinite(qd)) || (gl >= 3 && !(fabsf(q) < 100.f)));   // qvel is clipped to 10
+        bool bad = gl < C::NJ && (!(isfinite(q) && isfinite(qd)) || (!cheetah && gl >= 3 && !(fabsf(q) < 100.f)));   // qvel is clipped to 10
         const bool anybad = gballot(bad) != 0u;
         const float height = S[C::oQ + 1], ang = S[C::oQ + 2];
         bool ok = !anybad;
         if (m->kind == 12) ok = ok && height > -0.3f && fabsf(ang) < 0.2f;
-        else ok = ok && 1.0f > height && height > -0.2f && -1.0f < ang && ang < 1.0f;
+        else if (!cheetah) ok = ok && 1.0f > height && height > -0.2f && -1.0f < ang && ang < 1.0f;
         if (pred) {
             if (obs_out && gl < C::NJ) {
                 if (gl >= 1) obs_out[gl - 1] = q;
@@ -1323,10 +1344,12 @@ struct Env {
             if (gl == 0) {
                 if (!reset_pass) {
                     const float pot = anybad ? 0.f : (float)(((double)x - (double)T[T_POT_LO]) / m->dt_scene);
-                    const float pc = anybad ? 0.f : -1e-3f * ss;
-                    const float al = anybad ? 0.f : 1.0f;        // a non-finite state ends the episode with reward 0
+                    const float pc = anybad ? 0.f : (cheetah ? -0.1f : -1e-3f) * ss;
+                    const float al = (anybad || cheetah) ? 0.f : 1.0f;        // a non-finite state ends the episode with reward 0
                     if (rew_out) *rew_out = pot + al + pc;
-                    if (terms_out) { terms_out[0] = pot; terms_out[1] = al; terms_out[2] = pc; terms_out[3] = 0.f; terms_out[4] = 0.f; }
+                    if (terms_out) {
+                        terms_out[0] = pot; terms_out[1] = cheetah ? pc : al; terms_out[2] = cheetah ? 0.f : pc; terms_out[3] = 0.f; terms_out[4] = 0.f;
+                    }
                     if (anybad) T[T_HAVEZ] = 2.f;
                 }
                 T[T_POT_LO] = x;
@@ -1401,7 +1424,7 @@ struct Env {
                          bool pred = true) {
         if (m->kind <= 1 || m->kind == 9 || m->kind == 11) return pendulum_task(obs_out, rew_out, terms_out, reset_pass, pred);
         if (m->kind == 10) return reacher_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
-        if (m->kind == 12 || m->kind == 13) return mjwalker_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
+        if (m->kind == 12 || m->kind == 13 || m->kind == 16) return mjwalker_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
         return walker_task(act, obs_out, rew_out, terms_out, reset_pass, pred);
     }
 
@@ -1435,7 +1458,7 @@ struct Env {
                 if (m->kind <= 1) { if (gl == 0) S[C::oQ + 1] = nz + (m->kind == 1 ? 3.1415f : 0.f); }
                 else if (m->kind == 9 || m->kind == 11) S[C::oQ + 1 + gl] = nz;   // hinge, hinge2 (rs/robot_pendula.py:66-68)
                 else if (m->kind == 10) S[C::oQ + (gl ^ 2)] = nz;        // draws: target_x, target_y, joint0, joint1 -> dofs 2, 3, 0, 1
-                else if (m->kind == 12 || m->kind == 13) S[C::oQ + gl] = nz;   // every ordered joint incl. the root joints
+                else if (m->kind == 12 || m->kind == 13 || m->kind == 16) S[C::oQ + gl] = nz;   // every ordered joint incl. the root joints
                 else S[C::oQ + m->act_joint[gl]] = nz;
             }
             if (gl == 0) {

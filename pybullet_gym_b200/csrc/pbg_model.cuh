@@ -33,6 +33,7 @@ struct DevModel {
     int act_joint[MJ];
     int c_body[MCAND], c_foot[MCAND];
     float c_p[MCAND][3], c_rad[MCAND], c_thr[MCAND], c_mu[MCAND];
+    float c_spin[MCAND], c_roll[MCAND];      // combined spinning / rolling friction of a ground candidate (torsional rows)
     int p_ba[MPAIR], p_bb[MPAIR];
     float p_a0[MPAIR][3], p_a1[MPAIR][3], p_b0[MPAIR][3], p_b1[MPAIR][3], p_ra[MPAIR], p_rb[MPAIR], p_thr[MPAIR],
         p_mu[MPAIR];

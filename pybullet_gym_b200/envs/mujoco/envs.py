@@ -3,8 +3,8 @@
 Backed so far: InvertedDoublePendulumMuJoCoEnv-v0 (mujoco/gym_pendulum_envs.py:40-75, mujoco/robot_pendula.py:55-91),
 HopperMuJoCoEnv-v0 and Walker2DMuJoCoEnv-v0 (mujoco/gym_locomotion_envs.py:121-206, mujoco/robot_locomotors.py:86-165).
 The reference's InvertedPendulumMuJoCoEnv raises on its first reset (mujoco/robot_pendula.py:16 reads an undefined
-``self.swingup``); HalfCheetahMuJoCoEnv switches spinning / rolling friction and restitution on for every link
-(mujoco/robot_locomotors.py:209-210), which the CUDA contact rows do not model yet.  AntMuJoCoEnv-v0 and
+``self.swingup``).  HalfCheetahMuJoCoEnv-v0 (mujoco/gym_locomotion_envs.py:211-244, mujoco/robot_locomotors.py:169-211): its reset's
+changeDynamics call lands on the stadium floor (spec.py), which gives every ground contact torsional friction rows.  AntMuJoCoEnv-v0 and
 HumanoidMuJoCoEnv-v0 (mujoco/gym_locomotion_envs.py:246-260, mujoco/robot_locomotors.py:222-319) re-pack the WalkerBase state
 as qpos[2:] ++ qvel ++ zero padding (111 / 376 entries).
 """
@@ -123,6 +123,21 @@ class Walker2DMuJoCoEnv(WalkerBaseMuJoCoEnv):
         WalkerBaseMuJoCoEnv.__init__(self, self.robot, **kw)
 
 
+class HalfCheetahMuJoCoEnv(WalkerBaseMuJoCoEnv):
+    """rewards = [potential, power_cost], never done (mujoco/gym_locomotion_envs.py:216-244)."""
+
+    def __init__(self, **kw):
+        self.robot = _MJWalker("HalfCheetahMuJoCoEnv-v0")
+        WalkerBaseMuJoCoEnv.__init__(self, self.robot, **kw)
+
+    def _step(self, a):
+        state, rew, d, info = WalkerBaseMuJoCoEnv._step(self, a)
+        self.reward -= sum(self.rewards)
+        self.rewards = self.rewards[:2]
+        self.reward += sum(self.rewards)
+        return state, sum(self.rewards), d, info
+
+
 class Ant(R.WalkerBase):
     def __init__(self):
         R.WalkerBase.__init__(self, "AntMuJoCoEnv-v0")
@@ -162,4 +177,5 @@ class HumanoidMuJoCoEnv(_FloatingMuJoCoEnv):
 
 ENTRY_POINTS = {"InvertedDoublePendulumMuJoCoEnv-v0": InvertedDoublePendulumMuJoCoEnv,
                 "HopperMuJoCoEnv-v0": HopperMuJoCoEnv, "Walker2DMuJoCoEnv-v0": Walker2DMuJoCoEnv,
+                "HalfCheetahMuJoCoEnv-v0": HalfCheetahMuJoCoEnv,
                 "AntMuJoCoEnv-v0": AntMuJoCoEnv, "HumanoidMuJoCoEnv-v0": HumanoidMuJoCoEnv}

@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 KIND_PENDULUM, KIND_PENDULUM_SWINGUP, KIND_HOPPER, KIND_WALKER2D, KIND_HALFCHEETAH, KIND_ANT, KIND_HUMANOID, \
-    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM, KIND_REACHER, KIND_DOUBLE_PENDULUM_MJ, KIND_HOPPER_MJ, KIND_WALKER2D_MJ, KIND_ANT_MJ, KIND_HUMANOID_MJ = range(16)
+    KIND_FLAGRUN, KIND_FLAGRUN_HARDER, KIND_DOUBLE_PENDULUM, KIND_REACHER, KIND_DOUBLE_PENDULUM_MJ, KIND_HOPPER_MJ, KIND_WALKER2D_MJ, KIND_ANT_MJ, KIND_HUMANOID_MJ, KIND_HALFCHEETAH_MJ = range(17)
 
 
 @dataclass(frozen=True)
@@ -45,6 +45,8 @@ class SceneSpec:
     limit_split_impulse: bool = True
     split_impulse_threshold: float = -0.04
     torsional_friction: bool = False     # spinning / rolling friction rows (C1.11, C6-9)
+    ground_spinning_friction: float = 0.0    # the floor's own coefficients (changeDynamics(spinningFriction=, rollingFriction=))
+    ground_rolling_friction: float = 0.0
 
     @property
     def dt(self) -> float:
@@ -107,7 +109,7 @@ class EnvSpec:
             return 2
         if self.kind == KIND_REACHER:
             return 4            # target_x, target_y, joint0, joint1 (robot_manipulators.py:12-21)
-        if self.kind in (KIND_HOPPER_MJ, KIND_WALKER2D_MJ):
+        if self.kind in (KIND_HOPPER_MJ, KIND_WALKER2D_MJ, KIND_HALFCHEETAH_MJ):
             # add_ignored_joints=True puts the three root joints into ordered_joints, and WalkerBase.robot_specific_reset
             # draws for every ordered joint (mujoco/robot_bases.py:85-90, mujoco/robot_locomotors.py:16-19)
             return self.action_dim + 3
@@ -163,6 +165,17 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
     EnvSpec("Walker2DMuJoCoEnv-v0", KIND_WALKER2D_MJ, "walker2d.xml", "torso", 6, 17, 0.40,
             power_coef={"foot_joint": 30.0, "foot_left_joint": 30.0}, foot_list=("foot", "foot_left"),
             reward_threshold=2500.0, entry_point="pybulletgym.envs.mujoco.gym_locomotion_envs:Walker2DMuJoCoEnv"),
+    # HalfCheetah.robot_specific_reset (mujoco/robot_locomotors.py:207-210) calls changeDynamics(part.bodyIndex, part.bodyPartIndex,
+    # lateralFriction=0.8, spinningFriction=0.1, rollingFriction=0.1, restitution=0.5) for every part.  part.bodyIndex is the
+    # index into the robot's own body list (0), i.e. pybullet body 0 = the stadium floor, so what the call changes is the
+    # FLOOR (its base link for the torso's bodyPartIndex -1; [EXT] link indices that do not exist on the floor are taken to be
+    # ignored): lateral friction 0.8 (unchanged), restitution 0.5 (x link restitution 0 = 0) and spinning / rolling friction 0.1,
+    # which Bullet combines with every link's lateral friction -> torsional friction rows on all ground contacts.
+    EnvSpec("HalfCheetahMuJoCoEnv-v0", KIND_HALFCHEETAH_MJ, "half_cheetah.xml", "torso", 6, 17, 1.0,
+            power_coef={"bthigh": 120.0, "bshin": 90.0, "bfoot": 60.0, "fthigh": 140.0, "fshin": 60.0, "ffoot": 30.0},
+            foot_list=("ffoot", "fshin", "fthigh", "bfoot", "bshin", "bthigh"), reward_threshold=3000.0,
+            scene=SceneSpec(torsional_friction=True, ground_spinning_friction=0.1, ground_rolling_friction=0.1),
+            entry_point="pybulletgym.envs.mujoco.gym_locomotion_envs:HalfCheetahMuJoCoEnv"),
     EnvSpec("AntMuJoCoEnv-v0", KIND_ANT_MJ, "ant.xml", "torso", 8, 111, 2.5,
             foot_list=("front_left_foot", "front_right_foot", "left_back_foot", "right_back_foot"),
             reward_threshold=2500.0, entry_point="pybulletgym.envs.mujoco.gym_locomotion_envs:AntMuJoCoEnv"),
@@ -203,5 +216,5 @@ SPECS: Dict[str, EnvSpec] = {s.id: s for s in [
 UNBACKED_IDS = (
     "PusherPyBulletEnv-v0",
     "ThrowerPyBulletEnv-v0", "StrikerPyBulletEnv-v0", "AtlasPyBulletEnv-v0",
-    "InvertedPendulumMuJoCoEnv-v0", "HalfCheetahMuJoCoEnv-v0",
+    "InvertedPendulumMuJoCoEnv-v0",
 )

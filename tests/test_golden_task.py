@@ -68,9 +68,24 @@ def test_golden_membership_matches_compiler():
         g = json.load(open(path))
         spec = SPECS[g["env_id"]]
         bm = mj.parse_mjcf(spec.xml)
-        if spec.kind in (12, 13):      # MuJoCo-style Hopper / Walker2D: add_ignored_joints=True keeps the root joints
+        if spec.kind in (12, 13, 16):      # MuJoCo-style Hopper / Walker2D / HalfCheetah: add_ignored_joints=True keeps the root joints
             assert g["ordered_joints"] == [bm.links[i].joint_name for i in bm.dof_links()]
         else:
             assert g["ordered_joints"] == [bm.links[i].joint_name for i in bm.ordered_joints()]
         if 2 <= spec.kind <= 8:
             assert sorted(bm.part_names() + ["floor"]) == g["parts"]
+
+
+def test_halfcheetah_mujoco_torsional_friction_lands_on_the_floor():
+    """HalfCheetah.robot_specific_reset (mujoco/robot_locomotors.py:207-210) calls changeDynamics(part.bodyIndex, part.bodyPartIndex,
+    ..., spinningFriction=0.1, rollingFriction=0.1, ...): running the reference's own Python shows every call addressing pybullet
+    body 0 -- the stadium floor -- among them the floor's base link (-1).  The spec models exactly that: torsional friction rows
+    with the FLOOR's coefficients 0.1 / 0.1 (combined with each link's lateral friction), lateral friction 0.8 unchanged."""
+    from pybullet_gym_b200.spec import SPECS
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "task_HalfCheetahMuJoCo.json")))
+    calls = g["torsional_change_dynamics"]
+    assert calls and all(body == 0 and kind == "floor" for body, link, kind, kw in calls)
+    base = [kw for body, link, kind, kw in calls if link == -1]
+    assert base and all(kw == {"lateralFriction": 0.8, "spinningFriction": 0.1, "rollingFriction": 0.1, "restitution": 0.5} for kw in base)
+    sc = SPECS["HalfCheetahMuJoCoEnv-v0"].scene
+    assert sc.torsional_friction and sc.ground_spinning_friction == 0.1 and sc.ground_rolling_friction == 0.1 and sc.ground_friction == 0.8

@@ -26,9 +26,9 @@ pytestmark = pytest.mark.gpu
 IDS = ["InvertedPendulumPyBulletEnv-v0", "InvertedDoublePendulumPyBulletEnv-v0", "ReacherPyBulletEnv-v0", "HopperPyBulletEnv-v0", "Walker2DPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0",
        "AntPyBulletEnv-v0", "HumanoidPyBulletEnv-v0"]
 FLAGRUN_IDS = ["HumanoidFlagrunPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0"]
-PHYS_IDS = IDS + FLAGRUN_IDS
+PHYS_IDS = IDS + FLAGRUN_IDS + ["HalfCheetahMuJoCoEnv-v0"]      # the latter: torsional friction rows
 TASK_IDS = IDS + ["HumanoidFlagrunPyBulletEnv-v0", "HumanoidFlagrunHarderPyBulletEnv-v0", "InvertedDoublePendulumMuJoCoEnv-v0",
-                  "HopperMuJoCoEnv-v0", "Walker2DMuJoCoEnv-v0", "AntMuJoCoEnv-v0", "HumanoidMuJoCoEnv-v0"]
+                  "HopperMuJoCoEnv-v0", "Walker2DMuJoCoEnv-v0", "HalfCheetahMuJoCoEnv-v0", "AntMuJoCoEnv-v0", "HumanoidMuJoCoEnv-v0"]
 E = 48
 
 
@@ -114,7 +114,7 @@ def test_observation_reward_parity_T1(env_id, oracle_lib):
             tail = slice(oobs.shape[1] - nf, oobs.shape[1])
             worst_tail = max(worst_tail, np.abs(gobs[same_flags, tail] - oobs[same_flags, tail]).max())
             n_tail_cmp += int(same_flags.sum())
-        if env.spec.kind in (12, 13):
+        if env.spec.kind in (12, 13, 16):
             # MuJoCo-style walkers: terms[0] = dx / dt carries the fp32 error of x itself (x / 0.0165 * 6e-8)
             x = np.abs(ost[:, 0])
             worst_prog = max(worst_prog, (np.abs(gterms[:, 0] - oterms[:, 0]) / (1.0 + x)).max())
@@ -342,7 +342,7 @@ def _ks_pvalue(a, b):
 
 T4_CAP = {"HopperPyBulletEnv-v0": 1000, "Walker2DPyBulletEnv-v0": 1000, "HalfCheetahPyBulletEnv-v0": 1000,
           "AntPyBulletEnv-v0": 300, "HumanoidPyBulletEnv-v0": 300, "HumanoidFlagrunPyBulletEnv-v0": 300,
-          "HumanoidFlagrunHarderPyBulletEnv-v0": 300}
+          "HumanoidFlagrunHarderPyBulletEnv-v0": 300, "HalfCheetahMuJoCoEnv-v0": 200}
 
 
 def _t4_sample(env_id, oracle_lib, n, m, cap, gpu_seed, act_seed, orc_seed):

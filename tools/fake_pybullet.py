@@ -86,6 +86,8 @@ class FakeBulletClient:
 
     def changeDynamics(self, body, link, **kw):
         self.bodies[body].setdefault("dynamics", {}).update(kw)
+        self.dynamics_calls = getattr(self, "dynamics_calls", [])
+        self.dynamics_calls.append((int(body), int(link), self.bodies[body]["kind"], dict(kw)))
 
     def disconnect(self):
         pass

@@ -36,6 +36,7 @@ CASES = {
     "InvertedDoublePendulumMuJoCoEnv-v0": ("mujoco.gym_pendulum_envs", "InvertedDoublePendulumMuJoCoEnv", 3, 60, 0.3),
     "HopperMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "HopperMuJoCoEnv", 6, 40, 0.2),
     "Walker2DMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "Walker2DMuJoCoEnv", 4, 40, 1.3),
+    "HalfCheetahMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "HalfCheetahMuJoCoEnv", 3, 60, 1.3),
     "AntMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "AntMuJoCoEnv", 3, 40, 1.3),
     "HumanoidMuJoCoEnv-v0": ("mujoco.gym_locomotion_envs", "HumanoidMuJoCoEnv", 3, 40, 1.3),
     "ReacherPyBulletEnv-v0": ("gym_manipulator_envs", "ReacherBulletEnv", 3, 60, 1.3),
@@ -115,6 +116,11 @@ def main():
                "episodes": eps}
         if held:
             out["held"] = True
+        # changeDynamics calls that switch torsional friction on, with the body they land on (HalfCheetahMuJoCoEnv's reset
+        # addresses pybullet body `part.bodyIndex` = 0, the stadium floor: mujoco/robot_locomotors.py:207-210)
+        tors = [[b, l, kind, kw] for b, l, kind, kw in getattr(env._p, "dynamics_calls", []) if "spinningFriction" in kw]
+        if tors:
+            out["torsional_change_dynamics"] = tors
         stem = env_id.split("PyBullet")[0] if "PyBullet" in env_id else env_id.split("Env-")[0]
         path = os.path.join(OUT, "task_%s%s.json" % (stem, "Held" if held else ""))
         with open(path, "w") as f:
