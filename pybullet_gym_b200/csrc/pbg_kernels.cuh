@@ -580,7 +580,9 @@ struct Env {
         // Jacobian entries, one S_k load for all slots
 #pragma unroll
         for (int k = 0; k < C::ND; ++k) {
-            const V3 so = ld3(SH + k * 12), sv = ld3(SH + k * 12 + 3);
+            const float4 s03 = *reinterpret_cast<const float4 *>(SH + k * 12);
+            const float2 s45 = *reinterpret_cast<const float2 *>(SH + k * 12 + 4);
+            const V3 so = mk(s03.x, s03.y, s03.z), sv = mk(s03.w, s45.x, s45.y);
             const bool xk = C::HASX && k >= C::XD0;
 #pragma unroll
             for (int sl = 0; sl < NS; ++sl) {
@@ -964,16 +966,23 @@ struct Env {
         float r[2] = {0.f, 0.f};
         if (nrmax > 0) {
             for (int i = 0; i < nrmax; ++i) {
-                float yi[C::ND];
+                // row i of Y as float4 loads (rows are 16-byte aligned; entries ND.. of a row are padding and never used)
+                float yi[C::NDP];
 #pragma unroll
-                for (int k = 0; k < C::ND; ++k) yi[k] = Ym[i * C::LST + k];
+                for (int k4 = 0; k4 < C::NDP / 4; ++k4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(Ym + i * C::LST + 4 * k4);
+                    yi[4 * k4] = v.x; yi[4 * k4 + 1] = v.y; yi[4 * k4 + 2] = v.z; yi[4 * k4 + 3] = v.w;
+                }
                 const float l0 = lam[i];
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl) {
                     if (sl * C::LPE >= nrmax) continue;
-                    float aij = 0.f;
+                    // two partial sums: halves the dependent FMA chain of the dot product
+                    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                    for (int k = 0; k < C::ND; ++k) aij += yi[k] * Yr[sl][k];
+                    for (int k = 0; k + 1 < C::ND; k += 2) { a0 = fmaf(yi[k], Yr[sl][k], a0); a1 = fmaf(yi[k + 1], Yr[sl][k + 1], a1); }
+                    if (C::ND & 1) a0 = fmaf(yi[C::ND - 1], Yr[sl][C::ND - 1], a0);
+                    const float aij = a0 + a1;
                     const int jrow = sl * C::LPE + gl;
                     if (jrow < C::MAXR) Am[i * C::MAXRP + jrow] = aij;
                     r[sl] += aij * l0;
