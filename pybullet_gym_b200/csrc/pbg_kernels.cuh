@@ -139,7 +139,11 @@ struct KCfg {
     // two envs per warp: place the second env's block 16 banks away from the first one's (stride = 16 mod 32), so that the two
     // half-warps never collide, neither on env-uniform (broadcast) nor on lane-indexed shared-memory accesses
     static constexpr int ENV_FLOATS = LPE == 16 ? ENV_FLOATS_RAW + ((48 - ENV_FLOATS_RAW % 32) % 32) : ENV_FLOATS_RAW;
-    static constexpr size_t SMEM_BYTES = size_t(ENV_FLOATS) * EPB * sizeof(float);
+    static constexpr size_t ENV_BYTES = size_t(ENV_FLOATS) * EPB * sizeof(float);
+    // the model tables (13 KB of joint / geometry / scene constants read all over the step) are copied into shared memory behind
+    // the env blocks when they fit: lane-indexed table reads become shared-memory loads instead of L1-cached global loads
+    static constexpr bool MODEL_IN_SMEM = ENV_BYTES + sizeof(DevModel) <= 227 * 1024;
+    static constexpr size_t SMEM_BYTES = ENV_BYTES + (MODEL_IN_SMEM ? sizeof(DevModel) : 0);
     static constexpr int HIDCAP = ENV_FLOATS - sU;             // room for the fused policy's hidden activations
 };
 
@@ -1505,6 +1509,16 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     PBG_PHASE_BEGIN;
 #ifdef PBG_PHASE_CLOCKS
     const long long _kstart = clock64();
+#endif
+#ifndef PBG_NO_SMEM_MODEL
+    if (C::MODEL_IN_SMEM) {
+        static_assert(sizeof(DevModel) % 16 == 0 && C::ENV_BYTES % 16 == 0, "model copy is done in 16-byte words");
+        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<char *>(smem) + C::ENV_BYTES);
+        const float4 *src = reinterpret_cast<const float4 *>(model);
+        for (int i = threadIdx.x; i < int(sizeof(DevModel) / 16); i += C::THREADS) dst[i] = src[i];
+        __syncthreads();
+        model = reinterpret_cast<const DevModel *>(dst);
+    }
 #endif
     e.m = model;
     e.gl = lane & (C::LPE - 1);

@@ -17,7 +17,7 @@ constexpr int MPAIR = 84;   // max geom pairs (humanoid: 66 self-collision pairs
 constexpr int MFEET = 8;
 constexpr int TASK_FLOATS = 24;
 
-struct DevModel {
+struct alignas(16) DevModel {
     int nb, nj, nd, floating, ncand, npair, nact, nfeet, obs_dim, kind, maxdepth, torso_body, nlim;
     int parent[MB], jtype[MB], depth[MB], dof[MB];
     unsigned up[MJ + 6];        // per dof: dofs that move the dof's body (ancestors or self)
