@@ -112,6 +112,11 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
         d->depth[b] = pm->parent[b] < 0 ? 0 : d->depth[pm->parent[b]] + 1;
         if (d->depth[b] > d->maxdepth) d->maxdepth = d->depth[b];
         quat_to_mat(pm->q0 + 4 * b, d->q0m[b]);
+        if (k.q0id) {
+            const double *q = pm->q0 + 4 * b;
+            if (std::fabs(q[0]) > 1e-12 || std::fabs(q[1]) > 1e-12 || std::fabs(q[2]) > 1e-12 || std::fabs(std::fabs(q[3]) - 1.0) > 1e-12)
+                return "this env kind's kernel assumes identity rest rotations (q0) for every body";
+        }
         for (int i = 0; i < 3; ++i) {
             d->anchor_p[b][i] = (float)pm->anchor_p[3 * b + i];
             d->com_off[b][i] = (float)pm->com_off[3 * b + i];

@@ -7,7 +7,7 @@
 namespace pbg {
 
 struct KernelInfo {
-    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet, nnoise, ysz, off_task, nslot, maxr, tors;
+    int nb, nj, floating, nlim, maxc, ncand, npair, nfeet, nact, obs, sstride, canon, epb, threads, hasx, off_feet, nnoise, ysz, off_task, nslot, maxr, tors, q0id;
     size_t smem;
     void (*launch)(const DevModel *, const StepBuffers &, const LaunchArgs &, cudaStream_t);
     cudaError_t (*prepare)();

@@ -7,23 +7,23 @@ namespace pbg {
 
 // kernel configurations: NB, NJ, FLOATING, NLIM, MAXC, LPE, NCAND, NPAIR, NFEET, NACT, OBS, WARPS per CTA, CTAs per SM
 // 14 warps x 2 envs = 28 envs per CTA = one CTA per SM (7.2 KB shared memory per env): 148 CTAs hold 4144 envs.
-using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5, 4, 4>;
-using CfgDoublePendulum = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 9, 4, 4, 0, 2>;
-using CfgDoublePendulumMJ = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 11, 4, 4, 0, 2>;
-using CfgReacher = KCfg<4, 4, 0, 3, 0, 16, 0, 0, 0, 2, 9, 4, 4, 0, 4, TopoReacher>;
-using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15, 14, 1>;
-using CfgHopperMJ = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 11, 14, 1, 0, 6>;
-using CfgWalkerMJ = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 17, 14, 1, 0, 9, TopoBiped2D>;
-using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1, 0, 6, TopoBiped2D>;
-using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1, 0, 6, TopoBiped2D>;
+using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5, 4, 4, 0, 1, TopoDense, 0, 0, 1>;
+using CfgDoublePendulum = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 9, 4, 4, 0, 2, TopoDense, 0, 0, 1>;
+using CfgDoublePendulumMJ = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 11, 4, 4, 0, 2, TopoDense, 0, 0, 1>;
+using CfgReacher = KCfg<4, 4, 0, 3, 0, 16, 0, 0, 0, 2, 9, 4, 4, 0, 4, TopoReacher, 0, 0, 1>;
+using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15, 14, 1, 0, 3, TopoDense, 0, 0, 1>;
+using CfgHopperMJ = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 11, 14, 1, 0, 6, TopoDense, 0, 0, 1>;
+using CfgWalkerMJ = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 17, 14, 1, 0, 9, TopoBiped2D, 0, 0, 1>;
+using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1, 0, 6, TopoBiped2D, 0, 0, 1>;
+using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1, 0, 6, TopoBiped2D, 0, 0, 1>;
 // HalfCheetahMuJoCoEnv: the cheetah with torsional friction rows (6 rows per contact: up to 42 rows -> one env per warp)
-using CfgCheetahMJ = KCfg<9, 9, 0, 6, 6, 32, 16, 0, 6, 6, 17, 14, 1, 0, 9, TopoBiped2D, 0, 1>;
+using CfgCheetahMJ = KCfg<9, 9, 0, 6, 6, 32, 16, 0, 6, 6, 17, 14, 1, 0, 9, TopoBiped2D, 0, 1, 1>;
 #ifndef PBG_ANT_WARPS
 #define PBG_ANT_WARPS 14
 #define PBG_ANT_BLOCKS 1
 #endif
-using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28, PBG_ANT_WARPS, PBG_ANT_BLOCKS, 0, 8, TopoAnt>;
-using CfgAntMJ = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 111, PBG_ANT_WARPS, PBG_ANT_BLOCKS, 0, 8, TopoAnt>;
+using CfgAnt = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 28, PBG_ANT_WARPS, PBG_ANT_BLOCKS, 0, 8, TopoAnt, 0, 0, 1>;
+using CfgAntMJ = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 111, PBG_ANT_WARPS, PBG_ANT_BLOCKS, 0, 8, TopoAnt, 0, 0, 1>;
 using CfgHumanoidMJ = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 376, 14, 1, 0, 17, TopoHumanoid, 40>;
 // The humanoid kinds run 14 envs (warps) per SM -- 2048 envs are one wave of 147 CTAs -- which needs <= 16.2 KB of shared memory
 // per env: a row budget of 40 (17 possible limit rows + 12 x 3 contact rows would be 53; random-policy rollouts peak at 26 rows,
@@ -57,7 +57,7 @@ static void read_phases(unsigned long long *out32, int reset) {
 template <class C>
 static KernelInfo info_of() {
     KernelInfo ki = KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::MAXR, C::TORS, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases, {0}};
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::MAXR, C::TORS, C::Q0ID, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases, {0}};
     for (int k = 0; k < C::ND; ++k) ki.low[k] = C::low(k);
     return ki;
 }

@@ -68,7 +68,7 @@ struct TopoHumanoid {   // base 0-5, abdomen 6-8, right leg 9-12, left leg 13-16
 // XP_ > 0: the world also holds HumanoidFlagrunHarder's cube (rs/robot_locomotors.py:236-266), a second free
 // body that is the last body / the last six dofs / the last eight ground candidates / the last XP_ pairs.
 template <int NB_, int NJ_, int FLOATING_, int NLIM_, int MAXC_, int LPE_, int NCAND_, int NPAIR_, int NFEET_,
-          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_, class TOPO_ = TopoDense, int MAXROWS_ = 0, int TORS_ = 0>
+          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_, class TOPO_ = TopoDense, int MAXROWS_ = 0, int TORS_ = 0, int Q0ID_ = 0>
 struct KCfg {
     static constexpr int NNOISE = NNOISE_;                     // injectable reset draws per env (pbg_reset_with)
     static constexpr int HASX = XP_ > 0 ? 1 : 0;
@@ -90,6 +90,9 @@ struct KCfg {
     // TORS_: every contact also gets Bullet's torsional friction rows (one spinning about the normal, two rolling about the
     // tangents), placed between the normal rows and the lateral friction rows: RPC rows per contact
     static constexpr int TORS = TORS_ ? 1 : 0;
+    // Q0ID_: every body's rest rotation relative to its parent is the identity (true for all the MJCF robots but the Humanoid):
+    // forward kinematics skips that matrix product and the lanes do not carry the nine constants (pbg_create checks the model)
+    static constexpr int Q0ID = Q0ID_ ? 1 : 0;
     static constexpr int RPC = 3 + 3 * TORS;
     static constexpr int MAXR = MAXROWS_ > 0 ? MAXROWS_ : NLIM + RPC * MAXC;
     static_assert(MAXR <= NLIM + RPC * MAXC && MAXR >= NLIM, "row budget");
@@ -256,7 +259,7 @@ struct Env {
         const int b = gl < C::NB ? gl : 0;
         bparent = m->parent[b]; bjtype = m->jtype[b]; bdepth = gl < C::NB ? m->depth[b] : 1000; bdof = m->dof[b];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Q0[i] = m->q0m[b][i];
+        for (int i = 0; i < 9; ++i) Q0[i] = C::Q0ID ? 0.f : m->q0m[b][i];
 #pragma unroll
         for (int i = 0; i < 3; ++i) { anchor_p[i] = m->anchor_p[b][i]; com_off[i] = m->com_off[b][i]; axis[i] = m->axis[b][i]; }
         bmass = m->mass[b]; alen = m->axis_len[b];
@@ -295,11 +298,16 @@ struct Env {
                     al = a = mk(0, 0, 0);
                 } else {
                     float Rq[9];
+                    if (C::Q0ID) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i)
+                        for (int i = 0; i < 9; ++i) Rq[i] = Rp[i];
+                    } else {
 #pragma unroll
-                        for (int j = 0; j < 3; ++j)
-                            Rq[3 * i + j] = Rp[3 * i] * Q0[j] + Rp[3 * i + 1] * Q0[3 + j] + Rp[3 * i + 2] * Q0[6 + j];
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j)
+                                Rq[3 * i + j] = Rp[3 * i] * Q0[j] + Rp[3 * i + 1] * Q0[3 + j] + Rp[3 * i + 2] * Q0[6 + j];
+                    }
                     const float q = S[C::oQ + bdof - 6 * C::FLOATING], qd = S[C::oU + bdof];
                     A = xp + mulR(Rp, ld3(anchor_p));
                     const V3 ax = ld3(axis);
