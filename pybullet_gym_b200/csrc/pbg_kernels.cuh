@@ -93,6 +93,10 @@ struct KCfg {
     // Q0ID_: every body's rest rotation relative to its parent is the identity (true for all the MJCF robots but the Humanoid):
     // forward kinematics skips that matrix product and the lanes do not carry the nine constants (pbg_create checks the model)
     static constexpr int Q0ID = Q0ID_ ? 1 : 0;
+    static constexpr bool FKREG = true;       // link-frame constants of forward kinematics stay in registers (read at every tree level)
+    // kinds that are not register-bound (7 warps per SM: 255 registers per thread) also keep a body's kinematics of the pass in
+    // registers between forward kinematics and the wrench phase instead of re-reading its kin() record
+    static constexpr bool KINREG = WARPS_ <= 8;
     static constexpr int RPC = 3 + 3 * TORS;
     static constexpr int MAXR = MAXROWS_ > 0 ? MAXROWS_ : NLIM + RPC * MAXC;
     static_assert(MAXR <= NLIM + RPC * MAXC && MAXR >= NLIM, "row budget");
@@ -220,14 +224,12 @@ struct Env {
     float *sm;          // this env's shared-memory block
     int gl;             // lane within the group
     int grp;            // group within the warp
-    // lane-as-body constants
+    // lane-as-body constants.  Only the tree indices stay in registers; link frames, masses and inertias are read from the
+    // model tables (shared memory for most kinds) where they are used -- once per sub-step each -- and a body's kinematics of
+    // the current pass live in its kin() record: the kernel is register-bound (128 per thread at 14 warps per SM)
     int bparent, bjtype, bdepth, bdof;
-    float Q0[9], anchor_p[3], com_off[3], axis[3], alen, bmass, Ib[6];
-    // lane-as-body kinematics of the current pass
-    float R[9];
-    V3 x, w, v, al, a;
-    // lane-as-dof constants
-    unsigned up, down;
+    float anchor_p[3], com_off[3], axis[3], alen;     // link-frame constants of forward kinematics
+    float kR[9]; V3 kx, kw, kv, kal, ka;               // KINREG kinds: this body's kinematics of the current pass
     float tau;          // joint force of this dof for the current env step
     int nc, nl;         // active contacts / limit rows of this env (group-uniform)
     int dbg_nov;        // development: most rows beyond LPE any sub-step of this env step had (warp-wide)
@@ -258,15 +260,11 @@ struct Env {
     __device__ void load_lane_constants() {
         const int b = gl < C::NB ? gl : 0;
         bparent = m->parent[b]; bjtype = m->jtype[b]; bdepth = gl < C::NB ? m->depth[b] : 1000; bdof = m->dof[b];
+        if (C::FKREG) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Q0[i] = C::Q0ID ? 0.f : m->q0m[b][i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { anchor_p[i] = m->anchor_p[b][i]; com_off[i] = m->com_off[b][i]; axis[i] = m->axis[b][i]; }
-        bmass = m->mass[b]; alen = m->axis_len[b];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) Ib[i] = m->inertia[b][i];
-        const int k = gl < C::ND ? gl : 0;
-        up = m->up[k]; down = m->down[k];
+            for (int i = 0; i < 3; ++i) { anchor_p[i] = m->anchor_p[b][i]; com_off[i] = m->com_off[b][i]; axis[i] = m->axis[b][i]; }
+            alen = m->axis_len[b];
+        }
         tau = 0.f; nc = 0; nl = 0; ovf = 0; dbg = nullptr;
     }
 
@@ -278,8 +276,10 @@ struct Env {
         const int maxdepth = m->maxdepth;
         for (int lvl = 0; lvl <= maxdepth; ++lvl) {
             if (bdepth == lvl) {
-                float Rp[9];
-                V3 xp, wp, vp, alp, ap;
+                float Rp[9], R[9];
+                V3 xp, wp, vp, alp, ap, x, w, v, al, a;
+                al = a = mk(0, 0, 0);
+                const int b = gl;                    // bdepth == lvl only for gl < NB
                 if (bparent >= 0) {
                     const float *kp = kin(bparent);
 #pragma unroll
@@ -306,12 +306,13 @@ struct Env {
                         for (int i = 0; i < 3; ++i)
 #pragma unroll
                             for (int j = 0; j < 3; ++j)
-                                Rq[3 * i + j] = Rp[3 * i] * Q0[j] + Rp[3 * i + 1] * Q0[3 + j] + Rp[3 * i + 2] * Q0[6 + j];
+                                Rq[3 * i + j] = Rp[3 * i] * m->q0m[b][j] + Rp[3 * i + 1] * m->q0m[b][3 + j] + Rp[3 * i + 2] * m->q0m[b][6 + j];
                     }
                     const float q = S[C::oQ + bdof - 6 * C::FLOATING], qd = S[C::oU + bdof];
-                    A = xp + mulR(Rp, ld3(anchor_p));
-                    const V3 ax = ld3(axis);
-                    zw = alen * mulR(Rq, ax);       // motion subspace: the MJCF axis as written (Bullet does not normalise it)
+                    const V3 cOff = C::FKREG ? ld3(com_off) : ld3(m->com_off[b]);
+                    A = xp + mulR(Rp, C::FKREG ? ld3(anchor_p) : ld3(m->anchor_p[b]));
+                    const V3 ax = C::FKREG ? ld3(axis) : ld3(m->axis[b]);
+                    zw = (C::FKREG ? alen : m->axis_len[b]) * mulR(Rq, ax);       // motion subspace: the MJCF axis as written (Bullet does not normalise it)
                     const V3 rpA = A - xp;
                     if (bjtype == 1) {
                         float s, c;
@@ -326,7 +327,7 @@ struct Env {
 #pragma unroll
                             for (int j = 0; j < 3; ++j)
                                 R[3 * i + j] = Rq[3 * i] * Rj[j] + Rq[3 * i + 1] * Rj[3 + j] + Rq[3 * i + 2] * Rj[6 + j];
-                        const V3 rAi = mulR(R, ld3(com_off));
+                        const V3 rAi = mulR(R, cOff);
                         x = A + rAi;
                         w = wp + qd * zw;
                         v = vp + cross(wp, rpA) + cross(w, rAi);
@@ -338,7 +339,7 @@ struct Env {
                     } else {
 #pragma unroll
                         for (int i = 0; i < 9; ++i) R[i] = Rq[i];
-                        x = A + q * zw + mulR(R, ld3(com_off));
+                        x = A + q * zw + mulR(R, cOff);
                         w = wp;
                         const V3 rpi = x - xp;
                         v = vp + cross(wp, rpi) + qd * zw;
@@ -347,6 +348,11 @@ struct Env {
                             a = ap + cross(alp, rpi) + cross(wp, cross(wp, rpi)) + (2.f * qd) * cross(wp, zw);
                         }
                     }
+                }
+                if (C::KINREG) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) kR[i] = R[i];
+                    kx = x; kw = w; kv = v; kal = al; ka = a;
                 }
                 float *k = kin(gl);
 #pragma unroll
@@ -792,9 +798,18 @@ struct Env {
         // --- body wrench + composite inertia entries (lane = body)
         float *acc = sm + C::sACC;
         if (gl < C::NB) {
+            // this body's kinematics of the pass, from its kin() record
+            const float *kb = kin(gl);
+            float R[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = C::KINREG ? kR[i] : kb[i];
+            const V3 x = C::KINREG ? kx : ld3(kb + 9), w = C::KINREG ? kw : ld3(kb + 12), v = C::KINREG ? kv : ld3(kb + 15);
+            const V3 al = C::KINREG ? kal : ld3(kb + 18), a = C::KINREG ? ka : ld3(kb + 21);
+            const float bmass = m->mass[gl];
             // world inertia I = R Ib R^T
             float T[9];   // R * Ib
             {
+                const float *Ib = m->inertia[gl];
                 const float Ixx = Ib[0], Iyy = Ib[1], Izz = Ib[2], Ixy = Ib[3], Ixz = Ib[4], Iyz = Ib[5];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
@@ -901,6 +916,7 @@ struct Env {
         // --- joint-space inertia: lane k keeps M[l][k] for the dofs l it supports (its descendants; the part of its row /
         // column the leaves-first factorisation reads), in registers
         float Mr[C::ND];
+        const unsigned down = m->down[gl < C::ND ? gl : 0];
 #pragma unroll
         for (int l = 0; l < C::ND; ++l) {
             const float4 s1 = *reinterpret_cast<const float4 *>(SH + l * 12 + 4);
@@ -1090,9 +1106,10 @@ struct Env {
         // mean x / y of robot.parts (lane = body)
         float px = 0.f, py = 0.f, pn = 0.f;
         if (gl < C::NB) {
-            const V3 o = mulR(R, ld3(m->part_sum[gl]));
+            const float *kb = kin(gl);
+            const V3 o = mulR(kb, ld3(m->part_sum[gl]));
             pn = m->part_cnt[gl];
-            px = pn * x.x + o.x; py = pn * x.y + o.y;
+            px = pn * kb[9] + o.x; py = pn * kb[10] + o.y;
         }
         px = gsum(px); py = gsum(py); pn = gsum(pn);
         const float floorp = T[T_FLOOR];
