@@ -377,3 +377,65 @@ def test_steps_capture_into_a_cuda_graph(env_id):
     st_g, st_e = graphed.stats(), eager.stats()
     assert st_g["steps"] == 2 * K * n
     assert st_g["episodes"] == st_e["episodes"] and st_g["length_sum"] == st_e["length_sum"]
+
+
+def test_cross_stream_ordering_is_the_library_s_job():
+    """pbg_step_host runs on a private stream and pbg_stats blocks on the legacy stream; neither used to be ordered
+    after a reset / step the caller had enqueued on ANOTHER stream.  The handle now remembers the stream of its last
+    stream-ordered call and waits for it: reset on a busy side stream followed directly by step_host / stats gives the same
+    result as the fully synchronised sequence."""
+    n = 512
+    env, twin = _mk("AntPyBulletEnv-v0", n, seed=21), _mk("AntPyBulletEnv-v0", n, seed=21)
+    a = (torch.rand(n, env.action_dim) * 2 - 1).pin_memory()
+    bufs = [(torch.empty(n, env.obs_dim).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory())
+            for _ in range(2)]
+    side = torch.cuda.Stream()
+    busy = torch.empty(64 * 1024 * 1024, device="cuda")
+    with torch.cuda.stream(side):
+        for _ in range(20):
+            busy.normal_()                      # keeps the side stream busy for a few ms before the reset runs
+        env.reset()
+        env.step_fast(torch.zeros(n, env.action_dim, device="cuda"))
+    env.step_host(a, *bufs[0])                  # no synchronisation by the caller
+    st = env.stats()
+    twin.reset(); torch.cuda.synchronize()
+    twin.step_fast(torch.zeros(n, twin.action_dim, device="cuda")); torch.cuda.synchronize()
+    twin.step_host(a, *bufs[1])
+    assert torch.equal(bufs[0][0], bufs[1][0]) and torch.equal(bufs[0][1], bufs[1][1]) and torch.equal(bufs[0][2], bufs[1][2])
+    assert st["steps"] == 2 * n == twin.stats()["steps"]
+
+
+def test_raw_pointer_paths_check_their_arguments():
+    """step_fast / step_host take raw data pointers; a wrong device / dtype / shape / stride or a step before the
+    first reset must raise instead of reading garbage."""
+    env = _mk("HopperPyBulletEnv-v0", 64)
+    good = torch.zeros(64, env.action_dim, device="cuda")
+    with pytest.raises(RuntimeError):
+        env.step_fast(good)                                     # before reset()
+    from pybullet_gym_b200 import _lib
+    with pytest.raises(_lib.PbgError):
+        env.step(good)                                          # the library refuses as well (PBG_ERR_INVALID)
+    env.reset()
+    env.step_fast(good)
+    for bad in (good.cpu(), good.double(), torch.zeros(63, env.action_dim, device="cuda"), torch.zeros(64, 2 * env.action_dim, device="cuda")[:, ::2]):
+        with pytest.raises(ValueError):
+            env.step_fast(bad)
+    with pytest.raises(ValueError):
+        env.step_host(good, torch.empty(64, env.obs_dim).pin_memory(), torch.empty(64).pin_memory(), torch.empty(64, dtype=torch.uint8).pin_memory())
+
+
+def test_restore_brings_back_the_step_outputs():
+    """observe() is the task half of a step, not a way to get the observation back; snapshot() therefore carries the
+    output buffers and restore() puts them back."""
+    env = _mk("HumanoidFlagrunPyBulletEnv-v0", 128, seed=3, auto_reset=True)
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    for _ in range(12):
+        obs, rew, done, info = env.step(torch.rand(128, env.action_dim, device="cuda", generator=gen) * 2 - 1)
+    keep = (obs.clone(), rew.clone(), done.clone(), info["reward_terms"].clone())
+    blob = env.snapshot()
+    for _ in range(5):
+        env.step(torch.rand(128, env.action_dim, device="cuda", generator=gen) * 2 - 1)
+    assert not torch.equal(env.obs, keep[0])
+    env.restore(blob)
+    assert torch.equal(env.obs, keep[0]) and torch.equal(env.reward, keep[1]) and torch.equal(env.done, keep[2]) and torch.equal(env.terms, keep[3])
