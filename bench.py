@@ -390,6 +390,7 @@ def run_ours(args):
                           "ms_per_step": 1e3 * s2, "timed_steps": min(K, 100) * r2, "e2e": world * En * Ke2 / te2,
                           "fp32_frac": frac, "hbm_gbs": alg_b * En / s2 / 1e9,
                           "resets_per_env_step": st2["episodes"] / max(1, st2["steps"]),
+                          "solver_budget_binds_per_env_step": st2.get("contact_overflow", 0) / max(1, st2["steps"]),
                           "mean_episode_len": st2["length_sum"] / max(1, st2["episodes"])})
             del w2, b2
 
@@ -429,7 +430,8 @@ def run_ours(args):
             "clocks": clocks,
             "episodes": {"finished": stats["episodes"], "mean_len": stats["length_sum"] / max(1, stats["episodes"]),
                          "mean_return": stats["return_sum"] / max(1, stats["episodes"]),
-                         "resets_per_env_step": stats["episodes"] / max(1, stats["steps"])},
+                         "resets_per_env_step": stats["episodes"] / max(1, stats["steps"]),
+                         "solver_budget_binds_per_env_step": stats.get("contact_overflow", 0) / max(1, stats["steps"])},
             "configs": extra,
         }
         if cpu is not None:

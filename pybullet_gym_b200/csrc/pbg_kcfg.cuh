@@ -27,10 +27,14 @@ using CfgAntMJ = KCfg<9, 8, 1, 8, 6, 16, 25, 0, 4, 8, 111, PBG_ANT_WARPS, PBG_AN
 using CfgHumanoidMJ = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 376, 14, 1, 0, 17, TopoHumanoid, 40>;
 // The humanoid kinds run 14 envs (warps) per SM -- 2048 envs are one wave of 147 CTAs -- which needs <= 16.2 KB of shared memory
 // per env: a row budget of 40 (17 possible limit rows + 12 x 3 contact rows would be 53; random-policy rollouts peak at 26 rows,
-// the robot lying on the ground in FlagrunHarder reaches 42 and keeps the full 53 with 7 envs per SM).
+// the robot lying on the ground in FlagrunHarder reaches 42: that kind has its own budget below).
 using CfgHumanoid = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 14, 1, 0, 17, TopoHumanoid, 40>;
 // HumanoidFlagrunHarder: the humanoid + the cube (one more free body, 8 corner candidates, 17 geom-vs-cube pairs)
-using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 7, 1, 17, 17, TopoHumanoid>;
+// FlagrunHarder (the humanoid + the cube: 29 dofs, 8 corner candidates, 17 geom-vs-cube pairs) also runs 14 envs per SM: a 36-row
+// budget (a robot lying on the ground reaches 42 rows; P(rows > 36) = 0.24 % of the random-policy env steps, the shallowest
+// contacts are dropped then and pbg_episode_stats.contact_overflow counts it) and L / Y rows without the 4-float padding
+// (some bank conflicts on the lane-strided row stores) bring the env block to 16.0 KB.
+using CfgHarder = KCfg<18, 17, 1, 17, 12, 32, 30, 66, 2, 17, 44, 14, 1, 17, 17, TopoHumanoid, 36, 0, 0, 0>;
 
 template <class C>
 static void launch_cfg(const DevModel *m, const StepBuffers &b, const LaunchArgs &la, cudaStream_t s) {

@@ -68,7 +68,7 @@ struct TopoHumanoid {   // base 0-5, abdomen 6-8, right leg 9-12, left leg 13-16
 // XP_ > 0: the world also holds HumanoidFlagrunHarder's cube (rs/robot_locomotors.py:236-266), a second free
 // body that is the last body / the last six dofs / the last eight ground candidates / the last XP_ pairs.
 template <int NB_, int NJ_, int FLOATING_, int NLIM_, int MAXC_, int LPE_, int NCAND_, int NPAIR_, int NFEET_,
-          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_, class TOPO_ = TopoDense, int MAXROWS_ = 0, int TORS_ = 0, int Q0ID_ = 0>
+          int NACT_, int OBS_, int WARPS_, int MIN_BLOCKS_, int XP_ = 0, int NNOISE_ = NACT_, class TOPO_ = TopoDense, int MAXROWS_ = 0, int TORS_ = 0, int Q0ID_ = 0, int LSTPAD_ = 4>
 struct KCfg {
     static constexpr int NNOISE = NNOISE_;                     // injectable reset draws per env (pbg_reset_with)
     static constexpr int HASX = XP_ > 0 ? 1 : 0;
@@ -103,7 +103,7 @@ struct KCfg {
     static_assert(!TORS || NPAIR_ + XP_ == 0, "torsional rows are implemented for ground contacts only");
     static constexpr int MAXRP = MAXR > 0 ? MAXR : 1;
     static constexpr int NDP = (ND + 3) / 4 * 4;
-    static constexpr int LST = NDP + 4;            // row stride of L / Y: float4 rows, conflict-free
+    static constexpr int LST = NDP + LSTPAD_;      // row stride of L / Y: float4 rows; + 4 makes lane-strided row accesses conflict-free
     static constexpr int EPW = 32 / LPE;
     // One CTA per SM: all warps of an SM run the same phase of the same substep at about the same
     // time (block barrier per substep), so the long straight-line phases are fetched once per SM
@@ -124,7 +124,7 @@ struct KCfg {
     static constexpr int CTS = 16;                 // contact record: bodyA bodyB slot pad pA3 pB3 n3 dist mu pad
     static constexpr int sST = 0;
     static constexpr int sL = (sST + SSTRIDE + 3) / 4 * 4;
-    static constexpr int sINV = sL + (ND + 1) * LST;
+    static constexpr int sINV = sL + ND * LST;
     static constexpr int sY = (sINV + NDP + 3) / 4 * 4;
     static constexpr int YSZ = MAXRP * LST > 72 ? MAXRP * LST : 72;
     static constexpr int sOUT = sY;                // staged outputs: obs[64] reward terms[5]

@@ -12,7 +12,7 @@ from typing import Dict, Tuple
 import torch
 import torch.distributed as dist
 
-STAT_KEYS = ("return_sum", "length_sum", "episodes", "truncated", "nonfinite", "steps")
+STAT_KEYS = ("return_sum", "length_sum", "episodes", "truncated", "nonfinite", "steps", "contact_overflow")
 
 
 def rank_world() -> Tuple[int, int, int]:
