@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PBG_VERSION 102
+#define PBG_VERSION 103
 
 typedef enum {
     PBG_OK = 0,
@@ -190,6 +190,12 @@ int pbg_step(pbg_handle *h, const float *actions_dev, float *obs_dev, float *rew
 int pbg_set_policy(pbg_handle *h, int32_t h1, int32_t h2, const float *w1, const float *b1, const float *w2, const float *b2,
                    const float *w3, const float *b3);
 int pbg_rollout_policy(pbg_handle *h, int32_t nsteps, float *obs_dev, float *reward_sum_dev, uint8_t *done_any_dev, void *stream);
+/* Evaluates the fused policy on the tensor cores: the envs of a CTA form the rows of one small GEMM per layer (mma.sync
+ * m16n8k8, TF32 inputs rounded to nearest, FP32 accumulation), every weight is read once per CTA instead of once per warp.
+ * Opt-in because TF32 keeps 10 mantissa bits of the inputs: actions differ from the default FP32 evaluation by ~1e-3
+ * (absolute, for O(1) activations), so a rollout is no longer bit-identical to single steps driven by an FP32 policy outside.
+ * Takes effect at the next pbg_rollout_policy; 0 (default) = scalar FP32. */
+int pbg_set_policy_tensor_cores(pbg_handle *h, int32_t enabled);
 
 /* Host-buffer variant (the reference-facing call: numpy in, numpy out).  Copies actions H2D,
  * steps, copies obs/reward/done D2H and synchronises.  Buffers should be pinned for full speed. */

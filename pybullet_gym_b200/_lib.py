@@ -77,7 +77,7 @@ class PbgEpisodeStats(C.Structure):
                 ("truncated", C.c_int64), ("nonfinite", C.c_int64), ("steps", C.c_int64), ("contact_overflow", C.c_int64)]
 
 
-PBG_VERSION = 102          # include/pbg.h
+PBG_VERSION = 103          # include/pbg.h
 TASK_VIEW_DIM = 12         # PBG_TASK_VIEW_DIM
 TASK_VIEW_FIELDS = ("potential", "walk_target_x", "walk_target_y", "flag_timeout", "frame", "on_ground_frame_counter",
                     "episode_steps", "episode_return", "initial_z", "episode", "attacks", "flag_moves")
@@ -158,6 +158,7 @@ def lib():
     L.pbg_set_auto_reset.argtypes = [vp, C.c_int32]
     L.pbg_set_policy.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
     L.pbg_rollout_policy.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
+    L.pbg_set_policy_tensor_cores.argtypes = [vp, C.c_int32]
     L.pbg_set_zero_copy.argtypes = [vp, C.c_int32]
     L.pbg_last_host_path.argtypes = [vp]
     L.pbg_get_state.argtypes = [vp, vp, vp]
@@ -188,7 +189,7 @@ def lib():
 
 EXPORTS = ["pbg_version", "pbg_create", "pbg_destroy", "pbg_last_error", "pbg_num_envs", "pbg_obs_dim",
            "pbg_action_dim", "pbg_state_dim", "pbg_noise_dim", "pbg_reset", "pbg_reset_with", "pbg_step", "pbg_step_host",
-           "pbg_set_auto_reset", "pbg_set_zero_copy", "pbg_last_host_path", "pbg_set_policy", "pbg_rollout_policy", "pbg_get_state", "pbg_set_state", "pbg_physics_step", "pbg_physics_step_counts",
+           "pbg_set_auto_reset", "pbg_set_zero_copy", "pbg_last_host_path", "pbg_set_policy", "pbg_rollout_policy", "pbg_set_policy_tensor_cores", "pbg_get_state", "pbg_set_state", "pbg_physics_step", "pbg_physics_step_counts",
            "pbg_max_contacts", "pbg_max_rows", "pbg_measure_fp32_peak", "pbg_observe", "pbg_get_feet_contact", "pbg_stats", "pbg_launch_count",
            "pbg_snapshot_bytes", "pbg_snapshot", "pbg_restore", "pbg_set_seed", "pbg_get_task_view", "pbg_num_contact_slots",
            "pbg_enable_contact_export", "pbg_get_contact_candidates"]

@@ -49,6 +49,7 @@ struct pbg_handle {
     int debug_env = 0;
     float *policy_buf = nullptr;   // fused-policy weights (pbg_set_policy)
     PolicyDev policy{};
+    int policy_tc = 0;          // pbg_set_policy_tensor_cores
     int zero_copy = 1;          // pbg_step_host: let the kernel read / write mapped pinned host buffers directly
     int last_host_path = 0;     // 1: zero-copy, 2: staged copies
     int64_t launches = 0;
@@ -525,7 +526,14 @@ int pbg_set_policy(pbg_handle *h, int32_t h1, int32_t h2, const float *w1, const
         CUDA_TRY(h, cudaMemcpy(p, src[i], cnt[i] * sizeof(float), cudaMemcpyHostToDevice));
         dst[i] = p; p += cnt[i];
     }
-    h->policy = PolicyDev{dst[0], dst[1], dst[2], dst[3], dst[4], dst[5], h1, h2};
+    h->policy = PolicyDev{dst[0], dst[1], dst[2], dst[3], dst[4], dst[5], h1, h2, h->policy_tc};
+    return PBG_OK;
+}
+
+int pbg_set_policy_tensor_cores(pbg_handle *h, int32_t enabled) {
+    if (!h) return PBG_ERR_INVALID;
+    h->policy_tc = enabled ? 1 : 0;
+    h->policy.tc = h->policy_tc;
     return PBG_OK;
 }
 

@@ -1524,6 +1524,77 @@ struct Env {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Fused policy on the tensor cores (pbg_set_policy_tensor_cores).  The scalar MLP in Env::policy_actions evaluates one env per
+// lane group and streams the whole weight set through every warp: 15 % (Ant, 28-128-64-8) to 20 % (Humanoid, 44-256-128-17) of a
+// fused step.  Here the CTA's envs form the rows of one small GEMM per layer, Y[EPB x N] = act(X[EPB x K] W[K x N] + b):
+// work items are 16 x 8 output tiles (mma.sync.m16n8k8, TF32 inputs rounded to nearest, FP32 accumulation) dealt round-robin to
+// the warps, A fragments come from the env blocks in shared memory (row = env slot, stride ENV_FLOATS), B fragments straight
+// from the row-major weights in global memory (each weight is read once per CTA instead of once per warp).  TF32 keeps 10
+// mantissa bits of the inputs: actions differ from the FP32 path by ~1e-3, which is why this is opt-in and the FP32 path stays
+// the one that makes K fused steps bit-identical to K single steps with a torch FP32 policy.
+__device__ __forceinline__ unsigned f2tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// one layer for all env slots of the CTA; xin / yout point at slot 0's vectors, slot r's are r * ENV_FLOATS further
+template <class C>
+__device__ __forceinline__ void mlp_layer_tc(const float *__restrict__ W, const float *__restrict__ bias, const int K, const int N,
+                                             const bool relu, const float *xin, float *yout) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int MT = (C::EPB + 15) / 16;
+    const int NT = (N + 7) >> 3;
+    for (int item = warp; item < MT * NT; item += C::WARPS) {
+        const int mt = item % MT, nt = item / MT;
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        const bool v0 = r0 < C::EPB, v1 = r1 < C::EPB;
+        const float *x0 = xin + (v0 ? r0 : 0) * C::ENV_FLOATS, *x1 = xin + (v1 ? r1 : 0) * C::ENV_FLOATS;
+        const int n = nt * 8 + g;
+        const bool nv = n < N;
+        const float *wn = W + (nv ? n : 0);
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int k0 = 0; k0 < K; k0 += 8) {
+            const int ka = k0 + t, kb = ka + 4;
+            const bool ia = ka < K, ib = kb < K;
+            unsigned a[4], b[2];
+            a[0] = f2tf32(v0 && ia ? x0[ka] : 0.f); a[1] = f2tf32(v1 && ia ? x1[ka] : 0.f);
+            a[2] = f2tf32(v0 && ib ? x0[kb] : 0.f); a[3] = f2tf32(v1 && ib ? x1[kb] : 0.f);
+            b[0] = f2tf32(nv && ia ? __ldg(wn + ka * N) : 0.f); b[1] = f2tf32(nv && ib ? __ldg(wn + kb * N) : 0.f);
+            mma_tf32_16x8x8(c, a, b);
+        }
+        float *y0 = yout + (v0 ? r0 : 0) * C::ENV_FLOATS, *y1 = yout + (v1 ? r1 : 0) * C::ENV_FLOATS;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = nt * 8 + 2 * t + j;
+            if (col < N) {
+                const float bj = __ldg(bias + col);
+                float u0 = c[j] + bj, u1 = c[2 + j] + bj;
+                if (relu) { u0 = fmaxf(u0, 0.f); u1 = fmaxf(u1, 0.f); }
+                if (v0) y0[col] = u0;
+                if (v1) y1[col] = u1;
+            }
+        }
+    }
+}
+// observation (staged in every slot's sOUT) -> actions (every slot's sACTN); every thread of the CTA takes part
+template <class C>
+__device__ void policy_actions_tc(const PolicyDev &P, float *smem) {
+    __syncthreads();                                     // every warp's observation is staged
+    mlp_layer_tc<C>(P.w1, P.b1, C::OBSNZ, P.h1, true, smem + C::sOUT, smem + C::sU);
+    __syncthreads();
+    mlp_layer_tc<C>(P.w2, P.b2, P.h1, P.h2, true, smem + C::sU, smem + C::sU + P.h1);
+    __syncthreads();
+    mlp_layer_tc<C>(P.w3, P.b3, P.h2, C::NACT, false, smem + C::sU + P.h1, smem + C::sACTN);
+    __syncthreads();
+}
+
 // POLICY = true is the multi-step fused-policy instantiation (MODE_POLICY only); keeping it a separate kernel leaves the
 // single-step kernel's register allocation untouched.
 template <class C, bool POLICY = false>
@@ -1635,7 +1706,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
   for (int step = 0; step < nsteps; ++step) {
     const bool last_step = step == nsteps - 1;
     // hidden activations go to the kinematics / Delassus scratch, which is dead between the task phase and the next sub-step
-    if (policy_mode) e.policy_actions(B.policy, so_obs, e.sm + C::sU, e.sm + C::sACTN);
+    if (policy_mode) {
+        if (B.policy.tc) policy_actions_tc<C>(B.policy, smem);
+        else e.policy_actions(B.policy, so_obs, e.sm + C::sU, e.sm + C::sACTN);
+    }
     if (mode_eff == MODE_STEP || mode == MODE_PHYSICS) {
         // apply_action: tau = power * power_coef * clip(a, -1, 1) (rs/robot_locomotors.py:26-29),
         // plus the joint damping torque, both held for all substeps

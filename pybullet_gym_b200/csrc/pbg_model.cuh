@@ -67,6 +67,7 @@ enum {
 struct PolicyDev {
     const float *w1, *b1, *w2, *b2, *w3, *b3;
     int h1, h2;
+    int tc;     // 1: the CTA's envs go through the tensor cores together (mma.sync, TF32 inputs, FP32 accumulation)
 };
 
 struct StepBuffers {

@@ -31,7 +31,7 @@ def reduce_stats(stats: Dict[str, float], device="cpu") -> Dict[str, float]:
     """Sum the per-rank episode statistics over all ranks (no-op without an initialised process group)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return dict(stats)
-    t = torch.tensor([float(stats[k]) for k in STAT_KEYS], dtype=torch.float64, device=device)
+    t = torch.tensor([float(stats.get(k, 0)) for k in STAT_KEYS], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return {k: float(v) for k, v in zip(STAT_KEYS, t.tolist())}
 

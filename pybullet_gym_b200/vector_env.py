@@ -192,6 +192,11 @@ class VectorEnv:
         _lib.check(rc, self._h)
         return self.obs, self.reward, self.done
 
+    def set_policy_tensor_cores(self, enabled: bool):
+        """Fused policy through mma.sync (TF32 inputs, FP32 accumulation) instead of scalar FP32: faster, actions differ by
+        ~1e-3 (pbg_set_policy_tensor_cores)."""
+        _lib.check(self._L.pbg_set_policy_tensor_cores(self._h, int(enabled)), self._h)
+
     def set_zero_copy(self, enabled: bool):
         """pbg_step_host transport: kernel reads / writes pinned host buffers directly (default) or staged copies."""
         _lib.check(self._L.pbg_set_zero_copy(self._h, int(enabled)), self._h)

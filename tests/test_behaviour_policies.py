@@ -139,13 +139,50 @@ def test_fused_policy_rollout_matches_stepwise_policy():
 
 
 @pytest.mark.gpu
-def test_hopper_policy_whole_episode_in_one_launch():
+@pytest.mark.parametrize("name,n", [("Ant", 128), ("Ant", 37), ("Humanoid", 100), ("Hopper", 64), ("InvertedPendulum", 50)])
+def test_tensor_core_policy_is_close_to_the_fp32_policy(name, n):
+    """pbg_set_policy_tensor_cores: the CTA's envs go through mma.sync (TF32 inputs, FP32 accumulation) together.  From an
+    identical state one fused step lands within TF32 round-off of the FP32 policy's step (actions differ by ~1e-3, which the
+    contact dynamics amplify a little), for full and ragged CTAs (37 = one CTA of 28 + 9 envs; 100 humanoids = 7 CTAs of 14 + 2),
+    and stays bit-identical between one launch of K steps and K launches."""
+    torch = pytest.importorskip("torch")
+    from pybullet_gym_b200.vector_env import VectorEnv
+    w = dict(np.load(os.path.join(GOLD, "policy_%s.npz" % name)))
+    args = [w[k] for k in ("dense1_w", "dense1_b", "dense2_w", "dense2_b", "final_w", "final_b")]
+    envs = [VectorEnv(name + "PyBulletEnv-v0", n, device="cuda:0", seed=5, auto_reset=True) for _ in range(3)]
+    for e in envs:
+        e.set_policy(*args, obs_shift=w.get("obs_shift"))
+        e.reset()
+    f32, tc, tc2 = envs
+    for e in envs:
+        e.rollout_policy(3)                                           # off the reset pose, all three bit-identical so far
+    assert torch.equal(f32.get_state(), tc.get_state()) and torch.equal(f32.obs, tc2.obs)
+    tc.set_policy_tensor_cores(True); tc2.set_policy_tensor_cores(True)
+    s0 = f32.get_state().clone()
+    of, rf, df = f32.rollout_policy(1)
+    ot, rt, dt = tc.rollout_policy(1)
+    tc2.rollout_policy(1)
+    same = df == dt
+    assert same.float().mean().item() > 0.97
+    err = (of - ot).abs().max(dim=1).values[same]
+    assert torch.isfinite(ot).all() and err.median().item() < 2e-3 and err.max().item() < 0.25, (err.median().item(), err.max().item())
+    assert not torch.equal(s0, tc.get_state())                       # it did step
+    oa, ra, da = tc.rollout_policy(12)
+    for t in range(12):
+        ob_, rb, db = tc2.rollout_policy(1)
+    assert torch.equal(oa, ob_)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_hopper_policy_whole_episode_in_one_launch(tensor_cores):
     torch = pytest.importorskip("torch")
     from pybullet_gym_b200.vector_env import VectorEnv
     w = dict(np.load(os.path.join(GOLD, "policy_Hopper.npz")))
     n = 256
     env = VectorEnv("HopperPyBulletEnv-v0", n, device="cuda:0", seed=3, auto_reset=True)
     env.set_policy(*[w[k] for k in ("dense1_w", "dense1_b", "dense2_w", "dense2_b", "final_w", "final_b")])
+    env.set_policy_tensor_cores(tensor_cores)
     env.reset()
     obs, ret, done = env.rollout_policy(1000)
     torch.cuda.synchronize()
@@ -156,7 +193,8 @@ def test_hopper_policy_whole_episode_in_one_launch():
 
 
 @pytest.mark.gpu
-def test_humanoid_policy_fused_rollout():
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_humanoid_policy_fused_rollout(tensor_cores):
     """The Humanoid policy (with its demo's observation offset folded into the first bias) evaluated inside the step kernel:
     500 steps in one launch, most humanoids are still walking."""
     torch = pytest.importorskip("torch")
@@ -165,6 +203,7 @@ def test_humanoid_policy_fused_rollout():
     n = 256
     env = VectorEnv("HumanoidPyBulletEnv-v0", n, device="cuda:0", seed=3, auto_reset=True)
     env.set_policy(*[w[k] for k in ("dense1_w", "dense1_b", "dense2_w", "dense2_b", "final_w", "final_b")], obs_shift=w["obs_shift"])
+    env.set_policy_tensor_cores(tensor_cores)
     env.reset()
     obs, ret, done = env.rollout_policy(500)
     assert ret.median().item() > 1200.0, ret.median().item()         # ~3.4 per step while walking

@@ -22,7 +22,7 @@ def _worker(rank, world, port, q):
     r, w, l = sharding.rank_world()
     off, n = sharding.shard(r, w, 4096)
     stats = {"return_sum": 10.0 * (rank + 1), "length_sum": 100.0 * (rank + 1), "episodes": 3 + rank, "truncated": rank,
-             "nonfinite": 0, "steps": n * 5}
+             "nonfinite": 0, "steps": n * 5, "contact_overflow": 2 * rank}
     red = sharding.reduce_stats(stats)
     tmax = sharding.max_over_ranks(1.0 + rank)
     dist.barrier()
@@ -44,7 +44,7 @@ def test_two_rank_sharding_and_reductions():
     (r0, off0, n0, red0, t0), (r1, off1, n1, red1, t1) = out
     assert (off0, n0) == (0, 4096) and (off1, n1) == (4096, 4096)        # disjoint, contiguous env slices
     assert red0 == red1
-    assert red0["return_sum"] == 30.0 and red0["episodes"] == 7 and red0["steps"] == 2 * 4096 * 5
+    assert red0["return_sum"] == 30.0 and red0["episodes"] == 7 and red0["steps"] == 2 * 4096 * 5 and red0["contact_overflow"] == 2
     assert t0 == t1 == 2.0
 
 

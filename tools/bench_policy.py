@@ -14,14 +14,17 @@ env.reset()
 env.rollout_policy(200); torch.cuda.synchronize()          # into the policy's stationary regime (auto-reset on)
 print("%s x %d, policy %d-%d-%d-%d" % (name, E, w["dense1_w"].shape[0], w["dense1_w"].shape[1], w["dense2_w"].shape[1], w["final_w"].shape[1]))
 fused = {}
-for K in (1, 10, 50):
-    reps = max(1, 300 // K)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps): env.rollout_policy(K)
-    b.record(); torch.cuda.synchronize()
-    fused[K] = a.elapsed_time(b) / (K * reps)
-    print("fused policy K=%d: %.3e env-steps/s (%.4f ms/step)" % (K, E / (fused[K] * 1e-3), fused[K]))
+for tc in (True, False):
+  env.set_policy_tensor_cores(tc)
+  print("policy on %s" % ("tensor cores (mma.sync TF32)" if tc else "scalar FP32"))
+  for K in (1, 10, 50):
+      reps = max(1, 300 // K)
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      for _ in range(reps): env.rollout_policy(K)
+      b.record(); torch.cuda.synchronize()
+      fused[K] = a.elapsed_time(b) / (K * reps)
+      print("fused policy K=%d: %.3e env-steps/s (%.4f ms/step)" % (K, E / (fused[K] * 1e-3), fused[K]))
 wt = {k: torch.tensor(v, device="cuda") for k, v in w.items()}
 shift = wt["obs_shift"] if "obs_shift" in wt else 0.0
 ob = env.obs
@@ -38,5 +41,5 @@ b.record(); torch.cuda.synchronize()
 t_total = a.elapsed_time(b) / 300
 t_step = sum(x.elapsed_time(y) for x, y in ev) / 300
 print("torch MLP + pbg_step: %.3e env-steps/s (%.4f ms/step), of which the step kernel %.4f ms" % (E / (t_total * 1e-3), t_total, t_step))
-print("MLP inside the fused kernel: %.4f ms/step = %.1f %% of a fused step (K=50); outside (3 cuBLAS launches + elementwise): %.4f ms = %.1f %%"
+print("MLP inside the fused kernel: %.4f ms/step = %.1f %% of a fused step (K=50, scalar FP32); outside (3 cuBLAS launches + elementwise): %.4f ms = %.1f %%"
       % (fused[50] - t_step, 100 * (fused[50] - t_step) / fused[50], t_total - t_step, 100 * (t_total - t_step) / t_total))
