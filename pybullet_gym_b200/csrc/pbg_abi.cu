@@ -122,6 +122,15 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
             d->anchor_p[b][i] = (float)pm->anchor_p[3 * b + i];
             d->com_off[b][i] = (float)pm->com_off[3 * b + i];
         }
+        if (k.q0id == 2) {
+            // planar kinds (KCfg::PLANAR): hinges about +-y, slides in the xz plane, unit axes, fixed base
+            const double *ax = pm->axis + 3 * b;
+            const bool ok = pm->jtype[b] == PBG_JT_REVOLUTE
+                                ? (std::fabs(ax[0]) < 1e-12 && std::fabs(ax[2]) < 1e-12 && std::fabs(std::fabs(ax[1]) - 1.0) < 1e-12)
+                                : (pm->jtype[b] == PBG_JT_PRISMATIC && std::fabs(ax[1]) < 1e-12 &&
+                                   std::fabs(ax[0] * ax[0] + ax[2] * ax[2] - 1.0) < 1e-12);
+            if (!ok || pm->floating) return "this env kind's kernel assumes a planar robot: fixed base, unit hinge axes along +-y, unit slide axes in the xz plane";
+        }
         {
             // Bullet keeps a non-unit MJCF joint axis as written: rotation about its direction, motion subspace with its length
             const double *ax = pm->axis + 3 * b;

@@ -11,13 +11,13 @@ using CfgPendulum = KCfg<2, 2, 0, 1, 0, 16, 0, 0, 0, 1, 5, 4, 4, 0, 1, TopoDense
 using CfgDoublePendulum = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 9, 4, 4, 0, 2, TopoDense, 0, 0, 1>;
 using CfgDoublePendulumMJ = KCfg<3, 3, 0, 1, 0, 16, 0, 0, 0, 1, 11, 4, 4, 0, 2, TopoDense, 0, 0, 1>;
 using CfgReacher = KCfg<4, 4, 0, 3, 0, 16, 0, 0, 0, 2, 9, 4, 4, 0, 4, TopoReacher, 0, 0, 1>;
-using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15, 14, 1, 0, 3, TopoDense, 0, 0, 1>;
-using CfgHopperMJ = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 11, 14, 1, 0, 6, TopoDense, 0, 0, 1>;
-using CfgWalkerMJ = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 17, 14, 1, 0, 9, TopoBiped2D, 0, 0, 1>;
-using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1, 0, 6, TopoBiped2D, 0, 0, 1>;
-using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1, 0, 6, TopoBiped2D, 0, 0, 1>;
+using CfgHopper = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 15, 14, 1, 0, 3, TopoDense, 0, 0, 2>;
+using CfgHopperMJ = KCfg<6, 6, 0, 3, 6, 16, 8, 0, 1, 3, 11, 14, 1, 0, 6, TopoDense, 0, 0, 2>;
+using CfgWalkerMJ = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 17, 14, 1, 0, 9, TopoBiped2D, 0, 0, 2>;
+using CfgWalker = KCfg<9, 9, 0, 6, 6, 16, 14, 0, 2, 6, 22, 14, 1, 0, 6, TopoBiped2D, 0, 0, 2>;
+using CfgCheetah = KCfg<9, 9, 0, 6, 6, 16, 16, 0, 6, 6, 26, 14, 1, 0, 6, TopoBiped2D, 0, 0, 2>;
 // HalfCheetahMuJoCoEnv: the cheetah with torsional friction rows (6 rows per contact: up to 42 rows -> one env per warp)
-using CfgCheetahMJ = KCfg<9, 9, 0, 6, 6, 32, 16, 0, 6, 6, 17, 14, 1, 0, 9, TopoBiped2D, 0, 1, 1>;
+using CfgCheetahMJ = KCfg<9, 9, 0, 6, 6, 32, 16, 0, 6, 6, 17, 14, 1, 0, 9, TopoBiped2D, 0, 1, 2>;
 #ifndef PBG_ANT_WARPS
 #define PBG_ANT_WARPS 14
 #define PBG_ANT_BLOCKS 1
@@ -61,7 +61,7 @@ static void read_phases(unsigned long long *out32, int reset) {
 template <class C>
 static KernelInfo info_of() {
     KernelInfo ki = KernelInfo{C::NB, C::NJ, C::FLOATING, C::NLIM, C::MAXC, C::NCAND, C::NPAIR, C::NFEET, C::NACT, C::OBS,
-                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::MAXR, C::TORS, C::Q0ID, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases, {0}};
+                      C::SSTRIDE, C::CANON, C::EPB, C::THREADS, C::HASX, C::oF, C::NNOISE, C::HIDCAP, C::oT, C::NSLOT, C::MAXR, C::TORS, C::Q0RAW, C::SMEM_BYTES, &launch_cfg<C>, &prepare_cfg<C>, &read_phases, {0}};
     for (int k = 0; k < C::ND; ++k) ki.low[k] = C::low(k);
     return ki;
 }

@@ -93,6 +93,13 @@ struct KCfg {
     // Q0ID_: every body's rest rotation relative to its parent is the identity (true for all the MJCF robots but the Humanoid):
     // forward kinematics skips that matrix product and the lanes do not carry the nine constants (pbg_create checks the model)
     static constexpr int Q0ID = Q0ID_ ? 1 : 0;
+    // Q0ID_ == 2: the robot is also PLANAR -- fixed base, every hinge about +-y with a unit axis, every slide axis a unit vector in
+    // the xz plane (Hopper, Walker2D, HalfCheetah; pbg_create checks the model).  Orientations are then angles that add along the
+    // tree, angular velocities stay parallel to y, and forward kinematics becomes one lane-parallel pass plus two sweeps of
+    // parent-to-child additions (fk_planar) instead of a full 3-D frame composition per tree level.
+    static constexpr int PLANAR = Q0ID_ == 2 ? 1 : 0;
+    static constexpr int Q0RAW = Q0ID_;
+    static_assert(!PLANAR || (FLOATING_ == 0 && XP_ == 0), "planar kinds have a fixed base and no cube");
     static constexpr bool FKREG = true;       // link-frame constants of forward kinematics stay in registers (read at every tree level)
     // kinds that are not register-bound (7 warps per SM: 255 registers per thread) also keep a body's kinematics of the pass in
     // registers between forward kinematics and the wrench phase instead of re-reading its kin() record
@@ -271,7 +278,73 @@ struct Env {
     // ---------------------------------------------------------------- forward kinematics
     // lane = body, one tree level per round.  bias=true also propagates the velocity-product
     // accelerations needed for the bias wrench.
+    // Planar robots (C::PLANAR): body b's orientation is Ry(theta_b) with theta_b the signed sum of the hinge angles above it, its
+    // angular velocity (0, Omega_b, 0) likewise, so every lane first gets (theta, Omega) by one sweep of parent-to-child additions
+    // (two shuffles per tree level), then computes ITS segment -- parent COM to anchor to own COM -- and that segment's
+    // contributions to position, velocity and velocity-product acceleration on its own, and a second sweep adds the parents'
+    // totals (nine shuffles per level).  Same quantities, in the same kin() records, as the general routine below: with all
+    // axes parallel the angular velocity-product acceleration vanishes and w x (w x r) = -Omega^2 r_perp.
+    __device__ void fk_planar(bool bias) {
+        const float *S = st();
+        const int maxdepth = m->maxdepth;
+        const bool act = gl < C::NB;
+        const bool hinge = act && bjtype == 1;
+        const float q = act ? S[C::oQ + bdof] : 0.f, qd = act ? S[C::oU + bdof] : 0.f;
+        const V3 ax = ld3(axis), cOff = ld3(com_off), aP = ld3(anchor_p);
+        const int psrc = bparent < 0 ? 0 : bparent;
+        float th = hinge ? ax.y * q : 0.f, om = hinge ? ax.y * qd : 0.f, omp = 0.f;
+        for (int lvl = 1; lvl <= maxdepth; ++lvl) {
+            const float t = shfl(th, psrc), o = shfl(om, psrc);
+            if (bdepth == lvl) { th += t; om += o; omp = o; }
+        }
+        float s, c;
+        sincosf(th, &s, &c);
+        float sp = shfl(s, psrc), cp = shfl(c, psrc);
+        if (bparent < 0) { sp = 0.f; cp = 1.f; }
+        // Ry(theta) v = (c vx + s vz, vy, -s vx + c vz)
+        const V3 e = mk(cp * aP.x + sp * aP.z, aP.y, -sp * aP.x + cp * aP.z);              // parent COM -> joint anchor
+        V3 zw, f, dx, dv, da = mk(0.f, 0.f, 0.f);
+        if (hinge) {
+            zw = mk(0.f, ax.y, 0.f);
+            f = mk(c * cOff.x + s * cOff.z, cOff.y, -s * cOff.x + c * cOff.z);            // anchor -> own COM
+            dx = e + f;
+            dv = mk(omp * e.z + om * f.z, 0.f, -omp * e.x - om * f.x);                     // w_p x e + w x f
+            if (bias) da = mk(-omp * omp * e.x - om * om * f.x, 0.f, -omp * omp * e.z - om * om * f.z);
+        } else {
+            zw = mk(cp * ax.x + sp * ax.z, ax.y, -sp * ax.x + cp * ax.z);                  // slide: the link keeps its parent's orientation
+            f = mk(cp * cOff.x + sp * cOff.z, cOff.y, -sp * cOff.x + cp * cOff.z);
+            dx = e + q * zw + f;
+            dv = mk(omp * dx.z, 0.f, -omp * dx.x) + qd * zw;                                // w_p x (x - x_p) + qd z
+            if (bias) da = mk(-omp * omp * dx.x, 0.f, -omp * omp * dx.z) + (2.f * qd * omp) * mk(zw.z, 0.f, -zw.x);
+        }
+        V3 x = dx, v = dv, a = da;
+        for (int lvl = 1; lvl <= maxdepth; ++lvl) {
+            const V3 px = mk(shfl(x.x, psrc), shfl(x.y, psrc), shfl(x.z, psrc));
+            const V3 pv = mk(shfl(v.x, psrc), shfl(v.y, psrc), shfl(v.z, psrc));
+            if (bdepth == lvl) { x = x + px; v = v + pv; }
+            if (bias) {
+                const V3 pa = mk(shfl(a.x, psrc), shfl(a.y, psrc), shfl(a.z, psrc));
+                if (bdepth == lvl) a = a + pa;
+            }
+        }
+        if (act) {
+            const V3 A = hinge ? x - f : x - f - q * zw;
+            const V3 w = mk(0.f, om, 0.f);
+            float *k = kin(gl);
+            k[0] = c; k[1] = 0.f; k[2] = s; k[3] = 0.f; k[4] = 1.f; k[5] = 0.f; k[6] = -s; k[7] = 0.f; k[8] = c;
+            st3(k + 9, x); st3(k + 12, w); st3(k + 15, v);
+            if (bias) { st3(k + 18, mk(0.f, 0.f, 0.f)); st3(k + 21, a); }
+            st3(k + 24, zw); st3(k + 27, A);
+            if (C::KINREG) {
+                kR[0] = c; kR[1] = 0.f; kR[2] = s; kR[3] = 0.f; kR[4] = 1.f; kR[5] = 0.f; kR[6] = -s; kR[7] = 0.f; kR[8] = c;
+                kx = x; kw = w; kv = v; kal = mk(0.f, 0.f, 0.f); ka = a;
+            }
+        }
+        __syncwarp();
+    }
+
     __device__ void fk(bool bias) {
+        if (C::PLANAR) { fk_planar(bias); return; }
         const float *S = st();
         const int maxdepth = m->maxdepth;
         for (int lvl = 0; lvl <= maxdepth; ++lvl) {
