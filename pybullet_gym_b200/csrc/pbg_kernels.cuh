@@ -343,8 +343,148 @@ struct Env {
         __syncwarp();
     }
 
+    // General trees: the same idea as fk_planar in 3-D.  Only the orientation is a genuinely multiplicative recursion,
+    // R_b = R_p (Q0_b Rj(q_b)); everything else -- position, angular velocity, linear velocity, and the two velocity-product
+    // accelerations -- is a SUM along the chain of per-body increments that each lane can compute on its own once the previous
+    // quantity is known for itself and its parent:
+    //     dx = e + f (+ q z)                      e = R_p anchor, f = R_b com   (parent COM -> anchor -> own COM)
+    //     w  = w_p + qd z                         z = |axis| R_b axis
+    //     dv = w_p x e + w x f                    (slide: w_p x dx + qd z)
+    //     al = al_p + qd (w_p x z)
+    //     da = al_p x e + w_p x (w_p x e) + al x f + w x (w x f)        (slide: al_p x dx + w_p x (w_p x dx) + 2 qd (w_p x z))
+    // So: every lane builds its local rotation at once (sincos, Rodrigues, rest rotation), one sweep over the tree levels
+    // multiplies the rotations down (9 shuffles + 27 FMAs per level), and three more sweeps of pure parent-to-child additions
+    // (6, 6 and 3 shuffles per level) carry (x, w), (v, al) and a, with the cross products done by all lanes in parallel in
+    // between.  The level-by-level routine this replaces ran the whole per-body computation once per tree level with the one to
+    // four lanes of that level active: 27 % of a Humanoid step (six levels).
+    __device__ void fk_tree(bool bias) {
+        const float *S = st();
+        const int maxdepth = m->maxdepth;
+        const bool act = gl < C::NB;
+        const int b = act ? gl : 0;
+        const bool is_cube = C::HASX && act && bjtype == 4;
+        const bool rootfree = act && (bjtype == 3 || is_cube);
+        const bool hinge = act && bjtype == 1;
+        const bool child = act && bparent >= 0;
+        const int psrc = bparent < 0 ? 0 : bparent;
+        float L[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+        float q = 0.f, qd = 0.f;
+        V3 X = mk(0.f, 0.f, 0.f), W = X, V = X;
+        const V3 ax = ld3(axis), cOff = ld3(com_off), aP = ld3(anchor_p);
+        if (rootfree) {
+            const float *P = is_cube ? S + C::oX : S;
+            const float *U = S + C::oU + (is_cube ? C::XD0 : 0);
+            quat2mat(P + 3, L);
+            X = ld3(P); W = ld3(U); V = ld3(U + 3);
+        } else if (act) {
+            q = S[C::oQ + bdof - 6 * C::FLOATING]; qd = S[C::oU + bdof];
+            float Rj[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+            if (hinge) {
+                float sn, cs;
+                sincosf(q, &sn, &cs);
+                const float t = 1.f - cs;
+                Rj[0] = cs + t * ax.x * ax.x; Rj[1] = t * ax.x * ax.y - sn * ax.z; Rj[2] = t * ax.x * ax.z + sn * ax.y;
+                Rj[3] = t * ax.x * ax.y + sn * ax.z; Rj[4] = cs + t * ax.y * ax.y; Rj[5] = t * ax.y * ax.z - sn * ax.x;
+                Rj[6] = t * ax.x * ax.z - sn * ax.y; Rj[7] = t * ax.y * ax.z + sn * ax.x; Rj[8] = cs + t * ax.z * ax.z;
+            }
+            if (C::Q0ID) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) L[i] = Rj[i];
+            } else {
+                const float *Q0 = m->q0m[b];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        L[3 * i + j] = Q0[3 * i] * Rj[j] + Q0[3 * i + 1] * Rj[3 + j] + Q0[3 * i + 2] * Rj[6 + j];
+            }
+        }
+        // sweep 1: orientations
+        float R[9], Rp[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = L[i];
+        for (int lvl = 1; lvl <= maxdepth; ++lvl) {
+            float T[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) T[i] = shfl(R[i], psrc);
+            if (bdepth == lvl) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rp[i] = T[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        R[3 * i + j] = T[3 * i] * L[j] + T[3 * i + 1] * L[3 + j] + T[3 * i + 2] * L[6 + j];
+            }
+        }
+        // segment vectors and the world joint axis (motion subspace: the MJCF axis as written -- Bullet does not normalise it)
+        V3 zw = mk(0.f, 0.f, 0.f), e = zw, f = zw, dx = zw;
+        if (act && !rootfree) {
+            zw = alen * mulR(R, ax);
+            e = mulR(Rp, aP);
+            f = mulR(R, cOff);
+            dx = hinge ? e + f : e + q * zw + f;
+            X = dx;
+            W = hinge ? qd * zw : mk(0.f, 0.f, 0.f);
+        }
+        // sweep 2: positions and angular velocities
+        V3 Wp = mk(0.f, 0.f, 0.f);
+        for (int lvl = 1; lvl <= maxdepth; ++lvl) {
+            const V3 px = mk(shfl(X.x, psrc), shfl(X.y, psrc), shfl(X.z, psrc));
+            const V3 pw = mk(shfl(W.x, psrc), shfl(W.y, psrc), shfl(W.z, psrc));
+            if (bdepth == lvl) { X = X + px; Wp = pw; W = W + pw; }
+        }
+        V3 AL = mk(0.f, 0.f, 0.f);
+        if (act && !rootfree) {
+            V = hinge ? cross(Wp, e) + cross(W, f) : cross(Wp, dx) + qd * zw;
+            if (bias && hinge) AL = qd * cross(Wp, zw);
+        }
+        // sweep 3: linear velocities and angular velocity-product accelerations
+        V3 ALp = mk(0.f, 0.f, 0.f);
+        for (int lvl = 1; lvl <= maxdepth; ++lvl) {
+            const V3 pv = mk(shfl(V.x, psrc), shfl(V.y, psrc), shfl(V.z, psrc));
+            if (bdepth == lvl) V = V + pv;
+            if (bias) {
+                const V3 pal = mk(shfl(AL.x, psrc), shfl(AL.y, psrc), shfl(AL.z, psrc));
+                if (bdepth == lvl) { ALp = pal; AL = AL + pal; }
+            }
+        }
+        V3 Acc = mk(0.f, 0.f, 0.f);
+        if (bias) {
+            if (act && !rootfree) {
+                Acc = hinge ? cross(ALp, e) + cross(Wp, cross(Wp, e)) + cross(AL, f) + cross(W, cross(W, f))
+                            : cross(ALp, dx) + cross(Wp, cross(Wp, dx)) + (2.f * qd) * cross(Wp, zw);
+            }
+            // sweep 4: linear velocity-product accelerations
+            for (int lvl = 1; lvl <= maxdepth; ++lvl) {
+                const V3 pa = mk(shfl(Acc.x, psrc), shfl(Acc.y, psrc), shfl(Acc.z, psrc));
+                if (bdepth == lvl) Acc = Acc + pa;
+            }
+        }
+        if (act) {
+            const V3 A = rootfree ? mk(0.f, 0.f, 0.f) : (hinge ? X - f : X - f - q * zw);
+            float *k = kin(gl);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) k[i] = R[i];
+            st3(k + 9, X); st3(k + 12, W); st3(k + 15, V);
+            if (bias) { st3(k + 18, AL); st3(k + 21, Acc); }
+            st3(k + 24, zw); st3(k + 27, A);
+            if (C::KINREG) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) kR[i] = R[i];
+                kx = X; kw = W; kv = V; kal = AL; ka = Acc;
+            }
+        }
+        __syncwarp();
+        (void)child;
+    }
+
     __device__ void fk(bool bias) {
         if (C::PLANAR) { fk_planar(bias); return; }
+#ifndef PBG_FK_LEVELS
+        fk_tree(bias);
+        return;
+#endif
         const float *S = st();
         const int maxdepth = m->maxdepth;
         for (int lvl = 0; lvl <= maxdepth; ++lvl) {
