@@ -284,24 +284,28 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
     const int nxp = k.hasx ? pm->ng : 0;
     if (pm->npair + nxp > k.npair || pm->npair + nxp > MPAIR) return "too many geom pairs for the kernel";
     d->npair = pm->npair + nxp;
+    d->ng = 0;
+    if (d->npair > 0) {
+        if (pm->ng > MGEOM) return "too many collision geoms for the pair tables";
+        d->ng = pm->ng;
+        for (int g = 0; g < pm->ng; ++g) {
+            d->g_body[g] = pm->geom_body[g];
+            for (int i = 0; i < 3; ++i) { d->g_p0[g][i] = (float)pm->geom_p0[3 * g + i]; d->g_p1[g][i] = (float)pm->geom_p1[3 * g + i]; }
+        }
+    }
     for (int g = 0; g < nxp; ++g) {
         const int p = pm->npair + g;
+        d->p_ga[p] = g; d->p_gb[p] = -1;
         d->p_ba[p] = pm->geom_body[g]; d->p_bb[p] = XB; d->p_box[p] = 1;
-        for (int i = 0; i < 3; ++i) {
-            d->p_a0[p][i] = (float)pm->geom_p0[3 * g + i]; d->p_a1[p][i] = (float)pm->geom_p1[3 * g + i];
-            d->p_b0[p][i] = (float)pm->cube_half;
-        }
+        d->p_half[p] = (float)pm->cube_half;
         d->p_ra[p] = (float)pm->geom_radius[g]; d->p_rb[p] = 0.f;
         d->p_thr[p] = (float)std::fmin(pm->geom_threshold[g], pm->cube_threshold);
         d->p_mu[p] = (float)(pm->geom_friction[g] * pm->cube_friction);
     }
     for (int p = 0; p < pm->npair; ++p) {
         const int a = pm->pair_a[p], b = pm->pair_b[p];
+        d->p_ga[p] = a; d->p_gb[p] = b;
         d->p_ba[p] = pm->geom_body[a]; d->p_bb[p] = pm->geom_body[b];
-        for (int i = 0; i < 3; ++i) {
-            d->p_a0[p][i] = (float)pm->geom_p0[3 * a + i]; d->p_a1[p][i] = (float)pm->geom_p1[3 * a + i];
-            d->p_b0[p][i] = (float)pm->geom_p0[3 * b + i]; d->p_b1[p][i] = (float)pm->geom_p1[3 * b + i];
-        }
         d->p_ra[p] = (float)pm->geom_radius[a]; d->p_rb[p] = (float)pm->geom_radius[b];
         d->p_thr[p] = (float)std::fmin(pm->geom_threshold[a], pm->geom_threshold[b]);
         d->p_mu[p] = (float)(pm->geom_friction[a] * pm->geom_friction[b]);

@@ -276,8 +276,7 @@ struct Env {
     }
 
     // ---------------------------------------------------------------- forward kinematics
-    // lane = body, one tree level per round.  bias=true also propagates the velocity-product
-    // accelerations needed for the bias wrench.
+    // lane = body.  bias=true also propagates the velocity-product accelerations needed for the bias wrench.
     // Planar robots (C::PLANAR): body b's orientation is Ry(theta_b) with theta_b the signed sum of the hinge angles above it, its
     // angular velocity (0, Omega_b, 0) likewise, so every lane first gets (theta, Omega) by one sweep of parent-to-child additions
     // (two shuffles per tree level), then computes ITS segment -- parent COM to anchor to own COM -- and that segment's
@@ -365,7 +364,6 @@ struct Env {
         const bool is_cube = C::HASX && act && bjtype == 4;
         const bool rootfree = act && (bjtype == 3 || is_cube);
         const bool hinge = act && bjtype == 1;
-        const bool child = act && bparent >= 0;
         const int psrc = bparent < 0 ? 0 : bparent;
         float L[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
         float q = 0.f, qd = 0.f;
@@ -476,106 +474,11 @@ struct Env {
             }
         }
         __syncwarp();
-        (void)child;
     }
 
     __device__ void fk(bool bias) {
-        if (C::PLANAR) { fk_planar(bias); return; }
-#ifndef PBG_FK_LEVELS
-        fk_tree(bias);
-        return;
-#endif
-        const float *S = st();
-        const int maxdepth = m->maxdepth;
-        for (int lvl = 0; lvl <= maxdepth; ++lvl) {
-            if (bdepth == lvl) {
-                float Rp[9], R[9];
-                V3 xp, wp, vp, alp, ap, x, w, v, al, a;
-                al = a = mk(0, 0, 0);
-                const int b = gl;                    // bdepth == lvl only for gl < NB
-                if (bparent >= 0) {
-                    const float *kp = kin(bparent);
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) Rp[i] = kp[i];
-                    xp = ld3(kp + 9); wp = ld3(kp + 12); vp = ld3(kp + 15); alp = ld3(kp + 18); ap = ld3(kp + 21);
-                } else {
-                    Rp[0] = 1; Rp[1] = 0; Rp[2] = 0; Rp[3] = 0; Rp[4] = 1; Rp[5] = 0; Rp[6] = 0; Rp[7] = 0; Rp[8] = 1;
-                    xp = wp = vp = alp = ap = mk(0, 0, 0);
-                }
-                V3 zw = mk(0, 0, 0), A = mk(0, 0, 0);
-                if (bjtype == 3 || (C::HASX && bjtype == 4)) {   // floating root / the cube
-                    const float *P = (C::HASX && bjtype == 4) ? S + C::oX : S;
-                    const float *U = S + C::oU + ((C::HASX && bjtype == 4) ? C::XD0 : 0);
-                    quat2mat(P + 3, R);
-                    x = ld3(P); w = ld3(U); v = ld3(U + 3);
-                    al = a = mk(0, 0, 0);
-                } else {
-                    float Rq[9];
-                    if (C::Q0ID) {
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) Rq[i] = Rp[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 3; ++i)
-#pragma unroll
-                            for (int j = 0; j < 3; ++j)
-                                Rq[3 * i + j] = Rp[3 * i] * m->q0m[b][j] + Rp[3 * i + 1] * m->q0m[b][3 + j] + Rp[3 * i + 2] * m->q0m[b][6 + j];
-                    }
-                    const float q = S[C::oQ + bdof - 6 * C::FLOATING], qd = S[C::oU + bdof];
-                    const V3 cOff = C::FKREG ? ld3(com_off) : ld3(m->com_off[b]);
-                    A = xp + mulR(Rp, C::FKREG ? ld3(anchor_p) : ld3(m->anchor_p[b]));
-                    const V3 ax = C::FKREG ? ld3(axis) : ld3(m->axis[b]);
-                    zw = (C::FKREG ? alen : m->axis_len[b]) * mulR(Rq, ax);       // motion subspace: the MJCF axis as written (Bullet does not normalise it)
-                    const V3 rpA = A - xp;
-                    if (bjtype == 1) {
-                        float s, c;
-                        sincosf(q, &s, &c);
-                        const float t = 1.f - c;
-                        float Rj[9];
-                        Rj[0] = c + t * ax.x * ax.x; Rj[1] = t * ax.x * ax.y - s * ax.z; Rj[2] = t * ax.x * ax.z + s * ax.y;
-                        Rj[3] = t * ax.x * ax.y + s * ax.z; Rj[4] = c + t * ax.y * ax.y; Rj[5] = t * ax.y * ax.z - s * ax.x;
-                        Rj[6] = t * ax.x * ax.z - s * ax.y; Rj[7] = t * ax.y * ax.z + s * ax.x; Rj[8] = c + t * ax.z * ax.z;
-#pragma unroll
-                        for (int i = 0; i < 3; ++i)
-#pragma unroll
-                            for (int j = 0; j < 3; ++j)
-                                R[3 * i + j] = Rq[3 * i] * Rj[j] + Rq[3 * i + 1] * Rj[3 + j] + Rq[3 * i + 2] * Rj[6 + j];
-                        const V3 rAi = mulR(R, cOff);
-                        x = A + rAi;
-                        w = wp + qd * zw;
-                        v = vp + cross(wp, rpA) + cross(w, rAi);
-                        if (bias) {
-                            al = alp + qd * cross(wp, zw);
-                            const V3 aA = ap + cross(alp, rpA) + cross(wp, cross(wp, rpA));
-                            a = aA + cross(al, rAi) + cross(w, cross(w, rAi));
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) R[i] = Rq[i];
-                        x = A + q * zw + mulR(R, cOff);
-                        w = wp;
-                        const V3 rpi = x - xp;
-                        v = vp + cross(wp, rpi) + qd * zw;
-                        if (bias) {
-                            al = alp;
-                            a = ap + cross(alp, rpi) + cross(wp, cross(wp, rpi)) + (2.f * qd) * cross(wp, zw);
-                        }
-                    }
-                }
-                if (C::KINREG) {
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) kR[i] = R[i];
-                    kx = x; kw = w; kv = v; kal = al; ka = a;
-                }
-                float *k = kin(gl);
-#pragma unroll
-                for (int i = 0; i < 9; ++i) k[i] = R[i];
-                st3(k + 9, x); st3(k + 12, w); st3(k + 15, v);
-                if (bias) { st3(k + 18, al); st3(k + 21, a); }
-                st3(k + 24, zw); st3(k + 27, A);
-            }
-            __syncwarp();
-        }
+        if (C::PLANAR) fk_planar(bias);
+        else fk_tree(bias);
     }
 
     // ---------------------------------------------------------------- contact generation
@@ -592,6 +495,18 @@ struct Env {
         V3 pa[PASSES], pb[PASSES], nn[PASSES];
         int total = 0;
         unsigned feet = 0;
+        // world end points of the geoms behind the pairs, once per pass (the constraint-row block is dead until build_rows)
+        float *gw = sm + C::sY;
+        if (C::NPAIR > 0) {
+            static_assert(C::NPAIR == 0 || C::YSZ >= 6 * MGEOM, "geom end-point staging lives in the constraint-row block");
+            for (int g = gl; g < m->ng; g += C::LPE) {
+                const float *kg = kin(m->g_body[g]);
+                const V3 xg = ld3(kg + 9);
+                st3(gw + 6 * g, xg + mulR(kg, ld3(m->g_p0[g])));
+                st3(gw + 6 * g + 3, xg + mulR(kg, ld3(m->g_p1[g])));
+            }
+            __syncwarp();
+        }
 #pragma unroll
         for (int p = 0; p < PASSES; ++p) {
             const int s = p * C::LPE + gl;
@@ -606,14 +521,15 @@ struct Env {
                 pa[p] = mk(c.x, c.y, c.z - r); pb[p] = mk(c.x, c.y, 0.f);
             } else if (C::NPAIR > 0 && s >= C::NCAND && s - C::NCAND < m->npair) {
                 const int pi = s - C::NCAND;
-                const float *ka = kin(m->p_ba[pi]), *kb = kin(m->p_bb[pi]);
-                const V3 p1 = ld3(ka + 9) + mulR(ka, ld3(m->p_a0[pi])), q1 = ld3(ka + 9) + mulR(ka, ld3(m->p_a1[pi]));
+                const float *kb = kin(m->p_bb[pi]);
+                const int ga = m->p_ga[pi];
+                const V3 p1 = ld3(gw + 6 * ga), q1 = ld3(gw + 6 * ga + 3);
                 if (C::HASX && m->p_box[pi]) {
                     // capsule / sphere against the cube: closest points of the segment and the box, in the box
                     // frame.  d/dt of the squared distance is monotone in t: 32 bisection steps (oracle.c closest_seg_box)
                     const V3 xb = ld3(kb + 9);
                     const V3 a0 = mulRt(kb, p1 - xb), dd = mulRt(kb, q1 - xb) - a0;
-                    const float hh = m->p_b0[pi][0];
+                    const float hh = m->p_half[pi];
                     // cheap exact reject: the box lies inside the sphere of radius sqrt(3) hh around its centre, so the
                     // segment-box distance is at least (segment-centre distance) - sqrt(3) hh.  While the cube is away from
                     // the robot (most of an episode) no lane of the warp enters the bisection.
@@ -642,7 +558,8 @@ struct Env {
                     nn[p] = n; pa[p] = xb + mulR(kb, xx) - ra * n; pb[p] = xb + mulR(kb, cc);
                     }
                 } else {
-                const V3 p2 = ld3(kb + 9) + mulR(kb, ld3(m->p_b0[pi])), q2 = ld3(kb + 9) + mulR(kb, ld3(m->p_b1[pi]));
+                const int gb = m->p_gb[pi];
+                const V3 p2 = ld3(gw + 6 * gb), q2 = ld3(gw + 6 * gb + 3);
                 const V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
                 const float aa = dot(d1, d1), ee = dot(d2, d2), f = dot(d2, r);
                 float sp, tp;

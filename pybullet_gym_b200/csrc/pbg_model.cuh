@@ -14,6 +14,7 @@ constexpr int MJ = 24;      // max joint dofs
 constexpr int MSUB = 32;    // max Bullet links folded into the bodies (humanoid: 30)
 constexpr int MCAND = 40;   // max ground contact candidates (humanoid: 4 spheres + 13 capsules * 2, + 8 cube corners)
 constexpr int MPAIR = 84;   // max geom pairs (humanoid: 66 self-collision pairs + 17 geoms against the cube)
+constexpr int MGEOM = 24;   // max collision geoms that take part in geom pairs (humanoid: 17)
 constexpr int MFEET = 8;
 constexpr int TASK_FLOATS = 24;
 
@@ -35,9 +36,13 @@ struct alignas(16) DevModel {
     float c_p[MCAND][3], c_rad[MCAND], c_thr[MCAND], c_mu[MCAND];
     float c_spin[MCAND], c_roll[MCAND];      // combined spinning / rolling friction of a ground candidate (torsional rows)
     int p_ba[MPAIR], p_bb[MPAIR];
-    float p_a0[MPAIR][3], p_a1[MPAIR][3], p_b0[MPAIR][3], p_b1[MPAIR][3], p_ra[MPAIR], p_rb[MPAIR], p_thr[MPAIR],
-        p_mu[MPAIR];
-    int p_box[MPAIR];                         // 1: body B is the cube, p_b0 = half extents
+    float p_ra[MPAIR], p_rb[MPAIR], p_thr[MPAIR], p_mu[MPAIR];
+    float p_half[MPAIR];                      // pairs against the cube: its half extent
+    int p_box[MPAIR];                         // 1: body B is the cube
+    // the geoms behind the pairs: their end points are taken to world coordinates once per collision pass (every humanoid geom
+    // is in ~8 pairs) and the pairs read them from shared memory
+    int ng, g_body[MGEOM], p_ga[MPAIR], p_gb[MPAIR];      // p_gb = -1: body B is the cube
+    float g_p0[MGEOM][3], g_p1[MGEOM][3];
     float cube_pos0[3];
     int aux_body[2];                          // Reacher: fingertip / target bodies and their link-COM offsets
     float aux_off[2][3];
