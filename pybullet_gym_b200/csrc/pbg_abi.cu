@@ -320,6 +320,7 @@ static std::string build_dev_model(const pbg_model *pm, const KernelInfo &k, Dev
     d->limit_cost = (float)pm->joints_at_limit_cost; d->walk_tx = (float)pm->walk_target_x; d->walk_ty = (float)pm->walk_target_y;
     d->halflen = (float)pm->stadium_halflen; d->halfwidth = (float)pm->stadium_halfwidth;
     d->dt_scene = pm->timestep * pm->frame_skip;
+    d->inv_dt_scene = 1.0 / d->dt_scene;
     d->max_steps = pm->max_episode_steps;
     return "";
 }

@@ -73,6 +73,7 @@ struct KCfg {
     static constexpr int NNOISE = NNOISE_;                     // injectable reset draws per env (pbg_reset_with)
     static constexpr int HASX = XP_ > 0 ? 1 : 0;
     static constexpr int NB = NB_ + HASX, NJ = NJ_, FLOATING = FLOATING_, NLIM = NLIM_;
+    static constexpr int NB_ROBOT = NB_;
     static constexpr int XD0 = NJ_ + 6 * FLOATING_;            // first cube dof
     static constexpr int ND = XD0 + 6 * HASX;
     // structural coupling masks (see Topo* above); the cube's six dofs are a chain of their own
@@ -207,6 +208,16 @@ __device__ __forceinline__ void mat2quat(const float *m, float *q) {
 }
 
 // Philox4x32-10, bit-identical to oracle/oracle.c rng_uniform_s
+// The task layer runs once per env step, by which time the sub-step loop has pushed its code out of the 32 KB instruction cache: its
+// cost is instruction fetch (half of its stall samples are no_inst).  The libdevice routines it calls several times are kept
+// out of line so that each is fetched once and re-executed from the cache.
+static __device__ __noinline__ float atan2_shared(float y, float x) { return atan2f(y, x); }
+static __device__ __noinline__ float2 sincos_shared(float x) {
+    float s, c;
+    sincosf(x, &s, &c);
+    return make_float2(s, c);
+}
+
 __device__ __forceinline__ float rng_uniform(unsigned long long seed, unsigned long long env, unsigned ep,
                                              unsigned stream, unsigned n, float lo, float hi) {
     unsigned c0 = (unsigned)env, c1 = (unsigned)(env >> 32), c2 = ep, c3 = (stream << 24) | (n >> 2);
@@ -1252,30 +1263,32 @@ struct Env {
         // getEulerFromQuaternion(torso orientation) (rs/robot_bases.py:216-217) taken straight from the
         // rotation matrix: roll = atan2(R21, R22), pitch = asin(-R20), yaw = atan2(R10, R00).  The pitch
         // uses atan2(-R20, sqrt(R00^2 + R10^2)): identical value, but well conditioned in fp32 near +-pi/2.
-        const float roll = atan2f(kt[7], kt[8]);
-        const float pitch = atan2f(-kt[6], sqrtf(kt[0] * kt[0] + kt[3] * kt[3]));
-        const float yaw = atan2f(kt[3], kt[0]);
+        const float roll = atan2_shared(kt[7], kt[8]);
+        const float pitch = atan2_shared(-kt[6], sqrtf(kt[0] * kt[0] + kt[3] * kt[3]));
+        const float yaw = atan2_shared(kt[3], kt[0]);
         float initz = T[T_INITZ];
         if (reset_pass) {
             initz = m->initial_z >= 0.f ? m->initial_z : z;
         }
         float tx = T[T_TX], ty = T[T_TY];
         double ddy = (double)ty - (double)by, ddx = (double)tx - (double)bx;
-        float theta = atan2f(ty - by, tx - bx);
+        float theta = atan2_shared(ty - by, tx - bx);
         double dist = sqrt(ddy * ddy + ddx * ddx);
         const int kind = m->kind;
-        const bool flagrun = kind == 7 || kind == 8;
+        // compile-time capabilities of the configuration prune the blocks a kind can never enter (they are large: the cube attack
+        // alone holds five Philox evaluations)
+        const bool flagrun = C::NB_ROBOT == 18 && C::OBS == 44 && (kind == 7 || kind == 8);
         float flag_timeout = 0.f;
         int flag_cnt = 0;
         // HumanoidFlagrunHarder.calc_potential (rs/robot_locomotors.py:280-302) has side effects (crawl
         // bookkeeping) and is evaluated once per flag move and once per step, in that order
-        const bool harder = kind == 8;
+        const bool harder = C::HASX && kind == 8;
         bool crawl_has = harder && T[T_CRAWL_HAS] != 0.f;
         double crawl_start = harder ? __hiloint2double(__float_as_int(T[T_CRAWL_START_HI]), __float_as_int(T[T_CRAWL_START_LO])) : 0.0;
         double crawl_ign = harder ? __hiloint2double(__float_as_int(T[T_CRAWL_IGN_HI]), __float_as_int(T[T_CRAWL_IGN_LO])) : 0.0;
         const float leak = fminf(fmaxf(z, 0.f), 0.8f) / 0.8f + 1.0f;          // potential_leak()
         auto harder_potential = [&](double d) {
-            double frp = -d / m->dt_scene;
+            double frp = -d * m->inv_dt_scene;
             if (z < 0.8f) {
                 if (!crawl_has) { crawl_start = frp - crawl_ign; crawl_has = true; }
                 crawl_ign = frp - crawl_start;
@@ -1298,21 +1311,21 @@ struct Env {
                 flag_cnt += 1;
                 flag_timeout = 600.f / (float)m->nsub;
                 ddy = (double)ty - (double)by; ddx = (double)tx - (double)bx;
-                theta = atan2f(ty - by, tx - bx);
+                theta = atan2_shared(ty - by, tx - bx);
                 dist = sqrt(ddy * ddy + ddx * ddx);
                 if (harder) (void)harder_potential(dist);     // robot.potential = calc_potential(): value unused (quirk Q5)
             }
         }
         const float ang = theta - yaw;
-        float sy, cy;
-        sincosf(-yaw, &sy, &cy);
+        const float2 scy = sincos_shared(-yaw);
+        const float sy = scy.x, cy = scy.y;
         const float vx = cy * tsp.x - sy * tsp.y, vy = sy * tsp.x + cy * tsp.y, vz = tsp.z;
-        float sa, ca;
-        sincosf(ang, &sa, &ca);
+        const float2 sca = sincos_shared(ang);
+        const float sa = sca.x, ca = sca.y;
         // observation, clipped to +-5
         auto clip5 = [](float q) { return fminf(fmaxf(q, -5.f), 5.f); };
         const float o0 = clip5(z - initz);
-        const bool mjf = kind == 14 || kind == 15;
+        const bool mjf = C::OBS > 64 && (kind == 14 || kind == 15);
         if (mjf && obs_out && pred) {
             // MuJoCo-style Ant / Humanoid: [z, quat xyzw, q] ++ [base v, base omega, qdot] (unclipped), zeros after that
             if (gl == 0) { obs_out[0] = S[2]; obs_out[1] = S[3]; obs_out[2] = S[4]; obs_out[3] = S[5]; obs_out[4] = S[6]; }
@@ -1346,8 +1359,8 @@ struct Env {
                         const float speed = rng_uniform(rng_seed, rng_env, ep, 2u, 5u * h_att + 1u, 20.f, 30.f);
                         const float ttt = 4.0f / speed;
                         const V3 tgt = mk(bx + tsp.x * ttt, by + tsp.y * ttt, z + tsp.z * ttt);
-                        float sa_, ca_;
-                        sincosf(angle, &sa_, &ca_);
+                        const float2 sca_ = sincos_shared(angle);
+                        const float sa_ = sca_.x, ca_ = sca_.y;
                         const V3 pos = mk(tgt.x + 4.0f * ca_, tgt.y + 4.0f * sa_, tgt.z + 1.0f);
                         const V3 dv = tgt - pos;
                         const float sc = speed * rsqrtf(dot(dv, dv));
@@ -1366,7 +1379,7 @@ struct Env {
                 h_alive = h_og < 170 ? leak : -1.f;
             }
         }
-        const double pot_new = harder ? harder_potential(dist) : -dist / m->dt_scene;
+        const double pot_new = harder ? harder_potential(dist) : -dist * m->inv_dt_scene;
         {
             // alive uses state[0] + initial_z after the float32 round trip (rs/gym_locomotion_envs.py:61)
             // (MuJoCo-style variants pass state[0] = torso z itself: mujoco/gym_locomotion_envs.py:60)

@@ -53,7 +53,7 @@ struct alignas(16) DevModel {
     int nsub, niter, limit_split, max_contacts;
     // task
     float initial_z, elec_cost, stall_cost, limit_cost, walk_tx, walk_ty, halflen, halfwidth;
-    double dt_scene;
+    double dt_scene, inv_dt_scene;
     int max_steps;
 };
 
