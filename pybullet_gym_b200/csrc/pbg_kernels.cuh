@@ -745,10 +745,14 @@ struct Env {
             const bool xk = C::HASX && k >= C::XD0;
 #pragma unroll
             for (int sl = 0; sl < NS; ++sl) {
-                float val = 0.f;
-                if ((ma[sl] >> k) & 1u) val += (C::TORS && kind[sl] == 3) ? dot(d[sl], so) : dot(d[sl], sv + cross(so, xk ? pAx[sl] : pA[sl]));
-                if (C::NPAIR > 0) { if ((mb[sl] >> k) & 1u) val -= dot(d[sl], sv + cross(so, xk ? pBx[sl] : pB[sl])); }
-                if (kind[sl] == 0) val = (k == ldof[sl]) ? ldir[sl] : 0.f;
+                // lanes are rows of different bodies: the ancestor tests are hardly ever warp-uniform, so evaluate and select
+                const float va = (C::TORS && kind[sl] == 3) ? dot(d[sl], so) : dot(d[sl], sv + cross(so, xk ? pAx[sl] : pA[sl]));
+                float val = ((ma[sl] >> k) & 1u) ? va : 0.f;
+                if (C::NPAIR > 0) {
+                    const float vb = dot(d[sl], sv + cross(so, xk ? pBx[sl] : pB[sl]));
+                    val -= ((mb[sl] >> k) & 1u) ? vb : 0.f;
+                }
+                val = kind[sl] == 0 ? ((k == ldof[sl]) ? ldir[sl] : 0.f) : val;
                 J[sl][k] = val;
             }
         }
@@ -1265,14 +1269,17 @@ struct Env {
         // uses atan2(-R20, sqrt(R00^2 + R10^2)): identical value, but well conditioned in fp32 near +-pi/2.
         const float roll = atan2_shared(kt[7], kt[8]);
         const float pitch = atan2_shared(-kt[6], sqrtf(kt[0] * kt[0] + kt[3] * kt[3]));
-        const float yaw = atan2_shared(kt[3], kt[0]);
+        // yaw = atan2(R10, R00) and the target bearing theta = atan2(dy, dx) enter the observation only through sin / cos of
+        // (theta - yaw) and of -yaw: taken from the normalised vectors directly, no trigonometric calls (atan2(0, 0) = 0 kept)
+        const float nyaw = sqrtf(kt[0] * kt[0] + kt[3] * kt[3]);
+        const float cyaw = nyaw > 0.f ? kt[0] / nyaw : 1.f, syaw = nyaw > 0.f ? kt[3] / nyaw : 0.f;
         float initz = T[T_INITZ];
         if (reset_pass) {
             initz = m->initial_z >= 0.f ? m->initial_z : z;
         }
         float tx = T[T_TX], ty = T[T_TY];
         double ddy = (double)ty - (double)by, ddx = (double)tx - (double)bx;
-        float theta = atan2_shared(ty - by, tx - bx);
+        float thx = tx - bx, thy = ty - by;
         double dist = sqrt(ddy * ddy + ddx * ddx);
         const int kind = m->kind;
         // compile-time capabilities of the configuration prune the blocks a kind can never enter (they are large: the cube attack
@@ -1311,17 +1318,16 @@ struct Env {
                 flag_cnt += 1;
                 flag_timeout = 600.f / (float)m->nsub;
                 ddy = (double)ty - (double)by; ddx = (double)tx - (double)bx;
-                theta = atan2_shared(ty - by, tx - bx);
+                thx = tx - bx; thy = ty - by;
                 dist = sqrt(ddy * ddy + ddx * ddx);
                 if (harder) (void)harder_potential(dist);     // robot.potential = calc_potential(): value unused (quirk Q5)
             }
         }
-        const float ang = theta - yaw;
-        const float2 scy = sincos_shared(-yaw);
-        const float sy = scy.x, cy = scy.y;
+        const float sy = -syaw, cy = cyaw;                                      // sin / cos of -yaw
         const float vx = cy * tsp.x - sy * tsp.y, vy = sy * tsp.x + cy * tsp.y, vz = tsp.z;
-        const float2 sca = sincos_shared(ang);
-        const float sa = sca.x, ca = sca.y;
+        const float nth = sqrtf(thx * thx + thy * thy);
+        const float cth = nth > 0.f ? thx / nth : 1.f, sth = nth > 0.f ? thy / nth : 0.f;
+        const float sa = sth * cyaw - cth * syaw, ca = cth * cyaw + sth * syaw;  // sin / cos of (theta - yaw)
         // observation, clipped to +-5
         auto clip5 = [](float q) { return fminf(fmaxf(q, -5.f), 5.f); };
         const float o0 = clip5(z - initz);
