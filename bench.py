@@ -34,9 +34,10 @@ ALG = {
 }
 
 
-# the other single-GPU configurations BASELINE.json names (C2, C3, C4's upper size, C5): short runs reported under "configs"
+# the other single-GPU configurations BASELINE.json names (C2, C3, C4's upper size, C5) and the Humanoid at the metric's
+# 4096 envs/GPU: short runs reported under "configs"
 EXTRA_CONFIGS = [("HalfCheetahPyBulletEnv-v0", 4096), ("HopperPyBulletEnv-v0", 4096), ("Walker2DPyBulletEnv-v0", 4096),
-                 ("AntPyBulletEnv-v0", 16384), ("HumanoidFlagrunHarderPyBulletEnv-v0", 2048)]
+                 ("AntPyBulletEnv-v0", 16384), ("HumanoidFlagrunHarderPyBulletEnv-v0", 2048), ("HumanoidPyBulletEnv-v0", 4096)]
 
 
 def parse():
