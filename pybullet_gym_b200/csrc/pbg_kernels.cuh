@@ -1758,6 +1758,27 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
 #ifdef PBG_PHASE_CLOCKS
     const long long _kstart = clock64();
 #endif
+    e.gl = lane & (C::LPE - 1);
+    e.grp = lane / C::LPE;
+    const int slot = warp * C::EPW + e.grp;
+    e.sm = smem + slot * C::ENV_FLOATS;
+    const long long env_raw = (long long)blockIdx.x * C::EPB + slot;
+    const bool valid = env_raw < la.E;
+    const long long env = valid ? env_raw : (la.E - 1);
+    const unsigned long long genv = la.env_offset + (unsigned long long)env;
+    const int gl = e.gl;
+    // The env's state and actions are requested first (coalesced, vectorised; the actions may live in mapped pinned host memory --
+    // pbg_step_host's zero-copy path -- and are read exactly once), so that their latency runs under the model-table copy below.
+    float *gs = B.state + env * C::SSTRIDE;
+    constexpr int NLD = (C::SSTRIDE / 4 + C::LPE - 1) / C::LPE;
+    float4 sreg[NLD];
+#pragma unroll
+    for (int r = 0; r < NLD; ++r) {
+        const int i = r * C::LPE + gl;
+        sreg[r] = i < C::SSTRIDE / 4 ? reinterpret_cast<const float4 *>(gs)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float *gact = B.actions ? B.actions + env * C::NACT : nullptr;
+    const float areg = (gl < C::NACT && gact) ? gact[gl] : 0.f;
 #ifndef PBG_NO_SMEM_MODEL
     if (C::MODEL_IN_SMEM) {
         static_assert(sizeof(DevModel) % 16 == 0 && C::ENV_BYTES % 16 == 0, "model copy is done in 16-byte words");
@@ -1769,27 +1790,17 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) env_kernel(const De
     }
 #endif
     e.m = model;
-    e.gl = lane & (C::LPE - 1);
-    e.grp = lane / C::LPE;
-    const int slot = warp * C::EPW + e.grp;
-    e.sm = smem + slot * C::ENV_FLOATS;
-    const long long env_raw = (long long)blockIdx.x * C::EPB + slot;
-    const bool valid = env_raw < la.E;
-    const long long env = valid ? env_raw : (la.E - 1);
-    const unsigned long long genv = la.env_offset + (unsigned long long)env;
-    const int gl = e.gl;
     e.load_lane_constants();
     e.rng_seed = la.seed; e.rng_env = genv;
     if (B.debug && env_raw == la.debug_env) e.dbg = B.debug;
 
     float *S = e.st();
-    float *gs = B.state + env * C::SSTRIDE;
-    // coalesced, vectorised state load
-    for (int i = gl; i < C::SSTRIDE / 4; i += C::LPE)
-        reinterpret_cast<float4 *>(S)[i] = reinterpret_cast<const float4 *>(gs)[i];
-    // the actions may live in mapped pinned host memory (pbg_step_host zero-copy path): read them exactly once
-    const float *gact = B.actions ? B.actions + env * C::NACT : nullptr;
-    if (gl < C::NACT) e.sm[C::sACTN + gl] = gact ? gact[gl] : 0.f;
+#pragma unroll
+    for (int r = 0; r < NLD; ++r) {
+        const int i = r * C::LPE + gl;
+        if (i < C::SSTRIDE / 4) reinterpret_cast<float4 *>(S)[i] = sreg[r];
+    }
+    if (gl < C::NACT) e.sm[C::sACTN + gl] = areg;
     __syncwarp();
     float *T = S + C::oT;
     const int mode = la.mode;
