@@ -345,6 +345,7 @@ struct Env {
             st3(k + 9, x); st3(k + 12, w); st3(k + 15, v);
             if (bias) { st3(k + 18, mk(0.f, 0.f, 0.f)); st3(k + 21, a); }
             st3(k + 24, zw); st3(k + 27, A);
+            k[30] = th;                          // the body's accumulated angle: the task layer's pitch without an atan2f
             if (C::KINREG) {
                 kR[0] = c; kR[1] = 0.f; kR[2] = s; kR[3] = 0.f; kR[4] = 1.f; kR[5] = 0.f; kR[6] = -s; kR[7] = 0.f; kR[8] = c;
                 kx = x; kw = w; kv = v; kal = mk(0.f, 0.f, 0.f); ka = a;
@@ -1270,8 +1271,17 @@ struct Env {
         // getEulerFromQuaternion(torso orientation) (rs/robot_bases.py:216-217) taken straight from the
         // rotation matrix: roll = atan2(R21, R22), pitch = asin(-R20), yaw = atan2(R10, R00).  The pitch
         // uses atan2(-R20, sqrt(R00^2 + R10^2)): identical value, but well conditioned in fp32 near +-pi/2.
-        const float roll = atan2_shared(kt[7], kt[8]);
-        const float pitch = atan2_shared(-kt[6], sqrtf(kt[0] * kt[0] + kt[3] * kt[3]));
+        float roll, pitch;
+        if (C::PLANAR) {
+            // R = Ry(theta): roll = atan2(+0, cos) and pitch = atan2(sin, |cos|) follow from the accumulated angle itself
+            const float thw = kt[30] - 6.2831853071795865f * rintf(kt[30] * 0.15915494309189535f);      // (-pi, pi]
+            const bool fwd = kt[8] >= 0.f;
+            roll = fwd ? 0.f : 3.14159265358979324f;
+            pitch = fwd ? thw : (thw >= 0.f ? 3.14159265358979324f - thw : -3.14159265358979324f - thw);
+        } else {
+            roll = atan2_shared(kt[7], kt[8]);
+            pitch = atan2_shared(-kt[6], sqrtf(kt[0] * kt[0] + kt[3] * kt[3]));
+        }
         // yaw = atan2(R10, R00) and the target bearing theta = atan2(dy, dx) enter the observation only through sin / cos of
         // (theta - yaw) and of -yaw: taken from the normalised vectors directly, no trigonometric calls (atan2(0, 0) = 0 kept)
         const float nyaw = sqrtf(kt[0] * kt[0] + kt[3] * kt[3]);

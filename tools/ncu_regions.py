@@ -6,7 +6,7 @@ rep = sys.argv[1]
 srcf = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "pybullet_gym_b200", "csrc", "pbg_kernels.cuh")
 marks = []
 for i, l in enumerate(open(srcf), 1):
-    m = re.match(r"\s*(?:template <[^>]*>\s*)?__(?:device|global)__ .*?\b(\w+)\s*\(", l)
+    m = re.match(r"\s*(?:template <[^>]*>\s*)?(?:static\s+)?__(?:device|global)__ .*?\b(\w+)\s*\(", l)
     if m and not l.strip().startswith("//"):
         marks.append((i, m.group(1)))
 marks.append((10 ** 9, "end"))
