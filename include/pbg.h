@@ -244,7 +244,7 @@ int pbg_physics_step_counts(pbg_handle *h, const float *actions_dev, int32_t *nc
 int pbg_max_contacts(int kind);
 /* Constraint-row budget of the kernel for this env kind: with nl violated joint limits in a sub-step at most
  * min(pbg_max_contacts, (pbg_max_rows - nl) / 3) contacts (the deepest) get solver rows.  Equals nlim + 3 * max_contacts (never
- * binding) except for the humanoid kinds, where it is 40 (FlagrunHarder: 36); an oracle compared with the library applies the
+ * binding) except for the humanoid kinds, where it is 36; an oracle compared with the library applies the
  * same rule. */
 int pbg_max_rows(int kind);
 
