@@ -1151,6 +1151,9 @@ struct Env {
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl) {
                     if (sl * C::LPE >= nrmax) continue;
+                    // second-slot entries against the first LPE rows are the transposes of first-slot entries computed when the
+                    // loop reaches that second-slot row (same products, same order: bit-identical); they are copied below
+                    if (sl == 1 && i < C::LPE) continue;
                     // two partial sums: halves the dependent FMA chain of the dot product
                     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -1160,6 +1163,18 @@ struct Env {
                     const int jrow = sl * C::LPE + gl;
                     if (jrow < C::MAXR) Am[i * C::MAXRP + jrow] = aij;
                     r[sl] += aij * l0;
+                }
+            }
+            if (nrmax > C::LPE) {
+                __syncwarp();
+                const int jrow = C::LPE + gl;
+                if (jrow < C::MAXR) {
+#pragma unroll 4
+                    for (int i = 0; i < C::LPE; ++i) {
+                        const float a = Am[jrow * C::MAXRP + i];
+                        Am[i * C::MAXRP + jrow] = a;
+                        r[1] = fmaf(a, lam[i], r[1]);
+                    }
                 }
             }
         }
