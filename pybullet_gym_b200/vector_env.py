@@ -67,6 +67,7 @@ class VectorEnv:
         self.truncated = torch.zeros(E, dtype=torch.uint8, device=dev)
         self._first_reset_done = False
         self._ready = False          # a reset / set_state / restore has initialised the state
+        self._host_ok = {}           # step_host buffers that have passed the argument checks: id -> (address, numel, role, c_void_p)
         self._cand = None
 
     # ------------------------------------------------------------------ lifecycle
@@ -154,15 +155,31 @@ class VectorEnv:
                   done_host: torch.Tensor):
         """Host-buffer step through pbg_step_host: H2D actions, step, D2H obs/reward/done, synchronised.  Ordered after
         whatever this env enqueued before (reset() on torch's stream ...) by the library itself."""
+        # The argument checks cost more host time than the call itself (~8 us of a ~120 us step): a buffer that has passed them is
+        # remembered by object identity + storage address + element count, and only a new one is checked in full.
         E = self.num_envs
-        self._check_io(actions_host, (E, self.action_dim), torch.float32, "actions_host", False)
-        if obs_host is not None:
-            self._check_io(obs_host, (E, self.obs_dim), torch.float32, "obs_host", False)
-        if reward_host is not None:
-            self._check_io(reward_host, (E,), torch.float32, "reward_host", False)
-        if done_host is not None:
-            self._check_io(done_host, (E,), torch.uint8, "done_host", False)
-        rc = self._L.pbg_step_host(self._h, _ptr(actions_host), _ptr(obs_host), _ptr(reward_host), _ptr(done_host))
+        cache = self._host_ok
+        ptrs = []
+        for t, shape, dtype, name in ((actions_host, (E, self.action_dim), torch.float32, "actions_host"),
+                                      (obs_host, (E, self.obs_dim), torch.float32, "obs_host"),
+                                      (reward_host, (E,), torch.float32, "reward_host"),
+                                      (done_host, (E,), torch.uint8, "done_host")):
+            if t is None:
+                if name == "actions_host":
+                    raise ValueError("actions_host is required")
+                ptrs.append(None)
+                continue
+            p = t.data_ptr()
+            ent = cache.get(id(t))
+            if ent is None or ent[0] != p or ent[1] != t.numel() or ent[2] != name:
+                self._check_io(t, shape, dtype, name, False)
+                if len(cache) > 64:
+                    cache.clear()
+                ent = cache[id(t)] = (p, t.numel(), name, C.c_void_p(p))
+            ptrs.append(ent[3])
+        if not self._ready:
+            raise RuntimeError("step before reset(): the env state is uninitialised")
+        rc = self._L.pbg_step_host(self._h, ptrs[0], ptrs[1], ptrs[2], ptrs[3])
         if rc:
             _lib.check(rc, self._h)
 
