@@ -18,7 +18,7 @@
 #define MAXD 32
 #define MAXU (MAXD + 12)        /* base 6 + joints + cube 6 */
 #define MAXG 32
-#define MAXCAND 160
+#define MAXCAND 320
 #define MAXROWS 256
 #define MAXFEET 8
 
@@ -186,6 +186,9 @@ struct orc_env {
     /* Flagrun / FlagrunHarder (rs/robot_locomotors.py:195-302) */
     double flag_timeout; int flag_count, frame, on_ground, crawl_has, attacks; double crawl_start, crawl_ign;
     double tape[4096]; int tape_n, tape_pos;
+    /* ground_manifold = 1 (oracle-only probe): btPersistentManifold of each geom-vs-floor pair -- up to four cached
+     * points, each the geom's point in its link frame and the floor point in world coordinates */
+    struct { int on; v3 la, pb; } mf[MAXG][4];
     double last_dv[MAXU], last_ufree[MAXU], last_u0[MAXU];
 };
 
@@ -551,6 +554,53 @@ static void collide(orc_env *e) {
     for (int g = 0; g < m->ng; g++) {
         int npt = m->g_type[g] == ORC_G_CAPSULE ? 2 : 1;
         v3 a, b; geom_world(e, g, a, b);
+        if (m->ground_manifold) {
+            /* btConvexPlaneCollisionAlgorithm::processCollision for a non-polyhedral convex: ONE new point per pass (the support
+             * vertex towards the plane, kept if closer than the breaking threshold; btPersistentManifold::getCacheEntry replaces
+             * the nearest cached point within that threshold, else the point is added), then refreshContactPoints: cached
+             * points move with their bodies and are dropped once they separate or drift sideways by more than the threshold */
+            const int l = m->g_link[g];
+            const double thr = m->g_threshold[g], rad = m->g_radius[g];
+            if (m->g_ground[g]) {
+                const double *c = (npt == 2 && b[2] < a[2]) ? b : a;
+                if (c[2] - rad < thr) {
+                    v3 pw = {c[0], c[1], c[2] - rad}, t, la;
+                    v3sub(t, pw, e->p[l]);
+                    for (int i = 0; i < 3; i++) la[i] = e->R[l][0][i] * t[0] + e->R[l][1][i] * t[1] + e->R[l][2][i] * t[2];
+                    int best = -1; double bd = thr * thr;
+                    for (int k = 0; k < 4; k++) if (e->mf[g][k].on) {
+                        v3 d; v3sub(d, e->mf[g][k].la, la);
+                        if (v3dot(d, d) < bd) { bd = v3dot(d, d); best = k; }
+                    }
+                    if (best < 0) {
+                        for (int k = 0; k < 4 && best < 0; k++) if (!e->mf[g][k].on) best = k;
+                        if (best < 0) {   /* full: the shallowest cached point makes room (sortCachedPoints keeps the deepest) */
+                            double wz = -1e30;
+                            for (int k = 0; k < 4; k++) {
+                                v3 pa; m3mulv(pa, (double(*)[3])e->R[l], e->mf[g][k].la); v3add(pa, pa, e->p[l]);
+                                if (pa[2] > wz) { wz = pa[2]; best = k; }
+                            }
+                        }
+                        e->warm[slot + best] = 0.0;
+                    }
+                    e->mf[g][best].on = 1; v3cpy(e->mf[g][best].la, la); v3set(e->mf[g][best].pb, c[0], c[1], 0.0);
+                }
+            }
+            for (int k = 0; k < 4; k++, slot++) {
+                e->cand_active[slot] = 0;
+                if (!e->mf[g][k].on) continue;
+                v3 pa; m3mulv(pa, (double(*)[3])e->R[l], e->mf[g][k].la); v3add(pa, pa, e->p[l]);
+                const double dx = e->mf[g][k].pb[0] - pa[0], dy = e->mf[g][k].pb[1] - pa[1];
+                if (!m->g_ground[g] || pa[2] > thr || dx * dx + dy * dy > thr * thr) { e->mf[g][k].on = 0; continue; }
+                contact *ct = &all[n++];
+                ct->ga = g; ct->gb = -1; ct->la = l; ct->lb = -1; ct->slot = slot;
+                v3set(ct->n, 0, 0, 1); v3cpy(ct->pa, pa); v3cpy(ct->pb, e->mf[g][k].pb);
+                ct->dist = pa[2]; ct->mu = m->g_friction[g] * m->ground_friction;
+                ct->mu_spin = m->torsional ? m->g_spin[g] * m->ground_friction + m->ground_spin * m->g_friction[g] : 0;
+                ct->mu_roll = m->torsional ? m->g_roll[g] * m->ground_friction + m->ground_roll * m->g_friction[g] : 0;
+            }
+            continue;
+        }
         for (int k = 0; k < npt; k++, slot++) {
             e->cand_active[slot] = 0;
             if (!m->g_ground[g]) continue;
@@ -1258,6 +1308,7 @@ static void reset_common(orc_env *e, const double *noise, int floor_in_parts, do
     const orc_model *m = &e->m;
     memset(e->q, 0, sizeof(e->q)); memset(e->qd, 0, sizeof(e->qd)); memset(e->tau, 0, sizeof(e->tau));
     memset(e->warm, 0, sizeof(e->warm));
+    memset(e->mf, 0, sizeof(e->mf));   /* removeBody / restoreState: the manifolds start empty */
     if (m->floating) {
         /* snapshot pose = MJCF pose: base inertial frame */
         m3 R0; q2m(R0, &m->quat[0]);

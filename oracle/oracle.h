@@ -80,6 +80,10 @@ typedef struct {
     int32_t friction_cone;
     /* links whose COM the task layer reads besides torso_link (Reacher: fingertip, target); -1: unused */
     int32_t aux_link[2];
+    /* ground_manifold = 1: geom-vs-floor contacts come from a persistent manifold (one new point per collision pass, up to four
+     * cached points per geom, 0.02-style breaking threshold) instead of the instantaneous end-sphere candidates
+     * the CUDA kernel tests.  Oracle-only probe (tools/policy_probe.py). */
+    int32_t ground_manifold;
 } orc_model;
 
 typedef struct orc_env orc_env;

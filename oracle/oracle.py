@@ -56,6 +56,7 @@ class OrcModel(C.Structure):
         ("cube_friction", C.c_double), ("cube_threshold", C.c_double), ("cube_pos0", C.c_double * 3),
         ("friction_cone", C.c_int32),
         ("aux_link", C.c_int32 * 2),
+        ("ground_manifold", C.c_int32),
     ]
 
 

@@ -296,3 +296,24 @@ def test_airborne_angular_momentum_converges_first_order(env_id, scale, spin, or
         drift.append(w)
     assert drift[0] > 1e-3, drift                                        # a visible first-order error (Ant: ~0.3 % of |H| in the spin case)
     assert 0.45 < drift[1] / drift[0] < 0.55 and 0.45 < drift[2] / drift[1] < 0.55, drift
+
+
+def test_ground_manifold_switch_agrees_with_candidates_at_rest(oracle_lib):
+    """`ground_manifold` (oracle-only probe of SURVEY C5.2: one new floor point per collision pass and geom, up to four
+    cached points, dropped beyond the breaking threshold) must reach the same resting configuration as the instantaneous
+    end-sphere candidates the CUDA kernel tests: at rest the cached points ARE the end spheres' lowest points."""
+    import ctypes as C
+    rest = {}
+    for mode in (0, 1):
+        env = oracle_lib.OracleEnv("AntPyBulletEnv-v0", seed=1, ground_manifold=mode)
+        env.reset()
+        for _ in range(150):
+            ob, _, _, _ = env.step(np.zeros(env.nact))
+            assert oracle_lib.lib().orc_num_contacts(env._h) <= 4 * int(env.model.c.ng)
+        rest[mode] = (env.get_state().copy(), oracle_lib.lib().orc_num_contacts(env._h))
+    assert rest[0][1] == rest[1][1] > 0
+    assert np.abs(rest[0][0][:7] - rest[1][0][:7]).max() < 1e-4
+    # and a moving robot stays finite with manifolds on
+    env = oracle_lib.OracleEnv("HalfCheetahPyBulletEnv-v0", seed=3, ground_manifold=1)
+    n, ret, _ = env.rollout(600, action_seed=5)
+    assert n == 600 and np.isfinite(ret)

@@ -7,14 +7,14 @@ from pybullet_gym_b200.mjcf import compiler as mj
 def act(w, ob):
     ob=ob+w["obs_shift"]      # the Humanoid demos' `ob[0] += -1.4 + 0.8` (tools/extract_policy_weights.py)
     x=np.maximum(ob@w["dense1_w"]+w["dense1_b"],0); x=np.maximum(x@w["dense2_w"]+w["dense2_b"],0); return x@w["final_w"]+w["final_b"]
-def run(name, rules=None, scene_kw=None, eps=2, T=1000):
+def run(name, rules=None, scene_kw=None, eps=2, T=1000, **orc_kw):
     eid=name+"PyBulletEnv-v0"; w=np.load("tests/golden/policy_%s.npz"%name)
     spec=SPECS[eid]
     if scene_kw: spec=dataclasses.replace(spec, scene=dataclasses.replace(spec.scene, **scene_kw))
     bm=mj.parse_mjcf(spec.xml, rules) if rules else None
     out=[]
     for ep in range(eps):
-        e=OracleEnv(spec, seed=5, env_index=ep, bm=bm); ob=e.reset(); score=0; n=0
+        e=OracleEnv(spec, seed=5, env_index=ep, bm=bm, **orc_kw); ob=e.reset(); score=0; n=0
         for t in range(T):
             ob,r,d,_=e.step(act(w,ob)); score+=r; n+=1
             if d: break
@@ -60,3 +60,10 @@ for sc in ((0.25, 0.5, 2.0) if "torque" in sys.argv else ()):
 print("--- torsional friction rows")
 for kw in (dict(torsional_friction=True), dict(torsional_friction=True, warmstarting_factor=0.85)):
     print(kw, {n: run(n, None, kw, eps=3) for n in names}, flush=True)
+
+# persistent floor manifolds (oracle-only switch `ground_manifold`): one new point per collision pass,
+# up to four cached points per geom, instead of the instantaneous end-sphere candidates
+if "manifold" in sys.argv:
+    print("--- persistent floor manifolds")
+    for kw in (dict(), dict(ground_manifold=1)):
+        print(kw or "candidates (default)", {n: run(n, None, None, eps=4, **kw) for n in names_all}, flush=True)
