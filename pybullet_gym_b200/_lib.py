@@ -83,7 +83,12 @@ TASK_VIEW_FIELDS = ("potential", "walk_target_x", "walk_target_y", "flag_timeout
                     "episode_steps", "episode_return", "initial_z", "episode", "attacks", "flag_moves")
 
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+# -prec-div=false -prec-sqrt=false -ftz=true: single-precision divisions and square roots as reciprocal / rsqrt sequences
+# (2 ulp instead of the IEEE sequence with its slow-path call) and denormals flushed: Ant +4.3 %, Humanoid +6.1 % (A/B on one box,
+# profiles/r02_experiments.md); the parity suite runs against the oracle with these flags.  sinf / cosf / atan2f keep their
+# accurate versions (no -use_fast_math: __sinf of a 1e-3 rad half-angle would cost the quaternion integration 4 digits).
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-prec-div=false", "-prec-sqrt=false", "-ftz=true"]
 BUILD_DIR = os.path.join(CSRC, "_build")
 
 

@@ -849,15 +849,17 @@ struct Env {
         const int nf0max = wmax(nf0);
         for (int it = 0; it < niter; ++it) {
             for (int t = 0; t < nlmax; ++t) {
+                // A row index past this env's rows (its warp-mate has more of them) is neutralised OFF the dependent chain: the
+                // impulse change that comes back from the shuffle is some finite number of this env's own lanes, no lane
+                // takes it and its column of A is read as zeros -- bit-identical to zeroing the change itself
                 const bool on = t < nl;
                 const int i = on ? ((it & 1) ? t : nl - 1 - t) : 0;
                 const float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
-                float dl = shfl(cd, i);              // unconditional: both env groups of the warp take part
-                if (!on) dl = 0.f;
-                if (gl == i) lam0 += dl;
+                const float dl = shfl(cd, i);        // unconditional: both env groups of the warp take part
+                if (on && gl == i) lam0 += dl;
                 const float *arow = Ag + i * C::MAXRP;
-                r0 = fmaf(arow[0], dl, r0);
-                if (TWO) r1 = fmaf(arow[C::LPE], dl, r1);
+                r0 = fmaf(on ? arow[0] : 0.f, dl, r0);
+                if (TWO) r1 = fmaf(on ? arow[C::LPE] : 0.f, dl, r1);
             }
             {
                 const float *arow = Ag + nl * C::MAXRP;
@@ -865,27 +867,25 @@ struct Env {
                 for (int j = 0; j < ncmax; ++j) {
                     const bool on = j < nc;
                     const float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
-                    float dl = shfl(cd, on ? nl + j : 0);
-                    if (!on) dl = 0.f;
-                    if (gl == nl + j) lam0 += dl;
+                    const float dl = shfl(cd, nl + j);                       // (the source lane is taken modulo LPE)
+                    if (on && gl == nl + j) lam0 += dl;
                     r0 = fmaf(on ? arow[0] : 0.f, dl, r0);                   // a row index past this env's rows may point at stale storage
                     if (TWO) r1 = fmaf(on ? arow[C::LPE] : 0.f, dl, r1);
                     arow += C::MAXRP;
                 }
             }
+            // friction bounds of the sweep; a row whose normal impulse is zero is skipped (C4.6): bounds that pin it to its
+            // current impulse make its change come out as exactly 0 without a select in the dependent chain
             const float ln0 = shfl(lam0, myn0);
-            if (fr0) { hi0 = mu0 * ln0; lo0 = -hi0; }
-            const bool skip0 = fr0 && !(ln0 > 0.f);
+            if (fr0) { hi0 = mu0 * ln0; lo0 = -hi0; if (!(ln0 > 0.f)) { hi0 = lam0; lo0 = lam0; } }
             {
                 const float *arow = Ag + (nl + nc) * C::MAXRP;
 #pragma unroll 2
                 for (int j = 0; j < nf0max; ++j) {
                     const bool on = j < nf0;
-                    float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
-                    if (skip0) cd = 0.f;
-                    float dl = shfl(cd, on ? nl + nc + j : 0);
-                    if (!on) dl = 0.f;
-                    if (gl == nl + nc + j) lam0 += dl;
+                    const float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
+                    const float dl = shfl(cd, nl + nc + j);
+                    if (on && gl == nl + nc + j) lam0 += dl;
                     r0 = fmaf(on ? arow[0] : 0.f, dl, r0);
                     if (TWO) r1 = fmaf(on ? arow[C::LPE] : 0.f, dl, r1);
                     arow += C::MAXRP;
@@ -893,13 +893,12 @@ struct Env {
             }
             if (TWO) {
                 const float ln1 = shfl(lam0, myn1);
-                const float hi1 = fr1 ? mu1 * ln1 : 0.f, lo1 = -hi1;
-                const bool skip1 = !(ln1 > 0.f);
+                float hi1 = fr1 ? mu1 * ln1 : 0.f, lo1 = -hi1;
+                if (!(ln1 > 0.f)) { hi1 = lam1; lo1 = lam1; }    // skipped row (a lane without a second row keeps lam1 = 0)
                 const float *arow = Ag + C::LPE * C::MAXRP;
 #pragma unroll 2
                 for (int t = C::LPE; t < nrmax; ++t) {
-                    float cd = fminf(fmaxf(lam1 + fmaf(-r1, dinv1, rhs1), lo1), hi1) - lam1;
-                    if (skip1) cd = 0.f;
+                    const float cd = fminf(fmaxf(lam1 + fmaf(-r1, dinv1, rhs1), lo1), hi1) - lam1;
                     const float dl = shfl(cd, t - C::LPE);       // 0 from a lane without a second row
                     if (gl == t - C::LPE) lam1 += dl;
                     r0 = fmaf(arow[0], dl, r0);
