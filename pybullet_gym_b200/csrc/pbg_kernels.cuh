@@ -844,6 +844,11 @@ struct Env {
         const float rhs0 = rhs[0], dinv0 = dinv[0], mu0 = mu[0], rhs1 = rhs[1], dinv1 = dinv[1], mu1 = mu[1];
         float lam0 = lmb[0], r0 = r[0], lam1 = lmb[1], r1 = r[1];
         float lo0 = lo[0], hi0 = hi[0];
+        // every lane evaluates its row's candidate change each step: clamp(lambda + rhs - r / A_ii) - lambda with c = lambda + rhs
+        // kept beside lambda (it changes only when the lane's own row is taken), one addition less in the serial chain
+        float c0 = lam0 + rhs0;       // (the second slot keeps the plain form: one more live register costs it more, -0.8 %)
+#define PBG_CD0 (fminf(fmaxf(fmaf(-r0, dinv0, c0), lo0), hi0) - lam0)
+#define PBG_TAKE0(cond) if (cond) { lam0 += dl; c0 = lam0 + rhs0; }
         const int nlmax = wmax(nl), ncmax = wmax(nc);
         const int nf0 = (nr < C::LPE ? nr : C::LPE) - nl - nc;               // friction rows of the first slot
         const int nf0max = wmax(nf0);
@@ -854,9 +859,9 @@ struct Env {
                 // takes it and its column of A is read as zeros -- bit-identical to zeroing the change itself
                 const bool on = t < nl;
                 const int i = on ? ((it & 1) ? t : nl - 1 - t) : 0;
-                const float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
+                const float cd = PBG_CD0;
                 const float dl = shfl(cd, i);        // unconditional: both env groups of the warp take part
-                if (on && gl == i) lam0 += dl;
+                PBG_TAKE0(on && gl == i)
                 const float *arow = Ag + i * C::MAXRP;
                 r0 = fmaf(on ? arow[0] : 0.f, dl, r0);
                 if (TWO) r1 = fmaf(on ? arow[C::LPE] : 0.f, dl, r1);
@@ -866,9 +871,9 @@ struct Env {
 #pragma unroll 2
                 for (int j = 0; j < ncmax; ++j) {
                     const bool on = j < nc;
-                    const float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
+                    const float cd = PBG_CD0;
                     const float dl = shfl(cd, nl + j);                       // (the source lane is taken modulo LPE)
-                    if (on && gl == nl + j) lam0 += dl;
+                    PBG_TAKE0(on && gl == nl + j)
                     r0 = fmaf(on ? arow[0] : 0.f, dl, r0);                   // a row index past this env's rows may point at stale storage
                     if (TWO) r1 = fmaf(on ? arow[C::LPE] : 0.f, dl, r1);
                     arow += C::MAXRP;
@@ -883,9 +888,9 @@ struct Env {
 #pragma unroll 2
                 for (int j = 0; j < nf0max; ++j) {
                     const bool on = j < nf0;
-                    const float cd = fminf(fmaxf(lam0 + fmaf(-r0, dinv0, rhs0), lo0), hi0) - lam0;
+                    const float cd = PBG_CD0;
                     const float dl = shfl(cd, nl + nc + j);
-                    if (on && gl == nl + nc + j) lam0 += dl;
+                    PBG_TAKE0(on && gl == nl + nc + j)
                     r0 = fmaf(on ? arow[0] : 0.f, dl, r0);
                     if (TWO) r1 = fmaf(on ? arow[C::LPE] : 0.f, dl, r1);
                     arow += C::MAXRP;
@@ -908,6 +913,8 @@ struct Env {
             }
         }
         lmb[0] = lam0; r[0] = r0; lmb[1] = lam1; r[1] = r1;
+#undef PBG_CD0
+#undef PBG_TAKE0
     }
 
     // ---------------------------------------------------------------- dynamics of one substep
@@ -1222,10 +1229,20 @@ struct Env {
             const V3 om = ld3(cube ? u + C::XD0 : u);
             float wn = sqrtf(dot(om, om));
             if (wn * h > 0.25f * CUDART_PI_F) wn = 0.5f * (0.5f * CUDART_PI_F) / h;
+#ifndef PBG_QTRIG
+            // sin(x) / wn = (h / 2) sinc(x) and cos(x) of the half angle x = wn h / 2 <= pi / 8 (the clamp above) as Taylor polynomials
+            // in x^2: truncation below 2e-10 relative, i.e. as accurate as sinf / cosf in fp32, without their range reduction, the
+            // division and btTransformUtil's small-angle branch (whose two-term series this reproduces for wn < 0.001)
+            const float xh = 0.5f * wn * h, x2 = xh * xh;
+            const float sc = 0.5f * h * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -0.16666667f), 1.f);
+            const float aw = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, -2.7557319e-7f, 2.4801587e-5f), -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.f);
+            const float ax = om.x * sc, ay = om.y * sc, az = om.z * sc;
+#else
             float sc;
             if (wn < 0.001f) sc = 0.5f * h - h * h * h * 0.020833333333f * wn * wn;
             else sc = sinf(0.5f * wn * h) / wn;
             const float ax = om.x * sc, ay = om.y * sc, az = om.z * sc, aw = cosf(0.5f * wn * h);
+#endif
             const float bx = Q[0], by = Q[1], bz = Q[2], bw = Q[3];
             float qx = aw * bx + ax * bw + ay * bz - az * by;
             float qy = aw * by - ax * bz + ay * bw + az * bx;
