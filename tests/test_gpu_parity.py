@@ -396,8 +396,31 @@ def test_golden_reference_rollouts_whole_episodes(env_id, oracle_lib):
     unpredictable there).  A step that exceeds its bound is tolerated once per fixture, and ends its episode's window, only if that
     very step is exact from the CUDA path's own pre-step state (T2's per-sample bound): a discrete event hit 2e-5 off the oracle's
     trajectory.  done flags must agree wherever the bound is below 1e-3."""
-    import json, os
-    path = os.path.join(os.path.dirname(__file__), "golden", "task_%s.json" % env_id.split("PyBullet")[0])
+    import os
+    _replay_golden(env_id, os.path.join(os.path.dirname(__file__), "golden", "task_%s.json" % env_id.split("PyBullet")[0]), oracle_lib)
+
+
+# (task_HumanoidFlagrunPolicy.json is replayed by the oracle only, tests/test_golden_task.py: its flag positions are the reference's
+# np_random draws, which the oracle takes from the fixture's tape and the kernel draws from its own counter RNG)
+POLICY_IDS = {"HopperPyBulletEnv-v0": 30, "HalfCheetahPyBulletEnv-v0": 15, "AntPyBulletEnv-v0": 10, "HumanoidPyBulletEnv-v0": 5}
+
+
+@pytest.mark.parametrize("env_id", list(POLICY_IDS))
+def test_golden_policy_rollouts(env_id, oracle_lib):
+    """The same free-running replay on the policy-driven fixtures (task_*Policy.json: the reference's Python task layer stepped
+    with the reference's own pretrained MLP, i.e. walking gaits with feet touching down and lifting instead of random flailing).
+    These episodes are 100-300 steps long, far beyond the horizon over which ANY two integrations of a walking robot stay
+    comparable: three oracle twins 1e-7 apart at the reset are 4e-5 apart (bound 2e-2) after 41 Hopper, 22 HalfCheetah, 15 Ant and 7
+    Humanoid steps, and that is where the comparison has to end.  Inside the window the bar is the same per-step bound (observed
+    worst err / bound 0.16, 0.04, 0.008, 0.006); the minimum window lengths below guard against the window collapsing.  The whole
+    fixtures are replayed bit for bit by the oracle and checked against the reference's numbers in tests/test_golden_task.py."""
+    import os
+    _replay_golden(env_id, os.path.join(os.path.dirname(__file__), "golden", "task_%sPolicy.json" % env_id.split("PyBullet")[0]),
+                   oracle_lib, min_frac=0.0, min_steps=POLICY_IDS[env_id])
+
+
+def _replay_golden(env_id, path, oracle_lib, min_frac=0.25, min_steps=0):
+    import json
     g = json.load(open(path))
     env, chk = _mk(env_id, n=1), _mk(env_id, n=1)
     chk.reset()
@@ -456,5 +479,5 @@ def test_golden_reference_rollouts_whole_episodes(env_id, oracle_lib):
     print("\n  [golden %s] %d steps, worst err / bound %.3f" % (env_id, nsteps, worst_ratio))
     total = sum(len(ep["steps"]) for ep in g["episodes"])
     print("  [golden %s] compared %d of %d recorded steps" % (env_id, nsteps, total))
-    assert nsteps >= 0.25 * total        # a good part of every fixture lies inside the comparable window
+    assert nsteps >= min_frac * total and nsteps >= min_steps      # a good part of every fixture lies inside the comparable window
     assert events <= 1                   # at most one episode of a fixture may end on such an event

@@ -51,7 +51,23 @@ CASES = {
     # small scripted drift, so that the humanoid is still standing at frame 120 / 150 / ... and the reference's
     # cube attack (rs/robot_locomotors.py:251-266) fires; the cube itself keeps flying / colliding freely
     "HumanoidFlagrunHarderPyBulletEnv-v0#held": ("gym_locomotion_envs", "HumanoidFlagrunHarderBulletEnv", 1, 230, 0.2),
+    # "#policy": the actions come from the reference's own pretrained MLP for that env (tests/golden/policy_*.npz, extracted from
+    # its enjoy_TF_* scripts) evaluated on the reference's observation: long walking episodes -- feet touching down and lifting,
+    # joints at their stops, progress, a moving flag -- instead of a few dozen random-action steps before the robot falls
+    "HopperPyBulletEnv-v0#policy": ("gym_locomotion_envs", "HopperBulletEnv", 1, 300, 1.0),
+    "HalfCheetahPyBulletEnv-v0#policy": ("gym_locomotion_envs", "HalfCheetahBulletEnv", 1, 250, 1.0),
+    "AntPyBulletEnv-v0#policy": ("gym_locomotion_envs", "AntBulletEnv", 1, 250, 1.0),
+    "HumanoidPyBulletEnv-v0#policy": ("gym_locomotion_envs", "HumanoidBulletEnv", 1, 200, 1.0),
+    "HumanoidFlagrunPyBulletEnv-v0#policy": ("gym_locomotion_envs", "HumanoidFlagrunBulletEnv", 1, 320, 1.0),
 }
+
+
+def policy_action(w, ob):
+    """The demo scripts' forward pass (enjoy_TF_*: two ReLU layers, linear head; the Humanoid demos shift ob[0] first)."""
+    ob = np.asarray(ob, dtype=np.float64) + w["obs_shift"]
+    x = np.maximum(ob @ w["dense1_w"] + w["dense1_b"], 0)
+    x = np.maximum(x @ w["dense2_w"] + w["dense2_b"], 0)
+    return x @ w["final_w"] + w["final_b"]
 
 
 def main():
@@ -63,6 +79,7 @@ def main():
     for case_id, (mod, cls, episodes, max_steps, ascale) in CASES.items():
         env_id, _, variant = case_id.partition("#")
         held = variant == "held"
+        policy = np.load(os.path.join(OUT, "policy_%s.npz" % env_id.split("PyBullet")[0])) if variant == "policy" else None
         spec = SPECS[env_id]
         fp.FakeBulletClient.current_spec = spec
         fp.FakeBulletClient.max_contacts = 0
@@ -70,7 +87,13 @@ def main():
         import io
         import contextlib
         with contextlib.redirect_stdout(io.StringIO()):     # the reference prints "WalkerBase::__init__"
-            env = getattr(m, cls)()
+            if cls == "HumanoidBulletEnv" and variant:
+                # `def __init__(self, robot=Humanoid())` (rs/gym_locomotion_envs.py:147): the default robot is ONE object shared by
+                # every HumanoidBulletEnv of the process, already loaded into the first case's client -- a second env of this class
+                # gets its own robot through the constructor argument
+                env = getattr(m, cls)(robot=m.Humanoid())
+            else:
+                env = getattr(m, cls)()
         # gym.make() patches reset/step/seed to the most-derived _reset/_step/_seed
         # (gym.envs.registration.patch_deprecated_methods); call those directly
         env._seed(1234)
@@ -86,8 +109,11 @@ def main():
             noise, rec_tape = flat[:nN], None
             rec = {"noise": noise, "obs0": np.asarray(obs0, dtype=np.float64).tolist(), "steps": []}
             s_reset = env._p.orc.get_state().copy()
+            obs = obs0
             for t in range(max_steps):
                 a = (ascale * rng.uniform(-1, 1, nA)).astype(np.float64)   # |a| > 1 exercises quirk Q3
+                if policy is not None:
+                    a = np.asarray(policy_action(policy, obs), dtype=np.float64)
                 if held:
                     s_now = env._p.orc.get_state()
                     nrob = s_now.size - 13
@@ -116,13 +142,15 @@ def main():
                "episodes": eps}
         if held:
             out["held"] = True
+        if policy is not None:
+            out["policy"] = True
         # changeDynamics calls that switch torsional friction on, with the body they land on (HalfCheetahMuJoCoEnv's reset
         # addresses pybullet body `part.bodyIndex` = 0, the stadium floor: mujoco/robot_locomotors.py:207-210)
         tors = [[b, l, kind, kw] for b, l, kind, kw in getattr(env._p, "dynamics_calls", []) if "spinningFriction" in kw]
         if tors:
             out["torsional_change_dynamics"] = tors
         stem = env_id.split("PyBullet")[0] if "PyBullet" in env_id else env_id.split("Env-")[0]
-        path = os.path.join(OUT, "task_%s%s.json" % (stem, "Held" if held else ""))
+        path = os.path.join(OUT, "task_%s%s.json" % (stem, "Held" if held else ("Policy" if policy is not None else "")))
         with open(path, "w") as f:
             json.dump(out, f)
         nsteps = sum(len(e["steps"]) for e in eps)
