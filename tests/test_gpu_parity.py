@@ -280,6 +280,59 @@ def test_single_substep_and_step_parity_T2(env_id, oracle_lib):
         assert e4[fr].max() < 1e-4, e4[fr].max()
 
 
+GAIT_IDS = ["HopperPyBulletEnv-v0", "HalfCheetahPyBulletEnv-v0", "AntPyBulletEnv-v0", "HumanoidPyBulletEnv-v0", "HumanoidFlagrunPyBulletEnv-v0"]
+
+
+@pytest.mark.parametrize("env_id", GAIT_IDS)
+def test_single_step_parity_on_policy_gait_states_T2(env_id, oracle_lib):
+    """T2 on the states of a walking gait instead of random flailing: every state of the policy-driven golden episodes
+    (tests/golden/task_*Policy.json, the reference's pretrained MLP in the loop: stance / swing phases, feet touching down, joints
+    against their stops) is one env of a batch; ONE physics step of the kernel with the recorded action against the oracle from
+    the identical (float32-rounded) state, both with empty warm-start caches.  Same bars as T2: every sample within T2_K x the
+    oracle's own response to 1e-7 perturbations of that state (floor T2_FLOOR), median below 1e-4.  Unlike a free-running replay
+    this covers ALL steps of the episodes -- chaos cannot end the comparison."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "task_%sPolicy.json" % env_id.split("PyBullet")[0])))
+    ep = g["episodes"][0]
+    ref = oracle_lib.OracleEnv(env_id)                 # the fixture's oracle: no solver budget, replays the recorded trajectory
+    if ep.get("tape"):
+        ref.set_tape(ep["tape"])
+    ref.reset(noise=ep["noise"], floor_in_parts=False)
+    states, actions = [], []
+    for st in ep["steps"]:
+        states.append(ref.get_state().astype(np.float32))
+        actions.append(st["a"])
+        ref.step(st["a"])
+    S, A = np.stack(states), np.array(actions, np.float32)
+    n = len(S)
+    env = _mk(env_id, n=n)
+    env.reset()
+    env.set_state(torch.from_numpy(S))
+    env.physics_step(torch.from_numpy(A))
+    gk = env.get_state().cpu().numpy().astype(np.float64)
+    assert np.isfinite(gk).all()
+    o = _oracles(oracle_lib, env_id, 1)[0]             # the kernel's contact cap / row budget
+    rng = np.random.default_rng(11)
+    errs, bounds = [], []
+    for i in range(n):
+        si, ai = S[i].astype(np.float64), A[i].astype(np.float64)
+        o.reset(noise=np.zeros(env.noise_dim)); o.set_state(si); o.physics_step(ai)
+        r = o.get_state().copy()
+        err, sens, draws = _rel(gk[i], r).max(), 0.0, 0
+        # 4 perturbations per state; a state that misses its bound gets 16 more before it counts: a gait holds joints AT their stops
+        # (the Hopper's thigh sits at q = 0 within 1e-9 for dozens of steps), where a limit row switches on or off with the sign of a
+        # round-off and only about half of the 1e-7 draws land on the other side
+        while draws < 4 or (draws < 20 and err > max(T2_FLOOR, T2_K * sens)):
+            o.reset(noise=np.zeros(env.noise_dim)); o.set_state(si + rng.normal(size=si.shape) * 1e-7 * (1 + np.abs(si))); o.physics_step(ai)
+            sens = max(sens, _rel(o.get_state(), r).max())
+            draws += 1
+        errs.append(err); bounds.append(max(T2_FLOOR, T2_K * sens))
+    e, b = np.array(errs), np.array(bounds)
+    print("\n  [T2 gait %s] %d states: median %.1e max %.1e worst err/bound %.2f" % (env_id, n, np.median(e), e.max(), (e / b).max()))
+    assert np.median(e) < 1e-4, np.median(e)
+    assert (e <= b).all(), (int(np.argmax(e / b)), (e / b).max(), e.max())
+
+
 def test_oracle_sensitivity_reference(oracle_lib):
     """Documents the conditioning T2's per-sample bounds rest on: the double-precision oracle, perturbed
     by a float32-storage-sized 1e-7, moves by > 1e-5 after one Ant env step once contacts are active."""
