@@ -89,3 +89,19 @@ def test_halfcheetah_mujoco_torsional_friction_lands_on_the_floor():
     assert base and all(kw == {"lateralFriction": 0.8, "spinningFriction": 0.1, "rollingFriction": 0.1, "restitution": 0.5} for kw in base)
     sc = SPECS["HalfCheetahMuJoCoEnv-v0"].scene
     assert sc.torsional_friction and sc.ground_spinning_friction == 0.1 and sc.ground_rolling_friction == 0.1 and sc.ground_friction == 0.8
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pybulletgym"), reason="needs the reference checkout (build container only)")
+def test_golden_fixtures_regenerate_byte_identically_from_the_reference(tmp_path, oracle_lib):
+    """The committed fixtures ARE what the reference's unmodified Python computes: tools/gen_golden_task.py is run again
+    (reference modules imported from /root/reference on the stub client, oracle physics) into a scratch directory and every
+    task_*.json must come out byte for byte as committed."""
+    import subprocess, sys
+    root = os.path.join(os.path.dirname(__file__), "..")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_golden_task.py"), "--out", str(tmp_path)],
+                       capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    made = sorted(p.name for p in tmp_path.glob("task_*.json"))
+    assert made == [os.path.basename(p) for p in GOLDEN]
+    for name in made:
+        assert (tmp_path / name).read_bytes() == open(os.path.join(os.path.dirname(__file__), "golden", name), "rb").read(), name

@@ -13,7 +13,7 @@ tests/test_golden_task.py replays the same noise/actions through the C oracle (w
 the same code, so states agree bit for bit) and requires the oracle's task layer to reproduce the
 reference's numbers; this pins SURVEY.md Appendix A incl. quirks Q1-Q3, Q6, Q10 to reference source.
 
-Run in the build container only (needs /root/reference).  Usage: python tools/gen_golden_task.py
+Run in the build container only (needs /root/reference).  Usage: python tools/gen_golden_task.py [--out DIR]
 """
 import json
 import os
@@ -26,7 +26,9 @@ sys.path.insert(0, HERE)
 import fake_pybullet as fp  # noqa: E402
 
 REF = "/root/reference"
-OUT = os.path.join(HERE, "..", "tests", "golden")
+GOLDEN = os.path.join(HERE, "..", "tests", "golden")
+# `--out DIR` writes the fixtures somewhere else (tests/test_golden_task.py regenerates them into a scratch directory and compares bytes)
+OUT = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else GOLDEN
 
 CASES = {
     # env id -> (module, class, episodes, max steps per episode, action scale)
@@ -79,7 +81,7 @@ def main():
     for case_id, (mod, cls, episodes, max_steps, ascale) in CASES.items():
         env_id, _, variant = case_id.partition("#")
         held = variant == "held"
-        policy = np.load(os.path.join(OUT, "policy_%s.npz" % env_id.split("PyBullet")[0])) if variant == "policy" else None
+        policy = np.load(os.path.join(GOLDEN, "policy_%s.npz" % env_id.split("PyBullet")[0])) if variant == "policy" else None
         spec = SPECS[env_id]
         fp.FakeBulletClient.current_spec = spec
         fp.FakeBulletClient.max_contacts = 0
